@@ -1,0 +1,160 @@
+/*
+ * sphmw.h — C ABI of libsphmw.so, the B200-native WCSPH hot path behind the
+ * SmoothedParticles.jl API used by moschehaus/sph-mountain-waves.
+ *
+ * The reference has no FFI boundary of its own (it is 100 % Julia); the boundary
+ * it does have is its Julia API (src/SmoothedParticles.jl:14-79).  Every entry
+ * point below names the reference interface it replaces (file:line under
+ * /root/reference).  INTEGRATION.md shows the `ccall` shim a maintainer adds.
+ *
+ * Conventions
+ *   - plain C: opaque handle, pointers and sizes; no C++/torch types.
+ *   - every call returns 0 (SPHMW_OK) or a negative SPHMW_E_* code; the message
+ *     of the last failure on the calling thread is sphmw_last_error().
+ *   - host buffers are BORROWED for the duration of the call; device memory is
+ *     OWNED by the context.  Buffers passed to upload/download may also be device
+ *     pointers (UVA decides).
+ *   - particle fields cross the ABI as structure-of-arrays, component-major:
+ *     buf[c*n + i] is component c of particle i, i in the reference's particle
+ *     index order (`sys.particles[i+1]`).
+ *   - a context is driven by one host thread at a time (the reference's caller is
+ *     single-threaded, core.jl:125-142 fans out internally).
+ *   - all work is enqueued on the context's stream; only download, reduce,
+ *     create_cell_list(n_alive != NULL), pairs/keys dumps and sync block.
+ *   - there is NO CPU fallback: without a CUDA device sphmw_create fails.
+ */
+#ifndef SPHMW_H
+#define SPHMW_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHMW_OK 0
+#define SPHMW_E_INVALID (-1)        /* bad argument (AssertionError in the reference) */
+#define SPHMW_E_CUDA (-2)           /* CUDA runtime failure */
+#define SPHMW_E_UNSUPPORTED_OP (-3) /* operator not in the menu: no CPU fallback */
+#define SPHMW_E_UNKNOWN_FIELD (-4)
+#define SPHMW_E_CAPACITY (-5)
+#define SPHMW_E_STATE (-6)          /* e.g. binary op before create_cell_list */
+#define SPHMW_E_IO (-7)
+
+typedef struct sphmw_ctx sphmw_ctx;
+
+/* ≙ ParticleSystem(T, domain, h) — src/structs.jl:57-91.  `box_*` is
+ * boundarybox(domain) (structs.jl:63-65); 2D is detected exactly like the
+ * reference: key_lim[3] == 1 (structs.jl:70).
+ * Slab fields (multi-GPU, no reference equivalent): this context owns the global
+ * cell columns [slab_lo, slab_hi) along x and keeps one ghost column each side;
+ * slab_lo = slab_hi = -1 means "whole domain". */
+typedef struct sphmw_config {
+    double box_min[3];
+    double box_max[3];
+    double h;
+    int64_t capacity; /* max particles resident (owned + ghosts) */
+    int32_t device;   /* CUDA ordinal */
+    int32_t flags;    /* SPHMW_FLAG_* */
+    int64_t slab_lo;
+    int64_t slab_hi;
+} sphmw_config;
+
+#define SPHMW_FLAG_NONE 0
+
+int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out);
+int sphmw_destroy(sphmw_ctx *ctx);
+const char *sphmw_last_error(void);
+const char *sphmw_version(void);
+
+/* Use the caller's CUDA stream (cudaStream_t as void*); NULL = context's own. */
+int sphmw_set_stream(sphmw_ctx *ctx, void *cuda_stream);
+int sphmw_sync(sphmw_ctx *ctx);
+
+/* Driver constants, ≙ the module-level `const`s of a driver
+ * (src/current/wcsph_perturbed_witch.jl:25-75; collapse_dry.jl:30-66).
+ * Names: dt g c gamma alpha beta eps eta rho0 R_mass R_gas T_bg rho_floor P_floor
+ * z_t z_b gamma_r fluid m nu mu gx gy gz kh dt_pack c_pack zeta_pack */
+int sphmw_set_param(sphmw_ctx *ctx, const char *name, double value);
+int sphmw_get_param(sphmw_ctx *ctx, const char *name, double *value);
+
+/* key tables of the system — src/structs.jl:66-68 */
+int sphmw_key_tables(sphmw_ctx *ctx, int64_t phase[3], int64_t lim[3], int64_t *key_max,
+                     int32_t *dim);
+
+/* ≙ push!(sys.particles, ...) / length(sys.particles) — src/grids.jl:305-310.
+ * Sets the particle count; new particles have all fields zero. */
+int sphmw_resize(sphmw_ctx *ctx, int64_t n);
+int sphmw_count(sphmw_ctx *ctx, int64_t *n);
+
+/* ≙ ParticleField(sys, :name) get/set — src/structs.jl:118-125.
+ * Field names (ASCII | Julia): h x m v Dv rho_bg|ρ_bg rho_p|ρ′ rho|ρ P_bg P_p|P′ P
+ * theta_bg|θ_bg theta_p|θ′ theta|θ T_bg T_p|T′ T type A A_bg Drho rho0 a(=Dv) u(=v).
+ * ncomp must be 1 (scalars) or 3 (RealVector).  n must equal the particle count. */
+int sphmw_upload(sphmw_ctx *ctx, const char *field, const double *buf, int64_t n, int32_t ncomp);
+int sphmw_download(sphmw_ctx *ctx, const char *field, double *buf, int64_t n, int32_t ncomp);
+
+/* ≙ create_cell_list!(sys) — src/core.jl:51-90: removal of out-of-box particles
+ * with the reference's swap-from-end renumbering, cell keys (structs.jl:97-106),
+ * sort by (cell, index descending), cell-start table.  n_alive may be NULL
+ * (then the call does not block). */
+int sphmw_create_cell_list(sphmw_ctx *ctx, int64_t *n_alive);
+
+/* ≙ apply!(sys, f; self) / apply_unary! / apply_binary! — src/core.jl:125-161.
+ * `op` is "<scheme>.<closure>" from the fixed menu (sphmw_op_list), e.g.
+ * "wcsph.compute_density" ≙ wcsph_perturbed_witch.jl:226-228.  A closure that is
+ * not in the menu is SPHMW_E_UNSUPPORTED_OP.  Arity (unary/binary) is a
+ * property of the operator, as `hasmethod` decides in core.jl:153. */
+int sphmw_apply(sphmw_ctx *ctx, const char *op, int32_t self);
+/* newline-separated operator names; returns the length needed */
+int64_t sphmw_op_list(char *buf, int64_t cap);
+
+/* Fused fast path ≙ `for k in 1:nsteps verlet_step!(sys) end`
+ * (wcsph_perturbed_witch.jl:309-332, :371-373).  scheme: "wcsph" | "hopkins" |
+ * "hopkins_total" | "dambreak" | "collision".  Must leave the same state as the
+ * operator-by-operator sequence. */
+int sphmw_step(sphmw_ctx *ctx, const char *scheme, int32_t nsteps);
+
+/* Test hooks for bit-exact cell assignment / neighbour-pair parity. */
+/* 0-based cell key of every particle, reference index order (structs.jl:97-106) */
+int sphmw_cell_keys(sphmw_ctx *ctx, int64_t *keys, int64_t n);
+/* particle indices stored in one cell, in stored order (core.jl:26-41) */
+int sphmw_cell_entries(sphmw_ctx *ctx, int64_t key, int64_t *out, int64_t cap, int64_t *n);
+/* accepted pairs (r <= h, p != q) in the reference's traversal order
+ * (core.jl:94-112); fills at most cap, *n = total */
+int sphmw_pairs_dump(sphmw_ctx *ctx, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n);
+/* accepted pairs of the last binary pass (needs sphmw_count_pairs(ctx,1)) */
+int sphmw_count_pairs(sphmw_ctx *ctx, int32_t enable);
+int sphmw_pair_count(sphmw_ctx *ctx, int64_t *n);
+
+/* ≙ avg_velocity / max_velocity / length(sys.particles)
+ * (wcsph_perturbed_witch.jl:338-350,377).  what: "avg_speed" | "max_speed" |
+ * "count" | "sum:<field>" | "max:<field>" */
+int sphmw_reduce(sphmw_ctx *ctx, const char *what, double *out);
+
+/* ≙ the exported smoothing kernels, evaluated on the device — src/kernels.jl.
+ * name: wendland1|2|3, Dwendland1|2|3, rDwendland1|2|3, DDwendland3,
+ * spline23|24, Dspline23|24, rDspline23|24.  h, r, out: n doubles (host). */
+int sphmw_kernel_eval(const char *name, const double *h, const double *r, double *out,
+                      int64_t n, int32_t device);
+
+/* ≙ new_pvd_file / save_frame! / save_pvd_file — src/IO.jl:20-75.  Frames are
+ * written as VTK PolyData (.vtp, appended raw, one Verts cell per particle) plus
+ * a .pvd collection whose timestep values are the frame counter (IO.jl:73). */
+int sphmw_pvd_open(sphmw_ctx *ctx, const char *dir);
+int sphmw_pvd_save_frame(sphmw_ctx *ctx, const char *const *fields, int32_t nfields);
+int sphmw_pvd_close(sphmw_ctx *ctx);
+
+/* Per-kernel device timings accumulated since the last reset (CUDA events on the
+ * context's stream).  names: newline-separated, ms/calls: one entry per name. */
+int sphmw_timing_enable(sphmw_ctx *ctx, int32_t enable);
+int sphmw_timing_reset(sphmw_ctx *ctx);
+int64_t sphmw_timing_report(sphmw_ctx *ctx, char *names, int64_t cap, double *ms,
+                            int64_t *calls, int32_t max_entries);
+/* number of kernels this library launched on ctx since creation */
+int sphmw_launch_count(sphmw_ctx *ctx, int64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHMW_H */

@@ -1,0 +1,1233 @@
+// Particle operators on the device — replaces apply!/apply_unary!/apply_binary!
+// (src/core.jl:94-161) and the driver closures they are called with
+// (src/current/wcsph_perturbed_witch.jl:195-303, src/current/hopkins_*.jl,
+// sph_jl/examples/collapse_dry.jl:112-159, sph_jl/tests/test_collision_2d.jl:66-97,
+// src/utils/new_packing.jl:5-60).
+//
+// Closures cannot cross a C ABI (and the north star forbids JIT), so the menu of
+// operators below is fixed; each one restates one reference closure as a device
+// functor and is applied by the same two generic kernels.
+//
+// Arithmetic: this file is compiled with -fmad=false.  Every product/sum below is
+// written in the reference's evaluation order (Julia's n-ary * and + fold left),
+// so the FP64 sums are bit-identical to an IEEE evaluation of the reference
+// wherever no transcendental (exp, pow, cbrt) is involved.
+#include <math.h>
+#include <string.h>
+
+#include <string>
+
+#include "kernels_sph.cuh"
+#include "sphmw_internal.h"
+
+// Julia's max(a,b) propagates NaN (Base.max); fmax does not.
+__device__ __forceinline__ double jl_max(double a, double b) {
+    if (a != a || b != b) return a + b;
+    return a < b ? b : a;
+}
+
+// wcsph_perturbed_witch.jl:177-189
+__device__ __forceinline__ double background_density(const Params &c, double y) {
+    return c.rho0 * exp(-y * c.g / (c.R_mass * c.T_bg));
+}
+__device__ __forceinline__ double background_pressure(const Params &c, double y) {
+    double rho_bg = background_density(c, y);
+    return c.R_mass * c.T_bg * rho_bg;
+}
+__device__ __forceinline__ double background_pot_temperature(const Params &c, double y) {
+    double P_bg = background_pressure(c, y);
+    return c.T_bg * pow((c.T_bg * c.R_gas * c.rho0) / P_bg, 2.0 / 7.0);
+}
+
+// ===========================================================================
+// Unary operators: struct with static void apply<DIM>(Fields&, Params&, pos)
+// ===========================================================================
+#define FLD(slot) f.s[slot][p]
+
+// accelerate!  wcsph_perturbed_witch.jl:298-303 (+ buyoancy_force :253-256,
+// damping_structure :245-251).  Vector arithmetic per component, as StaticArrays
+// does: ((-g*e_a)*rho')/rho, e = VECY.
+template <bool HAS_DV>
+struct U_wcsph_accelerate {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        if (FLD(S_TYPE) == c.fluid) {
+            const double rho_p = FLD(S_RHO_P), rho = FLD(S_RHO);
+            const bool sponge = FLD(S_X1) >= c.sponge_z0;
+            const double hdt = 0.5 * c.dt;
+            {
+                double dv = HAS_DV ? FLD(S_DV0) : 0.0;
+                double buoy = -c.g * 0.0 * rho_p / rho;
+                double damp = sponge ? c.sponge_y * 0.0 : 0.0;
+                FLD(S_V0) += hdt * (dv + buoy + damp);
+            }
+            {
+                double dv = HAS_DV ? FLD(S_DV1) : 0.0;
+                double buoy = -c.g * 1.0 * rho_p / rho;
+                double damp = sponge ? c.sponge_y * 1.0 : 0.0;
+                FLD(S_V1) += hdt * (dv + buoy + damp);
+            }
+            if (DIM == 3) {
+                double dv = HAS_DV ? FLD(S_DV2) : 0.0;
+                double buoy = -c.g * 0.0 * rho_p / rho;
+                double damp = sponge ? c.sponge_y * 0.0 : 0.0;
+                FLD(S_V2) += hdt * (dv + buoy + damp);
+            }
+        }
+        if (HAS_DV) {
+            FLD(S_DV0) = 0.0;
+            FLD(S_DV1) = 0.0;
+            if (DIM == 3) FLD(S_DV2) = 0.0;
+        }
+    }
+};
+// move!  :292-296
+struct U_wcsph_move {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        if (FLD(S_TYPE) == c.fluid) {
+            FLD(S_X0) += c.dt * FLD(S_V0);
+            FLD(S_X1) += c.dt * FLD(S_V1);
+            if (DIM == 3) FLD(S_X2) += c.dt * FLD(S_V2);
+        }
+    }
+};
+// reset_density!  :220-223
+struct U_wcsph_reset_density {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &, int64_t p) {
+        FLD(S_RHO) = 0.0;
+        FLD(S_RHO_P) = 0.0;
+    }
+};
+// finalize_density!  :230-233
+struct U_wcsph_finalize_density {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        double rbg = background_density(c, FLD(S_X1));
+        FLD(S_RHO_BG) = rbg;
+        FLD(S_RHO_P) = FLD(S_RHO) - rbg;
+    }
+};
+// update_smoothing!  :235-238  (3D extrusion: cube root)
+struct U_wcsph_update_smoothing {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        double rho = jl_max(FLD(S_RHO), c.rho_floor);
+        FLD(S_H) = DIM == 2 ? c.eta * sqrt(FLD(S_M) / rho) : c.eta * cbrt(FLD(S_M) / rho);
+    }
+};
+// compute_pressure!  :195-199
+struct U_wcsph_compute_pressure {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        double pbg = background_pressure(c, FLD(S_X1));
+        double pp = sph_pow2(c.c) * FLD(S_RHO_P);
+        FLD(S_P_BG) = pbg;
+        FLD(S_P_P) = pp;
+        FLD(S_P) = pbg + pp;
+    }
+};
+// find_temperature!  :205-208
+struct U_wcsph_find_temperature {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        double T = FLD(S_P) / (c.R_mass * FLD(S_RHO));
+        FLD(S_T) = T;
+        FLD(S_T_P) = T - FLD(S_T_BG);
+    }
+};
+// find_pot_temp!  :210-214
+struct U_wcsph_find_pot_temp {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        double th = FLD(S_T) * pow((c.T_bg * c.R_gas * c.rho0) / FLD(S_P), 2.0 / 7.0);
+        double thbg = background_pot_temperature(c, FLD(S_X1));
+        FLD(S_TH) = th;
+        FLD(S_TH_BG) = thbg;
+        FLD(S_TH_P) = th - thbg;
+    }
+};
+
+// hopkins_perturbed_witch.jl:200-203
+struct U_hopkins_reset_pressure {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &, int64_t p) {
+        FLD(S_P) = 0.0;
+        FLD(S_P_P) = 0.0;
+    }
+};
+// hopkins_perturbed_witch.jl:210-214
+struct U_hopkins_finalize_pressure {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        double P = pow(FLD(S_P), c.gamma);
+        double pbg = background_pressure(c, FLD(S_X1));
+        FLD(S_P) = P;
+        FLD(S_P_BG) = pbg;
+        FLD(S_P_P) = P - pbg;
+    }
+};
+// hopkins_total_witch.jl:170-172
+struct U_ht_reset_pressure {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &, int64_t p) { FLD(S_P) = 0.0; }
+};
+// hopkins_total_witch.jl:179-181
+struct U_ht_finalize_pressure {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        FLD(S_P) = pow(FLD(S_P), c.gamma);
+    }
+};
+// hopkins_total_witch.jl:187-189
+struct U_ht_find_temperature {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        FLD(S_T) = FLD(S_P) / (c.R_mass * FLD(S_RHO));
+    }
+};
+// hopkins_total_witch.jl:191-193
+struct U_ht_find_pot_temp {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        FLD(S_TH) = FLD(S_T) * pow((c.T_bg * c.R_gas * c.rho0) / FLD(S_P), 2.0 / 7.0);
+    }
+};
+// hopkins_total_witch.jl:203-205
+struct U_ht_reset_density {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &, int64_t p) { FLD(S_RHO) = 0.0; }
+};
+// hopkins_total_witch.jl:270-272 — not type-gated
+struct U_ht_move {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        FLD(S_X0) += c.dt * FLD(S_V0);
+        FLD(S_X1) += c.dt * FLD(S_V1);
+        if (DIM == 3) FLD(S_X2) += c.dt * FLD(S_V2);
+    }
+};
+// hopkins_total_witch.jl:274-277, gravity :225-228
+struct U_ht_accelerate {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        const bool sponge = FLD(S_X1) >= c.sponge_z0;
+        const double hdt = 0.5 * c.dt;
+        FLD(S_V0) += hdt * (FLD(S_DV0) + -c.g * 0.0 + (sponge ? c.sponge_y * 0.0 : 0.0));
+        FLD(S_V1) += hdt * (FLD(S_DV1) + -c.g * 1.0 + (sponge ? c.sponge_y * 1.0 : 0.0));
+        if (DIM == 3)
+            FLD(S_V2) += hdt * (FLD(S_DV2) + -c.g * 0.0 + (sponge ? c.sponge_y * 0.0 : 0.0));
+        FLD(S_DV0) = 0.0;
+        FLD(S_DV1) = 0.0;
+        if (DIM == 3) FLD(S_DV2) = 0.0;
+    }
+};
+
+// collapse_dry.jl:123-127
+struct U_dam_find_pressure {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        double rho = FLD(S_RHO) + FLD(S_DRHO) * c.dt;
+        FLD(S_RHO) = rho;
+        FLD(S_DRHO) = 0.0;
+        FLD(S_P) = sph_pow2(c.c) * (rho - c.rho0);
+    }
+};
+// collapse_dry.jl:148-153
+struct U_dam_move {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        FLD(S_DV0) = 0.0;
+        FLD(S_DV1) = 0.0;
+        if (DIM == 3) FLD(S_DV2) = 0.0;
+        if (FLD(S_TYPE) == c.fluid) {
+            FLD(S_X0) += 0.5 * c.dt * FLD(S_V0);
+            FLD(S_X1) += 0.5 * c.dt * FLD(S_V1);
+            if (DIM == 3) FLD(S_X2) += 0.5 * c.dt * FLD(S_V2);
+        }
+    }
+};
+// collapse_dry.jl:155-159
+struct U_dam_accelerate {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        if (FLD(S_TYPE) == c.fluid) {
+            FLD(S_V0) += 0.5 * c.dt * (FLD(S_DV0) + c.gx);
+            FLD(S_V1) += 0.5 * c.dt * (FLD(S_DV1) + c.gy);
+            if (DIM == 3) FLD(S_V2) += 0.5 * c.dt * (FLD(S_DV2) + c.gz);
+        }
+    }
+};
+// test_collision_2d.jl:74-76
+struct U_col_find_pressure {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        FLD(S_P) = sph_pow2(c.c) * (FLD(S_RHO) - FLD(S_RHO0));
+    }
+};
+// test_collision_2d.jl:83-85
+struct U_col_reset_a {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &, int64_t p) {
+        FLD(S_DV0) = 0.0;
+        FLD(S_DV1) = 0.0;
+        if (DIM == 3) FLD(S_DV2) = 0.0;
+    }
+};
+// test_collision_2d.jl:87-89
+struct U_col_reset_rho {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &, int64_t p) { FLD(S_RHO) = 0.0; }
+};
+// test_collision_2d.jl:91-93
+struct U_col_move {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        FLD(S_X0) += c.dt * FLD(S_V0);
+        FLD(S_X1) += c.dt * FLD(S_V1);
+        if (DIM == 3) FLD(S_X2) += c.dt * FLD(S_V2);
+    }
+};
+// test_collision_2d.jl:95-97
+struct U_col_accelerate {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        FLD(S_V0) += 0.5 * c.dt * FLD(S_DV0);
+        FLD(S_V1) += 0.5 * c.dt * FLD(S_DV1);
+        if (DIM == 3) FLD(S_V2) += 0.5 * c.dt * FLD(S_DV2);
+    }
+};
+// new_packing.jl:5-9
+struct U_pack_reset_rho {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        if (FLD(S_TYPE) == c.fluid) FLD(S_RHO) = 0.0;
+    }
+};
+// new_packing.jl:49-57
+struct U_pack_accelerate {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        if (FLD(S_TYPE) == c.fluid) {
+            double den = 1.0 + c.zeta_pack * c.dt_pack;
+            FLD(S_V0) = (FLD(S_V0) + c.dt_pack * FLD(S_DV0)) / den;
+            FLD(S_V1) = (FLD(S_V1) + c.dt_pack * FLD(S_DV1)) / den;
+            if (DIM == 3) FLD(S_V2) = (FLD(S_V2) + c.dt_pack * FLD(S_DV2)) / den;
+        }
+        FLD(S_DV0) = 0.0;
+        FLD(S_DV1) = 0.0;
+        if (DIM == 3) FLD(S_DV2) = 0.0;
+    }
+};
+// new_packing.jl:59-63
+struct U_pack_move {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        if (FLD(S_TYPE) == c.fluid) {
+            FLD(S_X0) += c.dt_pack * FLD(S_V0);
+            FLD(S_X1) += c.dt_pack * FLD(S_V1);
+            if (DIM == 3) FLD(S_X2) += c.dt_pack * FLD(S_V2);
+        }
+    }
+};
+#undef FLD
+
+template <int DIM, class Op>
+__global__ void __launch_bounds__(256) k_unary(Fields f, Params c, int64_t n) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p < n) Op::template apply<DIM>(f, c, p);
+}
+
+// ===========================================================================
+// Binary operators.  A functor keeps the fields of p it reads/writes in
+// registers: init() loads them, pair() is the closure body for one accepted
+// neighbour q, finish() stores what the closure wrote to p.
+// ===========================================================================
+#define PF(slot) f.s[slot][p]
+#define QF(slot) f.s[slot][q]
+
+// compute_density!  wcsph_perturbed_witch.jl:226-228
+struct B_wcsph_density {
+    double rho, hp;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &, int64_t p) {
+        rho = PF(S_RHO);
+        hp = PF(S_H);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &, int64_t, int64_t q, double, double,
+                         double, double r) {
+        rho += QF(S_M) * sph_W<DIM>(hp, r);
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_RHO) = rho;
+    }
+};
+
+// shared body of balance_of_momentum!  wcsph_perturbed_witch.jl:261-286
+struct MomentumState {
+    double dv0, dv1, dv2;
+    double v0, v1, v2, hp, rho, prho, Pp, P;
+};
+
+struct B_wcsph_momentum {
+    MomentumState s;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &c, int64_t p) {
+        s.dv0 = PF(S_DV0);
+        s.dv1 = PF(S_DV1);
+        s.dv2 = DIM == 3 ? PF(S_DV2) : 0.0;
+        s.v0 = PF(S_V0);
+        s.v1 = PF(S_V1);
+        s.v2 = DIM == 3 ? PF(S_V2) : 0.0;
+        s.hp = PF(S_H);
+        s.rho = PF(S_RHO);
+        s.prho = jl_max(s.rho, c.rho_floor);
+        s.Pp = PF(S_P_P);
+        s.P = PF(S_P);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        double vx = s.v0 - QF(S_V0), vy = s.v1 - QF(S_V1);
+        double dot_product = dx * vx + dy * vy;
+        if (DIM == 3) {
+            double vz = s.v2 - QF(S_V2);
+            dot_product = dot_product + dz * vz;
+        }
+        double h_ij = 0.5 * (s.hp + QF(S_H));
+        double ker = sph_rDW<DIM>(h_ij, r);
+        double qrho = jl_max(QF(S_RHO), c.rho_floor);
+        double qm = QF(S_M);
+        // -q.m * (p.P'/prho^2 + q.P'/qrho^2) * ker * x_pq  (left fold, vector last)
+        double fc = -qm * (s.Pp / sph_pow2(s.prho) + QF(S_P_P) / sph_pow2(qrho)) * ker;
+        s.dv0 += fc * dx;
+        s.dv1 += fc * dy;
+        if (DIM == 3) s.dv2 += fc * dz;
+        if (dot_product < 0.0) {
+            double c_i = sqrt(c.gamma * s.P / s.prho);
+            double c_j = sqrt(c.gamma * QF(S_P) / qrho);
+            double c_ij = 0.5 * (c_i + c_j);
+            double rho_ij = 0.5 * (s.prho + qrho);
+            double mu_ij = (h_ij * dot_product) / (r * r + c.eps * h_ij * h_ij);
+            double pi_ij = (-c.alpha * c_ij * mu_ij + c.beta * mu_ij * mu_ij) / rho_ij;
+            double fv = -qm * pi_ij * ker;
+            s.dv0 += fv * dx;
+            s.dv1 += fv * dy;
+            if (DIM == 3) s.dv2 += fv * dz;
+        }
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_DV0) = s.dv0;
+        PF(S_DV1) = s.dv1;
+        if (DIM == 3) PF(S_DV2) = s.dv2;
+    }
+};
+
+// compute_pressure! (binary)  hopkins_perturbed_witch.jl:205-208
+struct B_hopkins_pressure {
+    double P, hp;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &, int64_t p) {
+        P = PF(S_P);
+        hp = PF(S_H);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double, double,
+                         double, double r) {
+        double ker = sph_W<DIM>(0.5 * (hp + QF(S_H)), r);
+        P += QF(S_M) * pow(QF(S_A), 1 / c.gamma) * ker;
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_P) = P;
+    }
+};
+
+// balance_of_momentum!  hopkins_total_witch.jl:233-264
+struct B_ht_momentum {
+    MomentumState s;
+    double A;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &c, int64_t p) {
+        s.dv0 = PF(S_DV0);
+        s.dv1 = PF(S_DV1);
+        s.dv2 = DIM == 3 ? PF(S_DV2) : 0.0;
+        s.v0 = PF(S_V0);
+        s.v1 = PF(S_V1);
+        s.v2 = DIM == 3 ? PF(S_V2) : 0.0;
+        s.hp = PF(S_H);
+        s.rho = PF(S_RHO);
+        s.prho = jl_max(s.rho, c.rho_floor);
+        s.P = PF(S_P);
+        A = PF(S_A);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        double vx = s.v0 - QF(S_V0), vy = s.v1 - QF(S_V1);
+        double dot_product = dx * vx + dy * vy;
+        if (DIM == 3) {
+            double vz = s.v2 - QF(S_V2);
+            dot_product = dot_product + dz * vz;
+        }
+        double qm = QF(S_M), qh = QF(S_H), qPraw = QF(S_P);
+        double prefac = qm * pow(A * QF(S_A), 1 / c.gamma);
+        double expfac = 1.0 - 2.0 / c.gamma;
+        double ker_i = sph_rDW<DIM>(s.hp, r);
+        double ker_j = sph_rDW<DIM>(qh, r);
+        double pP = jl_max(c.P_floor, s.P);
+        double qP = jl_max(c.P_floor, qPraw);
+        double fc = -prefac * (pow(pP, expfac) * ker_i + pow(qP, expfac) * ker_j);
+        s.dv0 += fc * dx;
+        s.dv1 += fc * dy;
+        if (DIM == 3) s.dv2 += fc * dz;
+        if (dot_product < 0.0) {
+            double h_ij = 0.5 * (s.hp + qh);
+            double ker_ij = sph_rDW<DIM>(h_ij, r);
+            double qrho = jl_max(QF(S_RHO), c.rho_floor);
+            double c_i = sqrt(c.gamma * s.P / s.prho);
+            double c_j = sqrt(c.gamma * qPraw / qrho);
+            double c_ij = 0.5 * (c_i + c_j);
+            double rho_ij = 0.5 * (s.prho + qrho);
+            double mu_ij = (h_ij * dot_product) / (r * r + c.eps * h_ij * h_ij);
+            double pi_ij = (-c.alpha * c_ij * mu_ij + c.beta * mu_ij * mu_ij) / rho_ij;
+            double fv = -qm * pi_ij * ker_ij;
+            s.dv0 += fv * dx;
+            s.dv1 += fv * dy;
+            if (DIM == 3) s.dv2 += fv * dz;
+        }
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_DV0) = s.dv0;
+        PF(S_DV1) = s.dv1;
+        if (DIM == 3) PF(S_DV2) = s.dv2;
+    }
+};
+
+// balance_of_mass!  collapse_dry.jl:112-115 (fixed h = kh, fixed mass m)
+struct B_dam_mass {
+    double drho, v0, v1, v2, rho;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &, int64_t p) {
+        drho = PF(S_DRHO);
+        v0 = PF(S_V0);
+        v1 = PF(S_V1);
+        v2 = DIM == 3 ? PF(S_V2) : 0.0;
+        rho = PF(S_RHO);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        double ker = c.m * rDwendland2(c.kh, r);
+        double d = dx * (v0 - QF(S_V0)) + dy * (v1 - QF(S_V1));
+        if (DIM == 3) d = d + dz * (v2 - QF(S_V2));
+        drho += ker * (d + 2 * c.nu * (rho - QF(S_RHO)));
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_DRHO) = drho;
+    }
+};
+// internal_force!  collapse_dry.jl:135-141
+struct B_dam_force {
+    double dv0, dv1, dv2, v0, v1, v2, P, rho;
+    bool fluid;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &c, int64_t p) {
+        dv0 = PF(S_DV0);
+        dv1 = PF(S_DV1);
+        dv2 = DIM == 3 ? PF(S_DV2) : 0.0;
+        v0 = PF(S_V0);
+        v1 = PF(S_V1);
+        v2 = DIM == 3 ? PF(S_V2) : 0.0;
+        P = PF(S_P);
+        rho = PF(S_RHO);
+        fluid = PF(S_TYPE) == c.fluid;
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        if (!fluid) return;
+        double ker = c.m * rDwendland2(c.kh, r);
+        double qrho = QF(S_RHO);
+        double a1 = -ker * (P / sph_pow2(rho) + QF(S_P) / sph_pow2(qrho));
+        dv0 += a1 * dx;
+        dv1 += a1 * dy;
+        if (DIM == 3) dv2 += a1 * dz;
+        double a2 = +2 * ker * c.mu / sph_pow2(c.rho0);
+        dv0 += a2 * (v0 - QF(S_V0));
+        dv1 += a2 * (v1 - QF(S_V1));
+        if (DIM == 3) dv2 += a2 * (v2 - QF(S_V2));
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_DV0) = dv0;
+        PF(S_DV1) = dv1;
+        if (DIM == 3) PF(S_DV2) = dv2;
+    }
+};
+// find_rho! / find_rho0!  test_collision_2d.jl:66-72
+template <int SLOT>
+struct B_col_rho {
+    double acc;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &, int64_t p) { acc = PF(SLOT); }
+    template <int DIM>
+    __device__ void pair(const Fields &, const Params &c, int64_t, int64_t, double, double, double,
+                         double r) {
+        acc += c.m * wendland2(c.kh, r);
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(SLOT) = acc;
+    }
+};
+// internal_force!  test_collision_2d.jl:78-81
+struct B_col_force {
+    double dv0, dv1, dv2, P;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &, int64_t p) {
+        dv0 = PF(S_DV0);
+        dv1 = PF(S_DV1);
+        dv2 = DIM == 3 ? PF(S_DV2) : 0.0;
+        P = PF(S_P);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        double ker = c.m * rDwendland2(c.kh, r);
+        double a = -ker * (P / sph_pow2(c.rho0) + QF(S_P) / sph_pow2(c.rho0));
+        dv0 += a * dx;
+        dv1 += a * dy;
+        if (DIM == 3) dv2 += a * dz;
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_DV0) = dv0;
+        PF(S_DV1) = dv1;
+        if (DIM == 3) PF(S_DV2) = dv2;
+    }
+};
+// accumulate_rho_pack!  new_packing.jl:11-15
+struct B_pack_rho {
+    double rho, hp;
+    bool fluid;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &c, int64_t p) {
+        rho = PF(S_RHO);
+        hp = PF(S_H);
+        fluid = PF(S_TYPE) == c.fluid;
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &, int64_t, int64_t q, double, double, double,
+                         double r) {
+        if (fluid) rho += QF(S_M) * sph_W<DIM>(hp, r);
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_RHO) = rho;
+    }
+};
+// balance_of_momentum_pack!  new_packing.jl:23-46
+struct B_pack_momentum {
+    double dv0, dv1, dv2, hp, rho_i, Pi, y;
+    bool fluid;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &c, int64_t p) {
+        dv0 = PF(S_DV0);
+        dv1 = PF(S_DV1);
+        dv2 = DIM == 3 ? PF(S_DV2) : 0.0;
+        hp = PF(S_H);
+        y = PF(S_X1);
+        rho_i = jl_max(PF(S_RHO), c.rho_floor);
+        Pi = sph_pow2(c.c_pack) * (rho_i - background_density(c, y));
+        fluid = PF(S_TYPE) == c.fluid;
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double, double dy,
+                         double, double r) {
+        if (!(fluid && QF(S_TYPE) == c.fluid)) return;
+        double rho_j = jl_max(QF(S_RHO), c.rho_floor);
+        double Pj = sph_pow2(c.c_pack) * (rho_j - background_density(c, QF(S_X1)));
+        double ker = sph_rDW<DIM>(0.5 * (hp + QF(S_H)), r);
+        double f1 = -QF(S_M) * (Pi / sph_pow2(rho_i) + Pj / sph_pow2(rho_j)) * ker * dy;
+        dv0 += f1 * 0.0;
+        dv1 += f1 * 1.0;
+        if (DIM == 3) dv2 += f1 * 0.0;
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_DV0) = dv0;
+        PF(S_DV1) = dv1;
+        if (DIM == 3) PF(S_DV2) = dv2;
+    }
+};
+
+// ---- fused operators of the fast path (sphmw_step, scheme "wcsph") --------
+// reset_density! + compute_density! + finalize_density! + update_smoothing! +
+// compute_pressure!  (wcsph_perturbed_witch.jl:316-323) in one pass, plus the
+// per-particle invariants of the pair force.
+struct B_wcsph_density_fused {
+    double rho, hp;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &, int64_t p) {
+        rho = 0.0;  // reset_density!
+        hp = PF(S_H);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &, int64_t, int64_t q, double, double,
+                         double, double r) {
+        rho += QF(S_M) * sph_W<DIM>(hp, r);
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &c, int64_t p) {
+        double y = PF(S_X1);
+        double rbg = background_density(c, y);  // finalize_density!
+        double rho_p = rho - rbg;
+        double rfl = jl_max(rho, c.rho_floor);  // update_smoothing!
+        double m = PF(S_M);
+        double hn = DIM == 2 ? c.eta * sqrt(m / rfl) : c.eta * cbrt(m / rfl);
+        double pbg = c.R_mass * c.T_bg * rbg;  // compute_pressure! (same rho_bg(y) value)
+        double pp = sph_pow2(c.c) * rho_p;
+        double P = pbg + pp;
+        PF(S_RHO) = rho;
+        PF(S_RHO_BG) = rbg;
+        PF(S_RHO_P) = rho_p;
+        PF(S_H) = hn;
+        PF(S_P_BG) = pbg;
+        PF(S_P_P) = pp;
+        PF(S_P) = P;
+        PF(S_PR2) = pp / sph_pow2(rfl);
+        PF(S_CS) = sqrt(c.gamma * P / rfl);
+    }
+};
+
+// balance_of_momentum! + accelerate!  (wcsph_perturbed_witch.jl:330-331).
+// Dv starts at 0 (accelerate! zeroed it) and is never stored; the new velocity
+// goes to the `out` field set because other threads still read the old one.
+struct B_wcsph_momentum_fused {
+    double dv0, dv1, dv2, v0, v1, v2, hp, prho, pr2, cs;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &c, int64_t p) {
+        dv0 = dv1 = dv2 = 0.0;
+        v0 = PF(S_V0);
+        v1 = PF(S_V1);
+        v2 = DIM == 3 ? PF(S_V2) : 0.0;
+        hp = PF(S_H);
+        prho = jl_max(PF(S_RHO), c.rho_floor);
+        pr2 = PF(S_PR2);
+        cs = PF(S_CS);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        double vx = v0 - QF(S_V0), vy = v1 - QF(S_V1);
+        double dot_product = dx * vx + dy * vy;
+        if (DIM == 3) {
+            double vz = v2 - QF(S_V2);
+            dot_product = dot_product + dz * vz;
+        }
+        double h_ij = 0.5 * (hp + QF(S_H));
+        double ker = sph_rDW<DIM>(h_ij, r);
+        double qm = QF(S_M);
+        double fc = -qm * (pr2 + QF(S_PR2)) * ker;
+        dv0 += fc * dx;
+        dv1 += fc * dy;
+        if (DIM == 3) dv2 += fc * dz;
+        if (dot_product < 0.0) {
+            double qrho = jl_max(QF(S_RHO), c.rho_floor);
+            double c_ij = 0.5 * (cs + QF(S_CS));
+            double rho_ij = 0.5 * (prho + qrho);
+            double mu_ij = (h_ij * dot_product) / (r * r + c.eps * h_ij * h_ij);
+            double pi_ij = (-c.alpha * c_ij * mu_ij + c.beta * mu_ij * mu_ij) / rho_ij;
+            double fv = -qm * pi_ij * ker;
+            dv0 += fv * dx;
+            dv1 += fv * dy;
+            if (DIM == 3) dv2 += fv * dz;
+        }
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &out, const Params &c, int64_t p) {
+        double n0 = v0, n1 = v1, n2 = v2;
+        if (PF(S_TYPE) == c.fluid) {  // accelerate!
+            const double rho_p = PF(S_RHO_P), rho = PF(S_RHO);
+            const bool sponge = PF(S_X1) >= c.sponge_z0;
+            const double hdt = 0.5 * c.dt;
+            n0 = v0 + hdt * (dv0 + -c.g * 0.0 * rho_p / rho + (sponge ? c.sponge_y * 0.0 : 0.0));
+            n1 = v1 + hdt * (dv1 + -c.g * 1.0 * rho_p / rho + (sponge ? c.sponge_y * 1.0 : 0.0));
+            if (DIM == 3)
+                n2 = v2 + hdt * (dv2 + -c.g * 0.0 * rho_p / rho + (sponge ? c.sponge_y * 0.0 : 0.0));
+        }
+        out.s[S_V0][p] = n0;
+        out.s[S_V1][p] = n1;
+        if (DIM == 3) out.s[S_V2][p] = n2;
+    }
+};
+#undef PF
+#undef QF
+
+// ---------------------------------------------------------------------------
+// generic neighbour traversal — _apply_binary!  src/core.jl:94-112.
+// One thread per particle (positions are cell-sorted, so a warp's particles sit
+// in a handful of adjacent cells and its neighbour reads hit the same lines).
+// Order of accumulation = the reference's: key_diff order (di outermost,
+// structs.jl:73-81), then the cell's stored order (index descending).
+// ---------------------------------------------------------------------------
+template <int DIM, class Op>
+__global__ void __launch_bounds__(128)
+k_binary(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
+         const uint32_t *__restrict__ cell_start, int64_t n, int self,
+         unsigned long long *pair_counter) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    Op op;
+    op.template init<DIM>(f, prm, p);
+    const double px = f.s[S_X0][p], py = f.s[S_X1][p], pz = DIM == 3 ? f.s[S_X2][p] : 0.0;
+    const long long k0 = key[p];
+    unsigned long long cnt = 0;
+    for (int d = 0; d < g.ndiff; ++d) {
+        long long nk = k0 + g.key_diff[d];
+        if (nk < 0 || nk >= g.key_max) continue;  // core.jl:98 — no per-axis wrap check
+        uint32_t b = cell_start[nk], e = cell_start[nk + 1];
+        for (uint32_t q = b; q < e; ++q) {
+            // dist(p,q) — core.jl:8-10, algebra.jl:49-60: left-to-right, no FMA
+            double dx = px - f.s[S_X0][q];
+            double dy = py - f.s[S_X1][q];
+            double dz = 0.0;
+            double r2 = dx * dx + dy * dy;
+            if (DIM == 3) {
+                dz = pz - f.s[S_X2][q];
+                r2 = r2 + dz * dz;
+            }
+            double r = sqrt(r2);
+            if ((r > g.h) || (q == p)) continue;  // core.jl:105
+            op.template pair<DIM>(f, prm, p, q, dx, dy, dz, r);
+            ++cnt;
+        }
+    }
+    if (self) op.template pair<DIM>(f, prm, p, p, 0.0, 0.0, 0.0, 0.0);  // core.jl:155-157
+    op.template finish<DIM>(f, out, prm, p);
+    if (pair_counter) {
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(__activemask(), cnt, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(pair_counter, cnt);
+    }
+}
+
+// accepted pairs in traversal order (test hook)
+template <int DIM>
+__global__ void k_pairs(Fields f, Grid g, const uint32_t *__restrict__ key,
+                        const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ idx,
+                        const uint32_t *__restrict__ pos_of_idx, int64_t n,
+                        const unsigned long long *__restrict__ offsets, long long *pi, long long *pj,
+                        long long cap, unsigned long long *counts) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // reference index
+    if (i >= n) return;
+    int64_t p = pos_of_idx[i];
+    const double px = f.s[S_X0][p], py = f.s[S_X1][p], pz = DIM == 3 ? f.s[S_X2][p] : 0.0;
+    const long long k0 = key[p];
+    unsigned long long cnt = 0;
+    unsigned long long base = offsets ? offsets[i] : 0;
+    for (int d = 0; d < g.ndiff; ++d) {
+        long long nk = k0 + g.key_diff[d];
+        if (nk < 0 || nk >= g.key_max) continue;
+        uint32_t b = cell_start[nk], e = cell_start[nk + 1];
+        for (uint32_t q = b; q < e; ++q) {
+            double dx = px - f.s[S_X0][q];
+            double dy = py - f.s[S_X1][q];
+            double r2 = dx * dx + dy * dy;
+            if (DIM == 3) {
+                double dz = pz - f.s[S_X2][q];
+                r2 = r2 + dz * dz;
+            }
+            double r = sqrt(r2);
+            if ((r > g.h) || ((int64_t)q == p)) continue;
+            if (offsets && (long long)(base + cnt) < cap) {
+                pi[base + cnt] = i;
+                pj[base + cnt] = idx[q];
+            }
+            ++cnt;
+        }
+    }
+    if (!offsets) counts[i] = cnt;
+}
+
+__global__ void k_scan_u64_serial(unsigned long long *a, int64_t n, unsigned long long *total) {
+    // test hook only (small n): single-thread exclusive scan
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            unsigned long long v = a[i];
+            a[i] = run;
+            run += v;
+        }
+        *total = run;
+    }
+}
+
+int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *nout) {
+    if (!c->cell_list_valid) { sphmw_set_error("cell list is not built"); return SPHMW_E_STATE; }
+    const int64_t n = c->n;
+    *nout = 0;
+    if (n == 0) return SPHMW_OK;
+    unsigned long long *counts = nullptr;
+    long long *dpi = nullptr, *dpj = nullptr;
+    CUDA_TRY(cudaMalloc(&counts, sizeof(unsigned long long) * (n + 1)));
+    int rc = [&]() -> int {
+        if (c->grid.dim == 2)
+            k_pairs<2><<<grid_for(n, 128), 128, 0, c->stream>>>(c->cur, c->grid, c->key, c->cell_start,
+                                                               c->idx, c->pos_of_idx, n, nullptr,
+                                                               nullptr, nullptr, 0, counts);
+        else
+            k_pairs<3><<<grid_for(n, 128), 128, 0, c->stream>>>(c->cur, c->grid, c->key, c->cell_start,
+                                                               c->idx, c->pos_of_idx, n, nullptr,
+                                                               nullptr, nullptr, 0, counts);
+        k_scan_u64_serial<<<1, 1, 0, c->stream>>>(counts, n, counts + n);
+        unsigned long long total = 0;
+        CUDA_TRY(cudaMemcpyAsync(&total, counts + n, sizeof(total), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        *nout = (int64_t)total;
+        int64_t m = std::min<int64_t>((int64_t)total, cap);
+        if (m <= 0 || !pi || !pj) return SPHMW_OK;
+        CUDA_TRY(cudaMalloc(&dpi, sizeof(long long) * m));
+        CUDA_TRY(cudaMalloc(&dpj, sizeof(long long) * m));
+        if (c->grid.dim == 2)
+            k_pairs<2><<<grid_for(n, 128), 128, 0, c->stream>>>(c->cur, c->grid, c->key, c->cell_start,
+                                                               c->idx, c->pos_of_idx, n, counts, dpi,
+                                                               dpj, m, nullptr);
+        else
+            k_pairs<3><<<grid_for(n, 128), 128, 0, c->stream>>>(c->cur, c->grid, c->key, c->cell_start,
+                                                               c->idx, c->pos_of_idx, n, counts, dpi,
+                                                               dpj, m, nullptr);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(pi, dpi, sizeof(long long) * m, cudaMemcpyDefault, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(pj, dpj, sizeof(long long) * m, cudaMemcpyDefault, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return SPHMW_OK;
+    }();
+    cudaFree(counts);
+    cudaFree(dpi);
+    cudaFree(dpj);
+    c->launches += 3;
+    return rc;
+}
+
+// ===========================================================================
+// operator menu and dispatch
+// ===========================================================================
+struct SlotList {
+    int s[16];
+    int n;
+};
+template <class... T>
+static inline SlotList make_slot_list(T... v) {
+    SlotList l{{(int)v...}, (int)sizeof...(v)};
+    return l;
+}
+#define SL(...) make_slot_list(__VA_ARGS__)
+
+// expand vector slots for the context's dimension
+static int need_slots(sphmw_ctx *c, const SlotList &reads, const SlotList &writes) {
+    auto expand = [&](int s, int out[3]) -> int {
+        if (s == S_X0 || s == S_V0 || s == S_DV0) {
+            out[0] = s;
+            out[1] = s + 1;
+            if (c->grid.dim == 3) { out[2] = s + 2; return 3; }
+            return 2;
+        }
+        out[0] = s;
+        return 1;
+    };
+    for (int i = 0; i < reads.n; ++i) {
+        int e[3];
+        int m = expand(reads.s[i], e);
+        for (int k = 0; k < m; ++k) {
+            if (c->allocated[e[k]] && c->stale[e[k]]) TRY(sphmw_materialize(c, e[k]));
+            TRY(sphmw_ensure_slot(c, e[k]));  // unset fields read as the constructor's zero
+        }
+    }
+    for (int i = 0; i < writes.n; ++i) {
+        int e[3];
+        int m = expand(writes.s[i], e);
+        for (int k = 0; k < m; ++k) {
+            if (c->allocated[e[k]] && c->stale[e[k]]) {
+                // about to be (partly) overwritten: bring it up to date first so that
+                // gated writes (type == FLUID) keep the other particles' values
+                TRY(sphmw_materialize(c, e[k]));
+            }
+            TRY(sphmw_ensure_slot(c, e[k]));
+            c->stale[e[k]] = false;
+        }
+    }
+    return SPHMW_OK;
+}
+
+template <class Op>
+static int run_unary(sphmw_ctx *c, const char *name) {
+    if (c->n == 0) return SPHMW_OK;
+    TIMED(c, name);
+    if (c->grid.dim == 2)
+        k_unary<2, Op><<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->cur, c->prm, c->n);
+    else
+        k_unary<3, Op><<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->cur, c->prm, c->n);
+    CUDA_TRY(cudaGetLastError());
+    return SPHMW_OK;
+}
+
+template <class Op>
+static int run_binary(sphmw_ctx *c, const char *name, int self, const Fields &out) {
+    if (!c->cell_list_valid) {
+        sphmw_set_error("%s: create_cell_list must be called after positions change", name);
+        return SPHMW_E_STATE;
+    }
+    if (c->n == 0) return SPHMW_OK;
+    unsigned long long *pc = c->count_pairs ? c->d_counters : nullptr;
+    if (pc) CUDA_TRY(cudaMemsetAsync(pc, 0, sizeof(unsigned long long), c->stream));
+    TIMED(c, name);
+    if (c->grid.dim == 2)
+        k_binary<2, Op><<<grid_for(c->n, 128), 128, 0, c->stream>>>(
+            c->cur, out, c->prm, c->grid, c->key, c->cell_start, c->n, self, pc);
+    else
+        k_binary<3, Op><<<grid_for(c->n, 128), 128, 0, c->stream>>>(
+            c->cur, out, c->prm, c->grid, c->key, c->cell_start, c->n, self, pc);
+    CUDA_TRY(cudaGetLastError());
+    return SPHMW_OK;
+}
+
+struct OpEntry {
+    const char *name;
+    bool binary;
+    int (*run)(sphmw_ctx *, const char *, int);
+};
+
+#define UNARY_ENTRY(NAME, OP, READS, WRITES, EXTRA)                         \
+    {NAME, false, [](sphmw_ctx *c, const char *nm, int) -> int {            \
+         TRY(need_slots(c, READS, WRITES));                                 \
+         TRY(run_unary<OP>(c, nm));                                         \
+         EXTRA;                                                             \
+         return SPHMW_OK;                                                   \
+     }}
+#define BINARY_ENTRY(NAME, OP, READS, WRITES, EXTRA)                        \
+    {NAME, true, [](sphmw_ctx *c, const char *nm, int self) -> int {        \
+         TRY(need_slots(c, READS, WRITES));                                 \
+         TRY((run_binary<OP>(c, nm, self, c->cur)));                        \
+         EXTRA;                                                             \
+         return SPHMW_OK;                                                   \
+     }}
+
+static const OpEntry OPS[] = {
+    UNARY_ENTRY("wcsph.accelerate", U_wcsph_accelerate<true>,
+                SL(S_TYPE, S_RHO_P, S_RHO, S_X0, S_DV0), SL(S_V0, S_DV0), c->dv_zero = true),
+    UNARY_ENTRY("wcsph.move", U_wcsph_move, SL(S_TYPE, S_V0), SL(S_X0), c->cell_list_valid = false),
+    UNARY_ENTRY("wcsph.reset_density", U_wcsph_reset_density, SL(S_TYPE), SL(S_RHO, S_RHO_P), ),
+    BINARY_ENTRY("wcsph.compute_density", B_wcsph_density, SL(S_X0, S_M, S_H), SL(S_RHO), ),
+    UNARY_ENTRY("wcsph.finalize_density", U_wcsph_finalize_density, SL(S_X0, S_RHO),
+                SL(S_RHO_BG, S_RHO_P), ),
+    UNARY_ENTRY("wcsph.update_smoothing", U_wcsph_update_smoothing, SL(S_M, S_RHO), SL(S_H), ),
+    UNARY_ENTRY("wcsph.compute_pressure", U_wcsph_compute_pressure, SL(S_X0, S_RHO_P),
+                SL(S_P_BG, S_P_P, S_P), ),
+    UNARY_ENTRY("wcsph.find_temperature", U_wcsph_find_temperature, SL(S_P, S_RHO, S_T_BG),
+                SL(S_T, S_T_P), ),
+    UNARY_ENTRY("wcsph.find_pot_temp", U_wcsph_find_pot_temp, SL(S_T, S_P, S_X0),
+                SL(S_TH, S_TH_BG, S_TH_P), ),
+    BINARY_ENTRY("wcsph.balance_of_momentum", B_wcsph_momentum,
+                 SL(S_X0, S_V0, S_H, S_M, S_RHO, S_P_P, S_P), SL(S_DV0), c->dv_zero = false),
+    UNARY_ENTRY("hopkins.reset_pressure", U_hopkins_reset_pressure, SL(S_TYPE), SL(S_P, S_P_P), ),
+    BINARY_ENTRY("hopkins.compute_pressure", B_hopkins_pressure, SL(S_X0, S_M, S_H, S_A), SL(S_P), ),
+    UNARY_ENTRY("hopkins.finalize_pressure", U_hopkins_finalize_pressure, SL(S_X0),
+                SL(S_P, S_P_BG, S_P_P), ),
+    UNARY_ENTRY("hopkins_total.reset_pressure", U_ht_reset_pressure, SL(S_TYPE), SL(S_P), ),
+    UNARY_ENTRY("hopkins_total.finalize_pressure", U_ht_finalize_pressure, SL(S_TYPE), SL(S_P), ),
+    UNARY_ENTRY("hopkins_total.find_temperature", U_ht_find_temperature, SL(S_P, S_RHO), SL(S_T), ),
+    UNARY_ENTRY("hopkins_total.find_pot_temp", U_ht_find_pot_temp, SL(S_T, S_P), SL(S_TH), ),
+    UNARY_ENTRY("hopkins_total.reset_density", U_ht_reset_density, SL(S_TYPE), SL(S_RHO), ),
+    BINARY_ENTRY("hopkins_total.balance_of_momentum", B_ht_momentum,
+                 SL(S_X0, S_V0, S_H, S_M, S_RHO, S_P, S_A), SL(S_DV0), c->dv_zero = false),
+    UNARY_ENTRY("hopkins_total.move", U_ht_move, SL(S_V0), SL(S_X0), c->cell_list_valid = false),
+    UNARY_ENTRY("hopkins_total.accelerate", U_ht_accelerate, SL(S_X0, S_DV0), SL(S_V0, S_DV0),
+                c->dv_zero = true),
+    BINARY_ENTRY("dambreak.balance_of_mass", B_dam_mass, SL(S_X0, S_V0, S_RHO), SL(S_DRHO), ),
+    UNARY_ENTRY("dambreak.find_pressure", U_dam_find_pressure, SL(S_DRHO), SL(S_RHO, S_DRHO, S_P), ),
+    BINARY_ENTRY("dambreak.internal_force", B_dam_force, SL(S_X0, S_V0, S_P, S_RHO, S_TYPE),
+                 SL(S_DV0), c->dv_zero = false),
+    UNARY_ENTRY("dambreak.move", U_dam_move, SL(S_TYPE, S_V0), SL(S_X0, S_DV0),
+                (c->cell_list_valid = false, c->dv_zero = true)),
+    UNARY_ENTRY("dambreak.accelerate", U_dam_accelerate, SL(S_TYPE, S_DV0), SL(S_V0), ),
+    BINARY_ENTRY("collision.find_rho", B_col_rho<S_RHO>, SL(S_X0), SL(S_RHO), ),
+    BINARY_ENTRY("collision.find_rho0", B_col_rho<S_RHO0>, SL(S_X0), SL(S_RHO0), ),
+    UNARY_ENTRY("collision.find_pressure", U_col_find_pressure, SL(S_RHO, S_RHO0), SL(S_P), ),
+    BINARY_ENTRY("collision.internal_force", B_col_force, SL(S_X0, S_P), SL(S_DV0),
+                 c->dv_zero = false),
+    UNARY_ENTRY("collision.reset_a", U_col_reset_a, SL(S_X0), SL(S_DV0), c->dv_zero = true),
+    UNARY_ENTRY("collision.reset_rho", U_col_reset_rho, SL(S_X0), SL(S_RHO), ),
+    UNARY_ENTRY("collision.move", U_col_move, SL(S_V0), SL(S_X0), c->cell_list_valid = false),
+    UNARY_ENTRY("collision.accelerate", U_col_accelerate, SL(S_DV0), SL(S_V0), ),
+    UNARY_ENTRY("packing.reset_rho", U_pack_reset_rho, SL(S_TYPE), SL(S_RHO), ),
+    BINARY_ENTRY("packing.accumulate_rho", B_pack_rho, SL(S_X0, S_M, S_H, S_TYPE), SL(S_RHO), ),
+    BINARY_ENTRY("packing.balance_of_momentum", B_pack_momentum,
+                 SL(S_X0, S_M, S_H, S_TYPE, S_RHO), SL(S_DV0), c->dv_zero = false),
+    UNARY_ENTRY("packing.accelerate", U_pack_accelerate, SL(S_TYPE, S_DV0), SL(S_V0, S_DV0),
+                c->dv_zero = true),
+    UNARY_ENTRY("packing.move", U_pack_move, SL(S_TYPE, S_V0), SL(S_X0),
+                c->cell_list_valid = false),
+    {nullptr, false, nullptr}};
+
+int64_t sphmw_list_ops(char *buf, int64_t cap) {
+    std::string all;
+    for (const OpEntry *e = OPS; e->name; ++e) {
+        all += e->name;
+        all += e->binary ? " binary\n" : " unary\n";
+    }
+    if (buf && cap > 0) {
+        size_t k = std::min<size_t>(all.size(), (size_t)cap - 1);
+        memcpy(buf, all.data(), k);
+        buf[k] = 0;
+    }
+    return (int64_t)all.size() + 1;
+}
+
+int sphmw_apply_named(sphmw_ctx *c, const char *op, int self) {
+    for (const OpEntry *e = OPS; e->name; ++e)
+        if (!strcmp(e->name, op)) {
+            if (self && !e->binary) {
+                // core.jl:151-161: `self` only matters for binary operators
+                self = 0;
+            }
+            return e->run(c, e->name, self);
+        }
+    sphmw_set_error("operator '%s' is not in the device menu (no CPU fallback)", op);
+    return SPHMW_E_UNSUPPORTED_OP;
+}
+
+// ---------------------------------------------------------------------------
+// lazily evaluated fields.  After a fused "wcsph" step T, T', theta, theta_bg,
+// theta' (diagnostics that never feed back) are stale; they are
+// rebuilt here by the very operators the reference runs every step
+// (find_temperature!, find_pot_temp!), from P, rho, x that have not changed since.
+// ---------------------------------------------------------------------------
+int sphmw_materialize(sphmw_ctx *c, int slot) {
+    if ((slot >= S_T_P && slot <= S_T) || (slot >= S_TH_BG && slot <= S_TH)) {
+        bool want = c->allocated[slot] ? c->stale[slot] : true;
+        if (!want) return SPHMW_OK;
+        if (!c->allocated[S_P] || !c->allocated[S_RHO]) return SPHMW_OK;  // nothing to derive from
+        for (int s : {S_T_P, S_T, S_TH_BG, S_TH_P, S_TH}) {
+            TRY(sphmw_ensure_slot(c, s));
+            c->stale[s] = false;
+        }
+        TRY(sphmw_ensure_slot(c, S_T_BG));
+        TRY(run_unary<U_wcsph_find_temperature>(c, "wcsph.find_temperature"));
+        TRY(run_unary<U_wcsph_find_pot_temp>(c, "wcsph.find_pot_temp"));
+        return SPHMW_OK;
+    }
+    if (c->allocated[slot] && c->stale[slot]) {
+        if (slot >= S_DV0 && slot <= S_DV2 && c->dv_zero) {
+            CUDA_TRY(cudaMemsetAsync(c->cur.s[slot], 0, sizeof(double) * c->cap, c->stream));
+            c->stale[slot] = false;
+            return SPHMW_OK;
+        }
+        sphmw_set_error("internal: slot %d is stale and has no rule", slot);
+        return SPHMW_E_STATE;
+    }
+    return SPHMW_OK;
+}
+
+// ===========================================================================
+// fused stepping
+// ===========================================================================
+static int apply_seq(sphmw_ctx *c, std::initializer_list<const char *> ops) {
+    for (const char *o : ops) {
+        if (!strcmp(o, "create_cell_list")) TRY(sphmw_build_cell_list(c, nullptr));
+        else if (o[0] == '+') TRY(sphmw_apply_named(c, o + 1, 1));
+        else TRY(sphmw_apply_named(c, o, 0));
+    }
+    return SPHMW_OK;
+}
+
+// wcsph_perturbed_witch.jl:309-332 with the unary sweeps fused into the two pair
+// passes; the redundant second create_cell_list! (:320, positions unchanged —
+// SURVEY quirk 4) is skipped.
+static int step_wcsph_fused(sphmw_ctx *c) {
+    // accelerate! + move!  (:311-312)
+    TRY(need_slots(c, SL(S_TYPE, S_RHO_P, S_RHO, S_X0, S_V0, S_M, S_H), SL(S_V0, S_X0)));
+    if (!c->dv_zero) {
+        TRY(need_slots(c, SL(S_DV0), SL(S_DV0)));
+        TRY(run_unary<U_wcsph_accelerate<true>>(c, "wcsph.accelerate"));
+        c->dv_zero = true;
+    } else {
+        TRY(run_unary<U_wcsph_accelerate<false>>(c, "wcsph.accelerate"));
+    }
+    // Dv is identically zero from here on and is not carried through the sort
+    for (int s = S_DV0; s <= S_DV2; ++s)
+        if (c->allocated[s]) c->stale[s] = true;
+    TRY(run_unary<U_wcsph_move>(c, "wcsph.move"));
+    c->cell_list_valid = false;
+    // diagnostics and per-step derived fields need not travel through the reorder
+    for (int s : {S_RHO_BG, S_P_BG, S_P_P, S_P, S_T_P, S_T, S_TH_BG, S_TH_P, S_TH, S_PR2, S_CS})
+        if (c->allocated[s]) c->stale[s] = true;
+    TRY(sphmw_build_cell_list(c, nullptr));  // :313
+    // :316-323
+    for (int s : {S_RHO_BG, S_RHO_P, S_RHO, S_P_BG, S_P_P, S_P, S_PR2, S_CS}) {
+        TRY(sphmw_ensure_slot(c, s));
+        c->stale[s] = false;
+    }
+    TRY((run_binary<B_wcsph_density_fused>(c, "wcsph.density_fused", 0, c->cur)));
+    // :326-327 find_temperature!/find_pot_temp! are diagnostics: left stale, rebuilt on demand
+    // :330-331
+    TRY((run_binary<B_wcsph_momentum_fused>(c, "wcsph.momentum_fused", 0, c->alt)));
+    std::swap(c->cur.s[S_V0], c->alt.s[S_V0]);
+    std::swap(c->cur.s[S_V1], c->alt.s[S_V1]);
+    if (c->grid.dim == 3) std::swap(c->cur.s[S_V2], c->alt.s[S_V2]);
+    return SPHMW_OK;
+}
+
+int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps) {
+    for (int k = 0; k < nsteps; ++k) {
+        if (!strcmp(scheme, "wcsph")) {
+            TRY(step_wcsph_fused(c));
+        } else if (!strcmp(scheme, "wcsph_unfused")) {
+            // the literal operator sequence of wcsph_perturbed_witch.jl:309-332
+            TRY(apply_seq(c, {"wcsph.accelerate", "wcsph.move", "create_cell_list",
+                              "wcsph.reset_density", "wcsph.compute_density",
+                              "wcsph.finalize_density", "wcsph.update_smoothing",
+                              "create_cell_list", "wcsph.compute_pressure",
+                              "wcsph.find_temperature", "wcsph.find_pot_temp",
+                              "wcsph.balance_of_momentum", "wcsph.accelerate"}));
+        } else if (!strcmp(scheme, "hopkins")) {
+            // hopkins_perturbed_witch.jl:325-349
+            TRY(apply_seq(c, {"wcsph.accelerate", "wcsph.move", "create_cell_list",
+                              "wcsph.reset_density", "wcsph.compute_density",
+                              "wcsph.finalize_density", "wcsph.update_smoothing",
+                              "hopkins.reset_pressure", "hopkins.compute_pressure",
+                              "hopkins.finalize_pressure", "wcsph.find_temperature",
+                              "wcsph.find_pot_temp", "wcsph.balance_of_momentum",
+                              "wcsph.accelerate"}));
+        } else if (!strcmp(scheme, "hopkins_total")) {
+            // hopkins_total_witch.jl:283-308
+            TRY(apply_seq(c, {"hopkins_total.accelerate", "hopkins_total.move", "create_cell_list",
+                              "hopkins_total.reset_density", "wcsph.compute_density",
+                              "wcsph.update_smoothing", "hopkins_total.reset_pressure",
+                              "hopkins.compute_pressure", "hopkins_total.finalize_pressure",
+                              "hopkins_total.find_temperature", "hopkins_total.find_pot_temp",
+                              "hopkins_total.balance_of_momentum", "hopkins_total.accelerate"}));
+        } else if (!strcmp(scheme, "dambreak")) {
+            // collapse_dry.jl:203-211
+            TRY(apply_seq(c, {"dambreak.accelerate", "dambreak.move", "create_cell_list",
+                              "dambreak.balance_of_mass", "dambreak.find_pressure", "dambreak.move",
+                              "create_cell_list", "dambreak.internal_force", "dambreak.accelerate"}));
+        } else if (!strcmp(scheme, "collision")) {
+            // test_collision_2d.jl:106-116
+            TRY(apply_seq(c, {"collision.accelerate", "collision.move", "create_cell_list",
+                              "collision.reset_rho", "+collision.find_rho",
+                              "collision.find_pressure", "collision.reset_a",
+                              "collision.internal_force", "collision.accelerate"}));
+        } else {
+            sphmw_set_error("unknown scheme '%s'", scheme);
+            return SPHMW_E_UNSUPPORTED_OP;
+        }
+    }
+    return SPHMW_OK;
+}

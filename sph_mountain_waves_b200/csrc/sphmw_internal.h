@@ -1,0 +1,171 @@
+// Internal declarations of libsphmw (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "sphmw.h"
+
+// ---------------------------------------------------------------------------
+// Particle fields.  One "slot" per scalar component; the union of the driver
+// Particle structs (wcsph_perturbed_witch.jl:83-102, hopkins_*:103,
+// collapse_dry.jl:74-82, test_collision_2d.jl:37-44) plus two derived per-particle
+// invariants of the pair force (S_PR2, S_CS) that only the fused step uses.
+// ---------------------------------------------------------------------------
+enum Slot : int {
+    S_H = 0,
+    S_X0, S_X1, S_X2,
+    S_M,
+    S_V0, S_V1, S_V2,
+    S_DV0, S_DV1, S_DV2,
+    S_RHO_BG, S_RHO_P, S_RHO,
+    S_P_BG, S_P_P, S_P,
+    S_TH_BG, S_TH_P, S_TH,
+    S_T_BG, S_T_P, S_T,
+    S_TYPE,
+    S_A, S_A_BG,
+    S_DRHO, S_RHO0,
+    S_PR2,  // P'/max(rho,floor)^2            (wcsph_perturbed_witch.jl:272)
+    S_CS,   // sqrt(gamma*P/max(rho,floor))   (wcsph_perturbed_witch.jl:276)
+    NSLOT
+};
+
+struct Fields {
+    double *s[NSLOT];
+};
+
+// driver constants (wcsph_perturbed_witch.jl:25-75 etc.); names match sphmw_set_param
+struct Params {
+    double dt, g, c, gamma, alpha, beta, eps, eta, rho0, R_mass, R_gas, T_bg;
+    double rho_floor, P_floor, z_t, z_b, gamma_r, fluid;
+    double m, nu, mu, gx, gy, gz, kh;
+    double dt_pack, c_pack, zeta_pack;
+    // derived on the host when a parameter changes
+    double sponge_y;  // -gamma_r*sin(pi/2*(1-(z_t-z_b)/z_b))^2  (:245-251)
+    double sponge_z0; // z_t - z_b
+};
+
+// neighbour-grid description passed to kernels by value (structs.jl:63-82)
+struct Grid {
+    double h;
+    double box[6];
+    long long phase[3];
+    long long lim[3];
+    long long key_max;
+    int key_diff[27];
+    int ndiff;
+    int dim;
+};
+
+struct TimingEntry {
+    int name_id;
+    cudaEvent_t a, b;
+};
+
+struct sphmw_ctx {
+    int device = 0;
+    Grid grid{};
+    Params prm{};
+    int64_t n = 0;       // particles resident (incl. ghosts in slab mode)
+    int64_t cap = 0;
+    int64_t slab_lo = -1, slab_hi = -1;
+
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+
+    Fields cur{};  // physical (cell-sorted) order
+    Fields alt{};  // reorder target / double buffer
+    bool allocated[NSLOT] = {};
+    bool stale[NSLOT] = {};  // contents not up to date: skip in reorder, rebuild on demand
+    bool dv_zero = true;     // Dv is known to be all-zero (never written since accelerate!)
+
+    uint32_t *idx = nullptr, *idx_alt = nullptr;  // reference particle index of each position
+    uint32_t *pos_of_idx = nullptr;               // inverse map
+    uint32_t *key = nullptr;         // cell key per position (key_max = dead bucket)
+    uint32_t *rank = nullptr;        // arrival rank inside the cell
+    uint32_t *src = nullptr;         // new position -> old position
+    uint32_t *cell_start = nullptr;  // key_max + 2 entries
+    uint32_t *scan_tmp = nullptr;
+    int64_t scan_tmp_len = 0;
+    uint32_t *removed = nullptr;     // [0] = count, [1..] = removed reference indices
+    int64_t removed_cap = 0;
+    uint32_t *h_removed = nullptr;   // pinned mirror
+    uint32_t *mv_old = nullptr, *mv_new = nullptr;
+    int64_t mv_cap = 0;
+    unsigned long long *d_counters = nullptr;  // [0] pair counter, [1] scratch
+    unsigned long long *h_counters = nullptr;  // pinned
+
+    double *staging = nullptr;  // 3*cap doubles
+    double *reduce_tmp = nullptr;
+
+    bool cell_list_valid = false;
+    bool count_pairs = false;
+    int64_t last_pair_count = 0;
+    bool scheme_first_step = true;
+
+    // pvd output (IO.jl:9-13)
+    std::string pvd_dir;
+    int64_t pvd_frame = 0;
+    std::vector<std::string> pvd_entries;
+    bool pvd_open = false;
+
+    // timing
+    bool timing = false;
+    std::vector<std::string> timing_names;
+    std::vector<double> timing_ms;
+    std::vector<int64_t> timing_calls;
+    std::vector<TimingEntry> timing_pending;
+    std::vector<cudaEvent_t> event_pool;
+    int64_t launches = 0;
+};
+
+// error plumbing -----------------------------------------------------------
+void sphmw_set_error(const char *fmt, ...);
+#define CUDA_TRY(expr)                                                              \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            sphmw_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                    \
+            return SPHMW_E_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+#define TRY(expr)            \
+    do {                     \
+        int _r = (expr);     \
+        if (_r != 0) return _r; \
+    } while (0)
+
+struct FieldDesc {
+    const char *name;
+    int slot;
+    int ncomp;
+};
+const FieldDesc *sphmw_find_field(const char *name);
+
+// implemented in cell_list.cu
+int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive);
+int sphmw_ensure_slot(sphmw_ctx *c, int slot);
+// implemented in pair_ops.cu
+int sphmw_apply_named(sphmw_ctx *c, const char *op, int self);
+int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps);
+int sphmw_materialize(sphmw_ctx *c, int slot);
+int64_t sphmw_list_ops(char *buf, int64_t cap);
+int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n);
+// implemented in frame_io.cpp
+int sphmw_write_vtp(const char *path, int64_t n, const double *points3n, int nfields,
+                    const char *const *names, const int *ncomps, const double *const *data);
+int sphmw_write_pvd(const char *path, const std::vector<std::string> &files);
+
+// timing helpers (api.cu)
+struct KernelTimer {
+    sphmw_ctx *c;
+    int pending_index;
+    KernelTimer(sphmw_ctx *ctx, const char *name);
+    ~KernelTimer();
+};
+#define TIMED(ctx, name) KernelTimer _kt_##__LINE__(ctx, name)
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }

@@ -1,0 +1,289 @@
+"""GPU parity tests proper: libsphmw (through the C ABI) against the CPU oracle on the
+same lattice-initialised inputs.  Bars (BASELINE.json north_star): cell assignment
+and neighbour-pair sets bit-exact; FP64 density/velocity within 1e-10 relative per
+step and 1e-6 after 1000 steps."""
+import numpy as np
+import pytest
+
+from sph_mountain_waves_b200 import cases
+from sph_mountain_waves_b200._capi import SphmwError, UnsupportedOperator
+from util import bits_equal, load_gpu, load_oracle, n_mismatch, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-10   # north_star: within 1e-10 relative per step
+TOL_1000 = 1e-6    # north_star: within 1e-6 after 1000 steps
+
+WCSPH_SEQ = ["wcsph.accelerate", "wcsph.move", "create_cell_list", "wcsph.reset_density",
+             "wcsph.compute_density", "wcsph.finalize_density", "wcsph.update_smoothing",
+             "create_cell_list", "wcsph.compute_pressure", "wcsph.find_temperature",
+             "wcsph.find_pot_temp", "wcsph.balance_of_momentum", "wcsph.accelerate"]
+# operators whose result involves exp/pow/cbrt (libm vs CUDA: <= 2 ulp apart)
+TRANSCENDENTAL = {"wcsph.finalize_density", "wcsph.compute_pressure", "wcsph.find_pot_temp"}
+WCSPH_FIELDS = ["x", "v", "Dv", "h", "m", "rho", "rho_p", "rho_bg", "P", "P_p", "P_bg", "T", "T_p",
+                "theta", "theta_p", "theta_bg", "type"]
+
+
+def small_2d():
+    return cases.mountain_wave_2d(n_y=20.0, dom_length=60e3)
+
+
+def small_witch_2d():
+    return cases.mountain_wave_2d(n_y=24.0, dom_length=80e3, h_m=3000.0, a=10e3, U=20.0)
+
+
+def small_3d():
+    return cases.bell_hill_3d(24, 12, 10, h_m=3000.0, a=8e3, U=20.0)
+
+
+CASES = {"static2d": small_2d, "witch2d": small_witch_2d, "hill3d": small_3d,
+         "dambreak": lambda: cases.collapse_dry(dr=4e-2), "collision": cases.collision_2d}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_cell_assignment_bit_exact(gpu, name):
+    case = CASES[name]()
+    o, s = load_oracle(case), load_gpu(case)
+    assert o.create_cell_list() == s.create_cell_list() == case.n
+    assert o.key_tables() == s.key_tables()
+    ko, ks = o.cell_keys(), s.cell_keys()
+    assert np.array_equal(ko, ks)
+    # stored order inside the cells (descending index, core.jl:32-37)
+    occupied = np.unique(ko)
+    rng = np.random.default_rng(0)
+    for key in rng.choice(occupied, size=min(200, len(occupied)), replace=False):
+        eo, es = o.cell_entries(int(key)), s.cell_entries(int(key))
+        assert np.array_equal(eo, es)
+        assert np.all(np.diff(es) < 0)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_neighbour_pairs_bit_exact(gpu, name):
+    case = CASES[name]()
+    o, s = load_oracle(case), load_gpu(case)
+    o.create_cell_list()
+    s.create_cell_list()
+    pio, pjo = o.pairs()
+    pis, pjs = s.pairs()
+    assert len(pio) == len(pis) > 0
+    # same set AND same traversal order (core.jl:94-112)
+    assert np.array_equal(pio, pis) and np.array_equal(pjo, pjs)
+
+
+@pytest.mark.parametrize("name", ["static2d", "witch2d", "hill3d"])
+def test_wcsph_operator_by_operator(gpu, name):
+    """every call of verlet_step! (wcsph_perturbed_witch.jl:309-332), one at a time,
+    two steps; compare all 18 fields after every call"""
+    case = CASES[name]()
+    o, s = load_oracle(case), load_gpu(case)
+    o.create_cell_list()
+    s.create_cell_list()
+    s.count_pairs(True)
+    worst = 0.0
+    for step in range(2):
+        for op in WCSPH_SEQ:
+            if op == "create_cell_list":
+                assert o.create_cell_list() == s.create_cell_list()
+                assert np.array_equal(o.cell_keys(), s.cell_keys())
+                continue
+            o.apply(op)
+            s.apply(op)
+            if op in ("wcsph.compute_density", "wcsph.balance_of_momentum"):
+                assert o.pair_count() == s.pair_count()
+            for f in WCSPH_FIELDS:
+                a, b = s.field(f), o.field(f)
+                e = rel_err(a, b)
+                worst = max(worst, e)
+                assert e <= TOL_STEP, (step, op, f, e)
+    # first sweep of the first step involves no transcendental at all on x, v, m, type
+    assert worst <= TOL_STEP
+
+
+@pytest.mark.parametrize("name", ["static2d", "hill3d"])
+def test_pair_sums_bitwise_where_no_transcendental(gpu, name):
+    """with identical inputs, the density sum (mul/add/div only) and the pair force
+    must be BIT-identical to the oracle: same neighbour order, no FMA contraction"""
+    case = CASES[name]()
+    o, s = load_oracle(case), load_gpu(case)
+    o.create_cell_list()
+    s.create_cell_list()
+    for op in ("wcsph.reset_density", "wcsph.compute_density"):
+        o.apply(op)
+        s.apply(op)
+    assert n_mismatch(s.field("rho"), o.field("rho")) == 0
+    # feed the oracle's (libm) thermodynamic state to the device, then compare the force
+    for op in ("wcsph.finalize_density", "wcsph.update_smoothing", "wcsph.compute_pressure"):
+        o.apply(op)
+    for f in ("rho_p", "rho_bg", "h", "P", "P_p", "P_bg"):
+        s.set_field(f, o.field(f))
+    o.apply("wcsph.balance_of_momentum")
+    s.apply("wcsph.balance_of_momentum")
+    assert n_mismatch(s.field("Dv"), o.field("Dv")) == 0
+    o.apply("wcsph.accelerate")
+    s.apply("wcsph.accelerate")
+    assert n_mismatch(s.field("v"), o.field("v")) == 0
+
+
+@pytest.mark.parametrize("name", ["static2d", "witch2d", "hill3d"])
+def test_fused_step_equals_operator_sequence(gpu, name):
+    """sphmw_step("wcsph") must leave the same state as the literal sequence"""
+    case = CASES[name]()
+    a, b = load_gpu(case), load_gpu(case)
+    a.create_cell_list()
+    b.create_cell_list()
+    a.step(3, "wcsph")
+    b.step(3, "wcsph_unfused")
+    for f in WCSPH_FIELDS:
+        assert bits_equal(a.field(f), b.field(f)), f
+
+
+@pytest.mark.parametrize("name", ["static2d", "witch2d", "hill3d"])
+def test_step_parity_vs_oracle(gpu, name):
+    case = CASES[name]()
+    o, s = load_oracle(case), load_gpu(case)
+    o.create_cell_list()
+    s.create_cell_list()
+    o.step("wcsph", 1)
+    s.step(1)
+    for f in ("rho", "v", "x", "h", "P", "theta", "T"):
+        assert rel_err(s.field(f), o.field(f)) <= TOL_STEP, f
+    o.step("wcsph", 19)
+    s.step(19)
+    assert len(o) == len(s)
+    for f in ("rho", "v", "x", "h"):
+        assert rel_err(s.field(f), o.field(f)) <= 20 * TOL_STEP, f
+
+
+def test_1000_steps_within_1e6(gpu):
+    case = cases.mountain_wave_2d(n_y=12.0, dom_length=40e3)
+    o, s = load_oracle(case), load_gpu(case)
+    o.create_cell_list()
+    s.create_cell_list()
+    o.step("wcsph", 1000)
+    s.step(1000)
+    assert len(o) == len(s)
+    for f in ("rho", "v", "x"):
+        assert rel_err(s.field(f), o.field(f)) <= TOL_1000, f
+
+
+def test_determinism_bitwise(gpu):
+    case = small_witch_2d()
+    out = []
+    for _ in range(2):
+        s = load_gpu(case)
+        s.create_cell_list()
+        s.step(5)
+        out.append({f: s.field(f) for f in ("x", "v", "rho", "h")})
+    for f in out[0]:
+        assert np.array_equal(out[0][f], out[1][f]), f
+
+
+def test_removal_swap_from_end_order(gpu):
+    """particles outside the bounding box are removed with the reference's
+    swap-from-end renumbering (core.jl:64-81), NaN positions included"""
+    case = small_2d()
+    f = {k: v.copy() for k, v in case.fields.items()}
+    n = case.n
+    rng = np.random.default_rng(3)
+    out = rng.choice(n, size=37, replace=False)
+    f["x"][out[:20], 1] = 1e9           # above the box
+    f["x"][out[20:30], 0] = -1e9        # left of it
+    f["x"][out[30:], 0] = np.nan        # NaN fails every comparison
+    f["x"][n - 1, 1] = 1e9              # last particle removed: swap with itself
+    f["x"][n - 2, 1] = 1e9
+    f["m"] = np.arange(n, dtype=np.float64)  # tag to follow identities
+    case2 = cases.Case(case.name, case.scheme, case.dim, case.box_min, case.box_max, case.h,
+                       case.params, f)
+    o, s = load_oracle(case2), load_gpu(case2)
+    no, ns = o.create_cell_list(), s.create_cell_list()
+    assert no == ns == len(s) < n
+    assert np.array_equal(o.field("m"), s.field("m"))
+    assert bits_equal(o.field("x"), s.field("x"))
+    assert np.array_equal(o.cell_keys(), s.cell_keys())
+    pio, pjo = o.pairs()
+    pis, pjs = s.pairs()
+    assert np.array_equal(pio, pis) and np.array_equal(pjo, pjs)
+    # and the system keeps stepping identically afterwards
+    o.step("wcsph", 2)
+    s.step(2)
+    assert rel_err(s.field("rho"), o.field("rho")) <= TOL_STEP
+
+
+def test_dambreak_steps(gpu):
+    """BASELINE config 1 operators (collapse_dry.jl:112-159, :203-211)"""
+    case = cases.collapse_dry(dr=4e-2)
+    o, s = load_oracle(case), load_gpu(case)
+    for sysm in (o, s):
+        sysm.create_cell_list()
+    o.apply("dambreak.internal_force")   # collapse_dry.jl:201
+    s.apply("dambreak.internal_force")
+    o.step("dambreak", 50)
+    s.step(50, "dambreak")
+    assert len(o) == len(s)
+    # no transcendental anywhere in this scheme: bit-identical
+    for f in ("x", "v", "rho", "P", "Dv"):
+        assert n_mismatch(s.field(f), o.field(f)) == 0, f
+
+
+def test_collision_2d_invariants(gpu):
+    """the reference's only integration test (test_collision_2d.jl:119-147): particle
+    count constant, energy drift < 1 %; here also bit-parity with the oracle"""
+    case = cases.collision_2d()
+    p = case.params
+    o, s = load_oracle(case), load_gpu(case)
+    for sysm, ap in ((o, lambda op, sf=False: o.apply(op, sf)), (s, lambda op, sf=False: s.apply(op, sf))):
+        sysm.create_cell_list()
+        ap("collision.find_rho0", True)
+        ap("collision.find_rho", True)
+        ap("collision.find_pressure")
+        ap("collision.internal_force")
+
+    def energy(sysm):
+        v, rho, rho0 = sysm.field("v"), sysm.field("rho"), sysm.field("rho0")
+        kin = 0.5 * p["m"] * np.sum(v * v, axis=1)
+        internal = 0.5 * p["m"] * p["c"] ** 2 * (rho - rho0) ** 2 / p["rho0"] ** 2
+        return float(np.sum(kin + internal))
+
+    nsteps = int(round(case.info["t_end"] / case.info["dt"]))
+    every = int(round(case.info["t_end"] / 10 / case.info["dt"]))
+    N, E = [], []
+    done = 0
+    for k in range(0, nsteps + 1, every):
+        # verlet_step! is called for k = 0..nsteps; sample after step k
+        todo = (k + 1) - done
+        s.step(todo, "collision")
+        o.step("collision", todo)
+        done += todo
+        N.append(len(s))
+        E.append(energy(s))
+        assert n_mismatch(s.field("v"), o.field("v")) == 0
+    assert all(n == N[0] for n in N)
+    assert max(e / E[0] - 1.0 for e in E) < 1e-2
+
+
+def test_errors(gpu):
+    case = small_2d()
+    s = load_gpu(case)
+    with pytest.raises(SphmwError):
+        s.apply("wcsph.compute_density")           # binary before create_cell_list
+    s.create_cell_list()
+    with pytest.raises(UnsupportedOperator):
+        s.apply("wcsph.no_such_closure")
+    with pytest.raises(UnsupportedOperator):
+        s.apply(lambda p: None)                    # host closure: no CPU fallback
+    with pytest.raises(KeyError):
+        s.field("nonexistent")
+    with pytest.raises(AssertionError):
+        cases.to_system(cases.Case("bad", "wcsph", 2, case.box_min, case.box_max, -1.0, {}, case.fields))
+
+
+def test_reductions(gpu):
+    case = small_witch_2d()
+    s = load_gpu(case)
+    s.create_cell_list()
+    s.step(3)
+    v = s.field("v")
+    speed = np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1] + v[:, 2] * v[:, 2])
+    assert abs(s.reduce("avg_speed") - speed.mean()) <= 1e-12 * speed.mean()
+    assert s.reduce("max_speed") == speed.max()
+    assert s.reduce("count") == len(s)
