@@ -74,18 +74,20 @@ def witch_2d(n_y: float = 510.0, **kw) -> Case:
 
 
 def bell_hill_3d(nx: int, ny: int, nz: int, h_m: float = 100.0, a: float = 10e3, U: float = 20.0,
-                 x_range: Optional[tuple] = None, name: Optional[str] = None) -> Case:
+                 lean: bool = False, clip: Optional[tuple] = None, name: Optional[str] = None) -> Case:
     """BASELINE configs 4/5: 3D extrusion on a cubic lattice with nx*ny*nz fluid
-    sites, dr = 26 km / ny, vertical axis x[2].  `x_range=(i0,i1)` generates only the
-    lattice planes i0 <= i < i1 of the GLOBAL index range (slab generation for
-    multi-GPU runs); indices stay global."""
+    cells, dr = 26 km / ny, vertical axis x[2].  `lean` keeps only the fields the step
+    carries; `clip=(xa, xb)` generates only the sites with xa <= x < xb (one rank's
+    x-slab; `info["group_counts"]` then gives the sizes of the three generation groups
+    so that ranks can agree on global particle indices)."""
     k = wpw.Constants(n_y=float(ny), h_m=h_m, a=a, U=U, dim=3, grid="cubic",
                       mountain_type=wpw.MOUNTAIN if h_m else wpw.FLUID)
     k.dom_length = nx * k.dr
     k.dom_width = nz * k.dr
-    sys = wpw.make_system(k)
+    sys = wpw.make_system(k, lean=lean, clip=clip)
     c = _from_system(name or f"bell_hill_3d_{nx}x{ny}x{nz}", sys, "wcsph")
-    c.info = dict(dr=k.dr, dt=k.dt, frame_every=int(round(k.dt_frame / k.dt)))
+    c.info = dict(dr=k.dr, dt=k.dt, frame_every=int(round(k.dt_frame / k.dt)),
+                  group_counts=tuple(sys.group_counts))
     return c
 
 

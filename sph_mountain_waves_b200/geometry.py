@@ -160,6 +160,23 @@ class Specification(Shape):
         return self.s.boundarybox()
 
 
+@dataclass
+class SlabClip(Shape):
+    """Not in the reference: `s` restricted to the half-open x-slab [xa, xb).  Used to
+    generate only one rank's share of a lattice (multi-GPU x-slabs) in the same
+    plane-major order as the whole shape."""
+    s: Shape
+    xa: float
+    xb: float
+
+    def is_inside(self, x):
+        return self.s.is_inside(x) & (x[:, 0] >= self.xa) & (x[:, 0] < self.xb)
+
+    def boundarybox(self):
+        b = self.s.boundarybox()
+        return Box(max(b.x1_min, self.xa), b.x2_min, b.x3_min, min(b.x1_max, self.xb), b.x2_max, b.x3_max)
+
+
 class BoundaryLayer(Shape):
     """geometry.jl:196-232 — points outside `s` with a lattice offset |dx| <= width
     that lands inside `s`."""

@@ -15,7 +15,7 @@ from typing import Dict, Optional
 
 import numpy as np
 
-from ..geometry import BoundaryLayer, Box, Rectangle, Specification
+from ..geometry import BoundaryLayer, Box, Rectangle, SlabClip, Specification
 from ..grids import Grid
 from ..system import (Operator, ParticleSystem, ParticleType, apply, create_cell_list,
                       generate_particles, new_pvd_file, save_frame, save_pvd_file)
@@ -116,12 +116,25 @@ def background_pot_temperature(k: Constants, y):
     return k.T_bg * ((k.T_bg * k.R_gas * k.rho0) / background_pressure(k, y)) ** (2 / 7)
 
 
-def particle_ctor(k: Constants, v, ptype: float):
-    """≙ Particle(x, v, type) inner constructor, :103-145 (vectorised over x)."""
+# the fields the step actually carries from one step to the next; everything else is
+# recomputed inside verlet_step! before it is read
+CORE_FIELDS = ("h", "x", "m", "v", "ρ′", "ρ", "type")
+LeanParticle = ParticleType("LeanParticle", CORE_FIELDS, scheme="wcsph")
+
+
+def particle_ctor(k: Constants, v, ptype: float, lean: bool = False):
+    """≙ Particle(x, v, type) inner constructor, :103-145 (vectorised over x).
+    `lean` returns only CORE_FIELDS (same values) for very large particle sets."""
     def ctor(x: np.ndarray):
         n = len(x)
         y = x[:, 1]
         rho_bg = background_density(k, y)
+        if lean:
+            cell = k.dr * k.dr if k.dim == 2 else k.dr * k.dr * k.dr
+            vv = np.zeros((n, 3))
+            vv[:] = v
+            return {"h": np.full(n, k.h0), "x": x, "v": vv, "rho_p": np.zeros(n),
+                    "rho": 0.0 + rho_bg, "type": np.full(n, ptype), "m": (0.0 + rho_bg) * cell}
         P_bg = background_pressure(k, y)
         th_bg = background_pot_temperature(k, y)
         cell = k.dr * k.dr if k.dim == 2 else k.dr * k.dr * k.dr
@@ -148,8 +161,10 @@ def witch_profile(k: Constants, x, z=None):
         return k.h_m / (1 + (x ** 2 + z ** 2) / k.a ** 2) ** 1.5
 
 
-def make_system(k: Optional[Constants] = None, **sys_kw) -> ParticleSystem:
-    """≙ make_system(), :152-170 (2D) and its 3D extrusion."""
+def make_system(k: Optional[Constants] = None, lean: bool = False, clip=None,
+                **sys_kw) -> ParticleSystem:
+    """≙ make_system(), :152-170 (2D) and its 3D extrusion.  `clip=(xa, xb)` generates
+    only the lattice sites with xa <= x < xb (one rank's x-slab)."""
     k = k or Constants()
     if k.dim == 2:
         grid = Grid(k.dr, k.grid, K=1.0)  # :154
@@ -161,13 +176,19 @@ def make_system(k: Optional[Constants] = None, **sys_kw) -> ParticleSystem:
                      k.dom_length / 2.0, k.dom_height, k.dom_width / 2.0)
         mountain = Specification(domain, lambda x: x[:, 1] <= witch_profile(k, x[:, 0], x[:, 2]))
     fence = BoundaryLayer(domain, grid, k.bc_width)  # :156
-    sys = ParticleSystem(Particle, domain + fence, k.h0, params=k.params(), **sys_kw)  # :161
+    sys = ParticleSystem(LeanParticle if lean else Particle, domain + fence, k.h0,
+                         params=k.params(), **sys_kw)  # :161
     wind = np.array([k.U, 0.0, 0.0])
-    generate_particles(sys, grid, domain - mountain, particle_ctor(k, wind, FLUID))  # :162
-    generate_particles(sys, grid, fence, particle_ctor(k, 0.0, WALL))  # :163
-    generate_particles(sys, grid, mountain,
-                       particle_ctor(k, wind if k.mountain_type == FLUID else 0.0, k.mountain_type))  # :164
+    cl = (lambda s: s) if clip is None else (lambda s: SlabClip(s, clip[0], clip[1]))
+    counts = [
+        generate_particles(sys, grid, cl(domain - mountain), particle_ctor(k, wind, FLUID, lean)),  # :162
+        generate_particles(sys, grid, cl(fence), particle_ctor(k, 0.0, WALL, lean)),  # :163
+        generate_particles(sys, grid, cl(mountain),
+                           particle_ctor(k, wind if k.mountain_type == FLUID else 0.0,
+                                         k.mountain_type, lean)),  # :164
+    ]
     sys.constants = k
+    sys.group_counts = counts
     return sys
 
 
