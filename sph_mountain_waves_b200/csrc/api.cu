@@ -286,6 +286,14 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
                 for (int dk = -1; dk <= 1; ++dk)
                     g.key_diff[g.ndiff++] = (int)(di + g.lim[0] * (dj + g.lim[1] * dk));
     }
+    {
+        // exact threshold for the cut-off test (sqrt is monotone and correctly rounded on
+        // host and device alike)
+        double t = g.h * g.h;
+        while (sqrt(t) > g.h) t = nextafter(t, 0.0);
+        while (sqrt(nextafter(t, INFINITY)) <= g.h) t = nextafter(t, INFINITY);
+        g.r2_max = t;
+    }
     memset(&c->prm, 0, sizeof(Params));
 
     int rc = [&]() -> int {

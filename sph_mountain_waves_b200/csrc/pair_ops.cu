@@ -804,8 +804,9 @@ k_binary(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ 
                 dz = pz - f.s[S_X2][q];
                 r2 = r2 + dz * dz;
             }
+            // core.jl:105 `r > sys.h || p == q`, decided on r2 (Grid::r2_max): same set, bit for bit
+            if ((r2 > g.r2_max) || (q == p)) continue;
             double r = sqrt(r2);
-            if ((r > g.h) || (q == p)) continue;  // core.jl:105
             op.template pair<DIM>(f, prm, p, q, dx, dy, dz, r);
             ++cnt;
         }
@@ -844,8 +845,7 @@ __global__ void k_pairs(Fields f, Grid g, const uint32_t *__restrict__ key,
                 double dz = pz - f.s[S_X2][q];
                 r2 = r2 + dz * dz;
             }
-            double r = sqrt(r2);
-            if ((r > g.h) || ((int64_t)q == p)) continue;
+            if ((r2 > g.r2_max) || ((int64_t)q == p)) continue;
             if (offsets && (long long)(base + cnt) < cap) {
                 pi[base + cnt] = i;
                 pj[base + cnt] = idx[q];

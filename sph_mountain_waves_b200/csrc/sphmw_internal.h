@@ -50,6 +50,9 @@ struct Params {
 // neighbour-grid description passed to kernels by value (structs.jl:63-82)
 struct Grid {
     double h;
+    // largest double whose correctly rounded sqrt is <= h:  sqrt(r2) > h  <=>  r2 > r2_max,
+    // so rejected candidates never pay for the FP64 square root (core.jl:104-105)
+    double r2_max;
     double box[6];
     long long phase[3];
     long long lim[3];

@@ -125,19 +125,22 @@ LeanParticle = ParticleType("LeanParticle", CORE_FIELDS, scheme="wcsph")
 def particle_ctor(k: Constants, v, ptype: float, lean: bool = False):
     """≙ Particle(x, v, type) inner constructor, :103-145 (vectorised over x).
     `lean` returns only CORE_FIELDS (same values) for very large particle sets."""
+    def mass(rho):
+        # :143  obj.m = obj.ρ * dr * dr  (left to right); one more factor dr in 3D
+        m = rho * k.dr * k.dr
+        return m if k.dim == 2 else m * k.dr
+
     def ctor(x: np.ndarray):
         n = len(x)
         y = x[:, 1]
         rho_bg = background_density(k, y)
         if lean:
-            cell = k.dr * k.dr if k.dim == 2 else k.dr * k.dr * k.dr
             vv = np.zeros((n, 3))
             vv[:] = v
             return {"h": np.full(n, k.h0), "x": x, "v": vv, "rho_p": np.zeros(n),
-                    "rho": 0.0 + rho_bg, "type": np.full(n, ptype), "m": (0.0 + rho_bg) * cell}
+                    "rho": 0.0 + rho_bg, "type": np.full(n, ptype), "m": mass(0.0 + rho_bg)}
         P_bg = background_pressure(k, y)
         th_bg = background_pot_temperature(k, y)
-        cell = k.dr * k.dr if k.dim == 2 else k.dr * k.dr * k.dr
         vv = np.zeros((n, 3))
         vv[:] = v
         return {
@@ -147,7 +150,7 @@ def particle_ctor(k: Constants, v, ptype: float, lean: bool = False):
             "theta_bg": th_bg, "theta_p": np.zeros(n), "theta": 0.0 + th_bg,
             "T_bg": np.full(n, k.T_bg), "T_p": np.zeros(n), "T": np.full(n, 0.0 + k.T_bg),
             "type": np.full(n, ptype),
-            "m": (0.0 + rho_bg) * cell,  # :143  obj.m = obj.ρ * dr * dr
+            "m": mass(0.0 + rho_bg),
         }
     return ctor
 

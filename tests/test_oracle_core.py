@@ -1,0 +1,172 @@
+"""The oracle's cell list / traversal / step against independent pure-Python restatements
+of the reference on small inputs, and against the invariants the reference's integration
+test asserts (sph_jl/tests/test_collision_2d.jl:141-147)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from sph_mountain_waves_b200 import cases
+from util import load_oracle
+
+
+def py_find_key(x, h, phase, lim):
+    # structs.jl:97-106, 1-based
+    i = 1 + int(math.floor(x[0] / h)) - phase[0]
+    j = 1 + int(math.floor(x[1] / h)) - phase[1]
+    k = 1 + int(math.floor(x[2] / h)) - phase[2]
+    return i + lim[0] * (j - 1) + lim[0] * lim[1] * (k - 1)
+
+
+def py_create_cell_list(xs, box, h, phase, lim):
+    """core.jl:51-90 literally, on a python list of positions; returns the surviving
+    original indices in their new order and the cells (1-based entries, descending)."""
+    particles = list(range(len(xs)))
+    removal = []
+    for i, p in enumerate(particles):
+        x = xs[p]
+        inside = (box[0] <= x[0] <= box[3]) and (box[1] <= x[1] <= box[4]) and (box[2] <= x[2] <= box[5])
+        if not inside:
+            removal.append(i + 1)
+    removal.sort(reverse=True)  # add_index! keeps entries descending
+    i = 1
+    while i <= len(removal):
+        particles[removal[i - 1] - 1] = particles[len(particles) - i]  # particles[end+1-i]
+        i += 1
+    if i > 1:
+        particles = particles[:len(particles) + 1 - i]
+    cells = {}
+    for i, p in enumerate(particles):
+        key = py_find_key(xs[p], h, phase, lim)
+        cells.setdefault(key, []).append(i + 1)
+    for key in cells:
+        cells[key].sort(reverse=True)
+    return particles, cells
+
+
+def py_pairs(xs, order, cells, h, phase, lim, key_diff, key_max):
+    out = []
+    for i, p in enumerate(order):
+        key = py_find_key(xs[p], h, phase, lim)
+        for dk in key_diff:
+            nk = key + dk
+            if 1 <= nk <= key_max:
+                for j1 in cells.get(nk, []):
+                    q = order[j1 - 1]
+                    d = [xs[p][a] - xs[q][a] for a in range(3)]
+                    r = math.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+                    if r > h or p == q:
+                        continue
+                    out.append((i, j1 - 1))
+    return out
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_cell_list_and_pairs_vs_python(dim):
+    rng = np.random.default_rng(7 + dim)
+    n = 400
+    h = 0.37
+    box_min = (-1.3, -0.7, 0.0 if dim == 2 else -0.9)
+    box_max = (1.9, 1.1, 0.0 if dim == 2 else 0.8)
+    x = np.zeros((n, 3))
+    for a in range(dim):
+        x[:, a] = rng.uniform(box_min[a] - 0.15, box_max[a] + 0.15, n)  # some fall outside
+    x[5, 0] = np.nan
+    x[n - 1, 1] = 50.0   # the last particle is removed: swap with itself
+    x[n - 3, 1] = 50.0
+    x[17] = (box_max[0], box_max[1], box_max[2])  # closed interval: exactly on the corner is inside
+    o = O.OracleSystem(box_min, box_max, h)
+    o.append({"x": x, "m": np.arange(n, dtype=float)})
+    phase, lim, key_max, d = o.key_tables()
+    assert d == dim
+    # structs.jl:70-82
+    if dim == 2:
+        key_diff = [di + lim[0] * dj for di in (-1, 0, 1) for dj in (-1, 0, 1)]
+    else:
+        key_diff = [di + lim[0] * (dj + lim[1] * dk) for di in (-1, 0, 1) for dj in (-1, 0, 1) for dk in (-1, 0, 1)]
+    order, cells = py_create_cell_list([tuple(r) for r in x], list(box_min) + list(box_max), h, phase, lim)
+    assert o.create_cell_list() == len(order) < n
+    assert np.array_equal(o.field("m").astype(int), np.array(order))
+    keys = o.cell_keys()
+    for i, p in enumerate(order):
+        assert keys[i] + 1 == py_find_key(x[p], h, phase, lim)
+    for key, entries in cells.items():
+        assert list(o.cell_entries(key - 1) + 1) == entries
+    pi, pj = o.pairs()
+    assert list(zip(pi.tolist(), pj.tolist())) == py_pairs([tuple(r) for r in x], order, cells, h, phase, lim,
+                                                            key_diff, key_max)
+
+
+def test_hydrostatic_initial_state_is_analytic():
+    """Particle constructor, wcsph_perturbed_witch.jl:125-143 and :177-189"""
+    case = cases.mountain_wave_2d(n_y=10.0, dom_length=30e3)
+    p = case.params
+    y = case.fields["x"][:, 1]
+    rho = p["rho0"] * np.exp(-y * p["g"] / (p["R_mass"] * p["T_bg"]))
+    assert np.array_equal(case.fields["rho"], rho)
+    assert np.array_equal(case.fields["P"], p["R_mass"] * p["T_bg"] * rho)
+    dr = case.info["dr"]
+    assert np.array_equal(case.fields["m"], rho * dr * dr)
+    assert np.all(case.fields["h"] == 1.8 * dr)
+    # index order = fluid bulk, wall fence, bottom row (as FLUID)
+    t = case.fields["type"]
+    first_wall = np.argmax(t == 1.0)
+    last_wall = len(t) - 1 - np.argmax(t[::-1] == 1.0)
+    assert np.all(t[:first_wall] == 0.0) and np.all(t[first_wall:last_wall + 1] == 1.0)
+    assert np.all(t[last_wall + 1:] == 0.0) and np.all(case.fields["x"][last_wall + 1:, 1] == 0.0)
+
+
+def test_density_without_self_term_quirk():
+    """no self contribution -> rho ~ 0.369 rho_bg on the hex lattice and
+    h inflates to ~2.96 dr after the first step"""
+    case = cases.mountain_wave_2d(n_y=30.0, dom_length=60e3)
+    o = load_oracle(case)
+    o.create_cell_list()
+    o.step("wcsph", 1)
+    interior = (case.fields["type"] == 0.0) & (case.fields["x"][:, 1] > 5e3) & (case.fields["x"][:, 1] < 20e3) \
+        & (np.abs(case.fields["x"][:, 0]) < 20e3)
+    ratio = (o.field("rho") / o.field("rho_bg"))[interior]
+    assert abs(np.median(ratio) - 0.369) < 2e-3
+    assert abs(np.median(o.field("h")[interior]) / case.info["dr"] - 2.963) < 5e-3
+
+
+def test_collision_2d_energy_and_count():
+    """sph_jl/tests/test_collision_2d.jl:119-147 on the oracle"""
+    case = cases.collision_2d()
+    p = case.params
+    o = load_oracle(case)
+    o.create_cell_list()
+    o.apply("collision.find_rho0", True)
+    o.apply("collision.find_rho", True)
+    o.apply("collision.find_pressure")
+    o.apply("collision.internal_force")
+    nsteps = int(round(case.info["t_end"] / case.info["dt"]))
+    every = int(round(case.info["t_end"] / 10 / case.info["dt"]))
+    N, E = [], []
+    for k in range(nsteps + 1):
+        o.step("collision", 1)
+        if k % every == 0:
+            v, rho, rho0 = o.field("v"), o.field("rho"), o.field("rho0")
+            kin = 0.5 * p["m"] * np.sum(v * v, axis=1)
+            internal = 0.5 * p["m"] * p["c"] ** 2 * (rho - rho0) ** 2 / p["rho0"] ** 2
+            N.append(len(o))
+            E.append(float(np.sum(kin + internal)))
+    assert all(n == N[0] for n in N)
+    assert max(e / E[0] - 1.0 for e in E) < 1e-2
+
+
+def test_thread_count_does_not_change_results():
+    """the reference's cell list is deterministic under any interleaving (sorted insertion
+    under a lock, core.jl:26-41); so is the oracle's"""
+    case = cases.mountain_wave_2d(n_y=16.0, dom_length=40e3)
+    out = []
+    for nt in (1, 4):
+        O.set_threads(nt)
+        o = load_oracle(case)
+        o.create_cell_list()
+        o.step("wcsph", 3)
+        out.append((o.field("rho"), o.field("v"), o.cell_keys()))
+    O.set_threads(O.max_threads())
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
