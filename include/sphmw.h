@@ -154,6 +154,31 @@ int64_t sphmw_timing_report(sphmw_ctx *ctx, char *names, int64_t cap, double *ms
 /* number of kernels this library launched on ctx since creation */
 int sphmw_launch_count(sphmw_ctx *ctx, int64_t *n);
 
+/* ---- x-slab decomposition over the GPUs of one box ------------------
+ * No reference equivalent: the reference is single-process (Threads.@threads,
+ * src/core.jl:54-139).  A context created with slab_lo/slab_hi owns the global cell
+ * columns [slab_lo, slab_hi) and keeps two ghost columns per side; it carries GLOBAL
+ * particle indices so that neighbour order, and with it every FP64 sum, is the same
+ * for any number of ranks.  Per step the host calls
+ *     sphmw_step_phase(ctx, "wcsph", 0)        accelerate! + move!
+ *     sphmw_halo_pack -> transport -> sphmw_halo_unpack
+ *     sphmw_step_phase(ctx, "wcsph", 1)        cell list, density pass, force pass + kick
+ * A record is sphmw_halo_record_doubles() doubles; buffers are DEVICE pointers owned by
+ * the caller (NULL = no neighbour on that side). */
+int sphmw_step_phase(sphmw_ctx *ctx, const char *scheme, int32_t phase);
+int sphmw_halo_record_doubles(void);
+/* counts: [0] records for the left neighbour, [1] for the right, [2],[3] migrants among
+ * them, [4] particles that left the global box (dropped).  Blocks. */
+int sphmw_halo_pack(sphmw_ctx *ctx, double *dev_buf_left, double *dev_buf_right,
+                    int64_t cap_records, int64_t counts[5]);
+int sphmw_halo_unpack(sphmw_ctx *ctx, const double *dev_buf, int64_t count, int64_t n_migrants);
+int sphmw_slab_counts(sphmw_ctx *ctx, int64_t *n_resident, int64_t *n_owned);
+/* global particle index of every resident particle (physical order) */
+int sphmw_set_index(sphmw_ctx *ctx, const int64_t *global_idx, int64_t n);
+/* physical-order read-back: indices + tags (0 owned, 1 ghost), and raw fields */
+int sphmw_download_index(sphmw_ctx *ctx, int64_t *global_idx, int32_t *tag, int64_t n);
+int sphmw_download_raw(sphmw_ctx *ctx, const char *field, double *buf, int64_t n, int32_t ncomp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,14 @@ _SIGS = {
     "sphmw_timing_report": (C.c_int64, [_P, C.c_char_p, C.c_int64, C.POINTER(C.c_double),
                                         C.POINTER(C.c_int64), C.c_int32]),
     "sphmw_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "sphmw_step_phase": (C.c_int, [_P, C.c_char_p, C.c_int32]),
+    "sphmw_halo_record_doubles": (C.c_int, []),
+    "sphmw_halo_pack": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "sphmw_halo_unpack": (C.c_int, [_P, C.c_void_p, C.c_int64, C.c_int64]),
+    "sphmw_slab_counts": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "sphmw_set_index": (C.c_int, [_P, C.c_void_p, C.c_int64]),
+    "sphmw_download_index": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_int64]),
+    "sphmw_download_raw": (C.c_int, [_P, C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
 }
 
 

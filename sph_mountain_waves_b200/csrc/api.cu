@@ -256,15 +256,20 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
     c->slab_lo = cfg->slab_lo;
     c->slab_hi = cfg->slab_hi;
     if (c->slab_lo >= 0) {
-        // local grid = owned columns + one ghost column each side; keys are local
+        // local grid = owned columns + GHOST_COLS ghost columns each side; keys are local
         if (!(c->slab_hi > c->slab_lo) || c->slab_hi > g.lim[0]) {
             delete c;
             sphmw_set_error("invalid slab [%lld,%lld) for %lld columns", (long long)c->slab_lo,
                             (long long)c->slab_hi, g.lim[0]);
             return SPHMW_E_INVALID;
         }
-        long long width = (c->slab_hi - c->slab_lo) + 2;
-        g.phase[0] += c->slab_lo - 1;
+        if (c->slab_hi - c->slab_lo < 2 * GHOST_COLS) {
+            delete c;
+            sphmw_set_error("a slab must own at least %d cell columns", 2 * GHOST_COLS);
+            return SPHMW_E_INVALID;
+        }
+        long long width = (c->slab_hi - c->slab_lo) + 2 * GHOST_COLS;
+        g.phase[0] += c->slab_lo - GHOST_COLS;
         g.key_max = g.key_max / g.lim[0] * width;
         g.lim[0] = width;
     }
@@ -301,7 +306,11 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
         c->stream = c->own_stream;
         CUDA_TRY(cudaMalloc(&c->idx, sizeof(uint32_t) * c->cap));
         CUDA_TRY(cudaMalloc(&c->idx_alt, sizeof(uint32_t) * c->cap));
-        CUDA_TRY(cudaMalloc(&c->pos_of_idx, sizeof(uint32_t) * c->cap));
+        if (c->slab_lo < 0) CUDA_TRY(cudaMalloc(&c->pos_of_idx, sizeof(uint32_t) * c->cap));
+        CUDA_TRY(cudaMalloc(&c->tag, sizeof(uint32_t) * c->cap));
+        CUDA_TRY(cudaMalloc(&c->tag_alt, sizeof(uint32_t) * c->cap));
+        CUDA_TRY(cudaMalloc(&c->halo_counters, sizeof(uint32_t) * 8));
+        CUDA_TRY(cudaMallocHost(&c->h_halo_counters, sizeof(uint32_t) * 8));
         CUDA_TRY(cudaMalloc(&c->key, sizeof(uint32_t) * c->cap));
         CUDA_TRY(cudaMalloc(&c->rank, sizeof(uint32_t) * c->cap));
         CUDA_TRY(cudaMalloc(&c->src, sizeof(uint32_t) * c->cap));
@@ -333,6 +342,8 @@ extern "C" int sphmw_destroy(sphmw_ctx *c) {
         cudaFree(c->alt.s[s]);
     }
     cudaFree(c->idx); cudaFree(c->idx_alt); cudaFree(c->pos_of_idx);
+    cudaFree(c->tag); cudaFree(c->tag_alt); cudaFree(c->halo_counters);
+    if (c->h_halo_counters) cudaFreeHost(c->h_halo_counters);
     cudaFree(c->key); cudaFree(c->rank); cudaFree(c->src);
     cudaFree(c->cell_start); cudaFree(c->scan_tmp); cudaFree(c->removed);
     cudaFree(c->mv_old); cudaFree(c->mv_new);
@@ -375,11 +386,12 @@ extern "C" int sphmw_key_tables(sphmw_ctx *c, int64_t phase[3], int64_t lim[3], 
 // ---------------------------------------------------------------------------
 // particle count and field storage
 // ---------------------------------------------------------------------------
-__global__ void k_iota(uint32_t *a, uint32_t *b, int64_t first, int64_t n) {
+__global__ void k_iota(uint32_t *a, uint32_t *b, uint32_t *tag, int64_t first, int64_t n) {
     int64_t i = first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) {
         a[i] = (uint32_t)i;
-        b[i] = (uint32_t)i;
+        if (b) b[i] = (uint32_t)i;
+        tag[i] = TAG_OWNED;
     }
 }
 
@@ -405,7 +417,7 @@ extern "C" int sphmw_resize(sphmw_ctx *c, int64_t n) {
         int64_t m = n - c->n;
         {
             TIMED(c, "iota");
-            k_iota<<<grid_for(m, 256), 256, 0, c->stream>>>(c->idx, c->pos_of_idx, c->n, n);
+            k_iota<<<grid_for(m, 256), 256, 0, c->stream>>>(c->idx, c->pos_of_idx, c->tag, c->n, n);
         }
         for (int s = 0; s < NSLOT; ++s)
             if (c->allocated[s])
@@ -417,6 +429,7 @@ extern "C" int sphmw_resize(sphmw_ctx *c, int64_t n) {
         }
     }
     c->n = n;
+    c->n_owned = n;
     c->cell_list_valid = false;
     return SPHMW_OK;
 }
@@ -657,9 +670,15 @@ extern "C" int sphmw_step(sphmw_ctx *c, const char *scheme, int32_t nsteps) {
     CUDA_TRY(cudaSetDevice(c->device));
     return sphmw_step_scheme(c, scheme, nsteps);
 }
+extern "C" int sphmw_step_phase(sphmw_ctx *c, const char *scheme, int32_t phase) {
+    if (!c || !scheme) { sphmw_set_error("bad argument"); return SPHMW_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    return sphmw_step_scheme_phase(c, scheme, phase);
+}
 extern "C" int sphmw_pairs_dump(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n) {
     if (!c || !n) return SPHMW_E_INVALID;
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->slab_lo >= 0) { sphmw_set_error("pairs_dump is a whole-domain test hook"); return SPHMW_E_STATE; }
     return sphmw_dump_pairs(c, pi, pj, cap, n);
 }
 extern "C" int sphmw_count_pairs(sphmw_ctx *c, int32_t enable) {

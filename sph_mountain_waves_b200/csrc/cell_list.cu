@@ -21,12 +21,41 @@
 // ---------------------------------------------------------------------------
 // keys + out-of-box detection
 // ---------------------------------------------------------------------------
-template <int DIM>
+// SLAB: ghosts of the previous exchange and particles that left the local columns are
+// dropped (tag == TAG_DEAD or column out of range); they are only counted, with one atomic
+// per warp, because a slab drops two ghost sheets per side every step.
+template <int DIM, bool SLAB>
 __global__ void k_keys(const double *__restrict__ x0, const double *__restrict__ x1,
                        const double *__restrict__ x2, int64_t n, Grid g,
                        uint32_t *__restrict__ key, uint32_t *__restrict__ removed,
-                       uint32_t removed_cap, const uint32_t *__restrict__ idx) {
+                       uint32_t removed_cap, const uint32_t *__restrict__ idx,
+                       const uint32_t *__restrict__ tag) {
     int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (SLAB) {
+        bool live = pos < n;
+        bool dead = false;
+        uint32_t k = 0;
+        if (live) {
+            double x = x0[pos], y = x1[pos], z = DIM == 3 ? x2[pos] : 0.0;
+            bool inside = tag[pos] != TAG_DEAD && g.box[0] <= x && x <= g.box[3] && g.box[1] <= y &&
+                          y <= g.box[4] && g.box[2] <= z && z <= g.box[5];
+            if (inside) {
+                long long i = (long long)floor(x / g.h) - g.phase[0];
+                long long j = (long long)floor(y / g.h) - g.phase[1];
+                long long kk = DIM == 3 ? (long long)floor(z / g.h) - g.phase[2] : 0;
+                if (i < 0 || i >= g.lim[0]) inside = false;
+                k = (uint32_t)(i + g.lim[0] * (j + g.lim[1] * kk));
+            }
+            if (!inside) {
+                k = (uint32_t)g.key_max;
+                dead = true;
+            }
+            key[pos] = k;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, dead);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&removed[0], (uint32_t)__popc(m));
+        return;
+    }
     if (pos >= n) return;
     double x = x0[pos], y = x1[pos], z = DIM == 3 ? x2[pos] : 0.0;
     // geometry.jl:24-30 — closed intervals; NaN fails every comparison
@@ -192,14 +221,16 @@ struct GatherList {
 __global__ void k_gather(GatherList gl, const uint32_t *__restrict__ src,
                          const uint32_t *__restrict__ idx, uint32_t *__restrict__ idx_out,
                          uint32_t *__restrict__ pos_of_idx, const uint32_t *__restrict__ key,
-                         uint32_t *__restrict__ key_out, int64_t n_new) {
+                         uint32_t *__restrict__ key_out, const uint32_t *__restrict__ tag,
+                         uint32_t *__restrict__ tag_out, int64_t n_new) {
     int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (slot >= n_new) return;
     uint32_t s = src[slot];
     uint32_t id = idx[s];
     idx_out[slot] = id;
-    pos_of_idx[id] = (uint32_t)slot;
+    if (pos_of_idx) pos_of_idx[id] = (uint32_t)slot;
     key_out[slot] = key[s];
+    tag_out[slot] = tag[s];
     for (int f = 0; f < gl.count; ++f) gl.to[f][slot] = gl.from[f][s];
 }
 
@@ -258,14 +289,15 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     CUDA_TRY(cudaMemsetAsync(c->removed, 0, sizeof(uint32_t), c->stream));
     {
         TIMED(c, "cell_keys");
-        if (g.dim == 2)
-            k_keys<2><<<grid_for(n, 256), 256, 0, c->stream>>>(
-                c->cur.s[S_X0], c->cur.s[S_X1], nullptr, n, g, c->key, c->removed,
-                (uint32_t)c->removed_cap, c->idx);
-        else
-            k_keys<3><<<grid_for(n, 256), 256, 0, c->stream>>>(
-                c->cur.s[S_X0], c->cur.s[S_X1], c->cur.s[S_X2], n, g, c->key, c->removed,
-                (uint32_t)c->removed_cap, c->idx);
+        const bool slab = c->slab_lo >= 0;
+        const unsigned gr = grid_for(n, 256);
+#define KEYS_ARGS c->cur.s[S_X0], c->cur.s[S_X1], c->cur.s[S_X2], n, g, c->key, c->removed, \
+                  (uint32_t)c->removed_cap, c->idx, c->tag
+        if (g.dim == 2 && !slab) k_keys<2, false><<<gr, 256, 0, c->stream>>>(KEYS_ARGS);
+        else if (g.dim == 2) k_keys<2, true><<<gr, 256, 0, c->stream>>>(KEYS_ARGS);
+        else if (!slab) k_keys<3, false><<<gr, 256, 0, c->stream>>>(KEYS_ARGS);
+        else k_keys<3, true><<<gr, 256, 0, c->stream>>>(KEYS_ARGS);
+#undef KEYS_ARGS
     }
     CUDA_TRY(cudaMemcpyAsync(c->h_removed, c->removed, sizeof(uint32_t), cudaMemcpyDeviceToHost,
                              c->stream));
@@ -282,7 +314,7 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     const int64_t k = c->h_removed[0];
-    if (k > 0) {
+    if (k > 0 && c->slab_lo < 0) {
         if (k > c->removed_cap) {
             sphmw_set_error("more than %lld particles left the domain in one step",
                             (long long)c->removed_cap);
@@ -332,13 +364,16 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     if (n_new > 0) {
         TIMED(c, "cell_gather");
         k_gather<<<grid_for(n_new, 256), 256, 0, c->stream>>>(gl, c->src, c->idx, c->idx_alt,
-                                                              c->pos_of_idx, c->key, c->rank, n_new);
+                                                              c->pos_of_idx, c->key, c->rank, c->tag,
+                                                              c->tag_alt, n_new);
     }
     CUDA_TRY(cudaGetLastError());
     for (int f = 0; f < gl.count; ++f) std::swap(c->cur.s[gathered[f]], c->alt.s[gathered[f]]);
     std::swap(c->idx, c->idx_alt);
     std::swap(c->key, c->rank);
+    std::swap(c->tag, c->tag_alt);
     c->n = n_new;
+    if (c->slab_lo < 0) c->n_owned = n_new;
     c->cell_list_valid = true;
     if (n_alive) *n_alive = n_new;
     return SPHMW_OK;

@@ -1,0 +1,258 @@
+// x-slab halo exchange, device side (the reference has no distributed path).
+//
+// A rank owns the global cell columns [slab_lo, slab_hi) and keeps GHOST_COLS = 2 ghost
+// columns on each side.  Once per step, after the drift, k_halo_pack classifies every
+// resident particle:
+//   ghost of the previous exchange      -> dropped
+//   owned, left the global box          -> dropped (counted as lost)
+//   owned, now in a ghost column        -> MIGRANT record to that neighbour; kept here as a ghost
+//   owned, in one of the two outermost owned columns -> GHOST record (a copy) to that neighbour
+// The host moves the records between x-adjacent ranks (NCCL send/recv through
+// torch.distributed, or any transport), k_halo_unpack appends what arrives, and the
+// ordinary cell-list build sorts owned and ghost particles together.  Because the second
+// ghost column makes the first one's density sum complete, ghost densities are recomputed
+// locally and no second exchange is needed before the force pass.
+#include <string.h>
+
+#include "sphmw_internal.h"
+
+template <int DIM>
+__global__ void k_halo_pack(Fields f, const uint32_t *__restrict__ idx, uint32_t *__restrict__ tag,
+                            int64_t n, Grid g, int has_left, int has_right, double *buf_l,
+                            double *buf_r, uint32_t cap, uint32_t *counters) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t t = tag[p];
+    if (t != TAG_OWNED) {
+        tag[p] = TAG_DEAD;
+        return;
+    }
+    double x = f.s[S_X0][p], y = f.s[S_X1][p], z = DIM == 3 ? f.s[S_X2][p] : 0.0;
+    bool inside = g.box[0] <= x && x <= g.box[3] && g.box[1] <= y && y <= g.box[4] &&
+                  g.box[2] <= z && z <= g.box[5];
+    if (!inside) {
+        tag[p] = TAG_DEAD;
+        atomicAdd(&counters[4], 1u);
+        return;
+    }
+    const long long W = g.lim[0];
+    long long i = (long long)floor(x / g.h) - g.phase[0];  // local column
+    int to_l = 0, to_r = 0;
+    double kind = HALO_KIND_GHOST;
+    if (i < GHOST_COLS) {
+        to_l = 1;
+        kind = HALO_KIND_MIGRANT;
+        tag[p] = (i >= 0 && has_left) ? TAG_GHOST : TAG_DEAD;
+    } else if (i >= W - GHOST_COLS) {
+        to_r = 1;
+        kind = HALO_KIND_MIGRANT;
+        tag[p] = (i < W && has_right) ? TAG_GHOST : TAG_DEAD;
+    } else {
+        to_l = i < 2 * GHOST_COLS;
+        to_r = i >= W - 2 * GHOST_COLS;
+    }
+    to_l = to_l && has_left;
+    to_r = to_r && has_right;
+    if (!to_l && !to_r) return;
+    double rec[HALO_RECORD];
+    rec[0] = x;
+    rec[1] = y;
+    rec[2] = z;
+    rec[3] = f.s[S_V0][p];
+    rec[4] = f.s[S_V1][p];
+    rec[5] = DIM == 3 ? f.s[S_V2][p] : 0.0;
+    rec[6] = f.s[S_M][p];
+    rec[7] = f.s[S_H][p];
+    rec[8] = f.s[S_RHO][p];
+    rec[9] = f.s[S_RHO_P][p];
+    rec[10] = f.s[S_TYPE][p];
+    rec[11] = (double)idx[p];
+    rec[12] = kind;
+    if (to_l) {
+        uint32_t s = atomicAdd(&counters[0], 1u);
+        if (kind == HALO_KIND_MIGRANT) atomicAdd(&counters[2], 1u);
+        if (s < cap)
+            for (int k = 0; k < HALO_RECORD; ++k) buf_l[(size_t)s * HALO_RECORD + k] = rec[k];
+    }
+    if (to_r) {
+        uint32_t s = atomicAdd(&counters[1], 1u);
+        if (kind == HALO_KIND_MIGRANT) atomicAdd(&counters[3], 1u);
+        if (s < cap)
+            for (int k = 0; k < HALO_RECORD; ++k) buf_r[(size_t)s * HALO_RECORD + k] = rec[k];
+    }
+}
+
+template <int DIM>
+__global__ void k_halo_unpack(Fields f, uint32_t *__restrict__ idx, uint32_t *__restrict__ tag,
+                              int64_t first, const double *__restrict__ buf, int64_t cnt) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const double *rec = buf + (size_t)t * HALO_RECORD;
+    int64_t p = first + t;
+    f.s[S_X0][p] = rec[0];
+    f.s[S_X1][p] = rec[1];
+    if (DIM == 3) f.s[S_X2][p] = rec[2];
+    f.s[S_V0][p] = rec[3];
+    f.s[S_V1][p] = rec[4];
+    if (DIM == 3) f.s[S_V2][p] = rec[5];
+    f.s[S_M][p] = rec[6];
+    f.s[S_H][p] = rec[7];
+    f.s[S_RHO][p] = rec[8];
+    f.s[S_RHO_P][p] = rec[9];
+    f.s[S_TYPE][p] = rec[10];
+    idx[p] = (uint32_t)rec[11];
+    tag[p] = rec[12] == HALO_KIND_MIGRANT ? TAG_OWNED : TAG_GHOST;
+}
+
+static const int CARRIED[] = {S_X0, S_X1, S_X2, S_V0, S_V1, S_V2, S_M, S_H, S_RHO, S_RHO_P, S_TYPE};
+
+static int ensure_carried(sphmw_ctx *c) {
+    for (int s : CARRIED) {
+        if (c->grid.dim == 2 && (s == S_X2 || s == S_V2)) continue;
+        TRY(sphmw_ensure_slot(c, s));
+        if (c->stale[s]) { sphmw_set_error("halo: carried field is stale"); return SPHMW_E_STATE; }
+    }
+    return SPHMW_OK;
+}
+
+extern "C" int sphmw_halo_record_doubles(void) { return HALO_RECORD; }
+
+// counts[0..4] = records to the left, to the right, migrants among them (left, right), lost.
+// Blocks (reads the counters back).
+extern "C" int sphmw_halo_pack(sphmw_ctx *c, double *dev_buf_left, double *dev_buf_right,
+                               int64_t cap_records, int64_t counts[5]) {
+    if (!c || !counts) { sphmw_set_error("null argument"); return SPHMW_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->slab_lo < 0) { sphmw_set_error("halo_pack: context has no slab"); return SPHMW_E_STATE; }
+    TRY(ensure_carried(c));
+    const int has_left = dev_buf_left != nullptr, has_right = dev_buf_right != nullptr;
+    CUDA_TRY(cudaMemsetAsync(c->halo_counters, 0, sizeof(uint32_t) * 8, c->stream));
+    if (c->n > 0) {
+        TIMED(c, "halo_pack");
+        if (c->grid.dim == 2)
+            k_halo_pack<2><<<grid_for(c->n, 256), 256, 0, c->stream>>>(
+                c->cur, c->idx, c->tag, c->n, c->grid, has_left, has_right, dev_buf_left,
+                dev_buf_right, (uint32_t)cap_records, c->halo_counters);
+        else
+            k_halo_pack<3><<<grid_for(c->n, 256), 256, 0, c->stream>>>(
+                c->cur, c->idx, c->tag, c->n, c->grid, has_left, has_right, dev_buf_left,
+                dev_buf_right, (uint32_t)cap_records, c->halo_counters);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_halo_counters, c->halo_counters, sizeof(uint32_t) * 8,
+                             cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 5; ++k) counts[k] = c->h_halo_counters[k];
+    if (counts[0] > cap_records || counts[1] > cap_records) {
+        sphmw_set_error("halo buffer too small: %lld/%lld records for capacity %lld",
+                        (long long)counts[0], (long long)counts[1], (long long)cap_records);
+        return SPHMW_E_CAPACITY;
+    }
+    c->n_owned -= counts[2] + counts[3] + counts[4];
+    c->cell_list_valid = false;
+    return SPHMW_OK;
+}
+
+// Appends `count` records; `n_migrants` of them (the sender's count) become owned.
+extern "C" int sphmw_halo_unpack(sphmw_ctx *c, const double *dev_buf, int64_t count,
+                                 int64_t n_migrants) {
+    if (!c) return SPHMW_E_INVALID;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->slab_lo < 0) { sphmw_set_error("halo_unpack: context has no slab"); return SPHMW_E_STATE; }
+    if (count <= 0) return SPHMW_OK;
+    if (c->n + count > c->cap) {
+        sphmw_set_error("halo_unpack: %lld + %lld particles exceed capacity %lld", (long long)c->n,
+                        (long long)count, (long long)c->cap);
+        return SPHMW_E_CAPACITY;
+    }
+    TRY(ensure_carried(c));
+    {
+        TIMED(c, "halo_unpack");
+        if (c->grid.dim == 2)
+            k_halo_unpack<2><<<grid_for(count, 256), 256, 0, c->stream>>>(
+                c->cur, c->idx, c->tag, c->n, dev_buf, count);
+        else
+            k_halo_unpack<3><<<grid_for(count, 256), 256, 0, c->stream>>>(
+                c->cur, c->idx, c->tag, c->n, dev_buf, count);
+        CUDA_TRY(cudaGetLastError());
+    }
+    c->n += count;
+    c->n_owned += n_migrants;
+    c->cell_list_valid = false;
+    return SPHMW_OK;
+}
+
+extern "C" int sphmw_slab_counts(sphmw_ctx *c, int64_t *n_resident, int64_t *n_owned) {
+    if (!c) return SPHMW_E_INVALID;
+    if (n_resident) *n_resident = c->n;
+    if (n_owned) *n_owned = c->n_owned;
+    return SPHMW_OK;
+}
+
+// ---- physical-order access (slab contexts carry GLOBAL particle indices, so the
+// index-ordered upload/download of whole-domain contexts does not apply) -----------
+__global__ void k_set_index(uint32_t *idx, const long long *g, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = (uint32_t)g[i];
+}
+__global__ void k_get_index(const uint32_t *idx, const uint32_t *tag, long long *g, int *t, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        g[i] = idx[i];
+        t[i] = (int)tag[i];
+    }
+}
+
+// global index of every resident particle, in the current physical order
+extern "C" int sphmw_set_index(sphmw_ctx *c, const int64_t *global_idx, int64_t n) {
+    if (!c || !global_idx) return SPHMW_E_INVALID;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->slab_lo < 0) { sphmw_set_error("set_index: context has no slab"); return SPHMW_E_STATE; }
+    if (n != c->n) { sphmw_set_error("set_index: n mismatch"); return SPHMW_E_INVALID; }
+    if (n == 0) return SPHMW_OK;
+    long long *d = (long long *)c->staging;
+    CUDA_TRY(cudaMemcpyAsync(d, global_idx, sizeof(int64_t) * n, cudaMemcpyDefault, c->stream));
+    k_set_index<<<grid_for(n, 256), 256, 0, c->stream>>>(c->idx, d, n);
+    c->launches += 1;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SPHMW_OK;
+}
+
+extern "C" int sphmw_download_index(sphmw_ctx *c, int64_t *global_idx, int32_t *tag, int64_t n) {
+    if (!c || !global_idx || !tag) return SPHMW_E_INVALID;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n != c->n) { sphmw_set_error("download_index: n mismatch"); return SPHMW_E_INVALID; }
+    if (n == 0) return SPHMW_OK;
+    long long *d = (long long *)c->staging;
+    int *dt = (int *)(c->staging + c->cap);
+    k_get_index<<<grid_for(n, 256), 256, 0, c->stream>>>(c->idx, c->tag, d, dt, n);
+    c->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(global_idx, d, sizeof(int64_t) * n, cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(tag, dt, sizeof(int32_t) * n, cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SPHMW_OK;
+}
+
+// one scalar component in physical order (component-major for vectors)
+extern "C" int sphmw_download_raw(sphmw_ctx *c, const char *field, double *buf, int64_t n,
+                                  int32_t ncomp) {
+    if (!c || !field || !buf) return SPHMW_E_INVALID;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const FieldDesc *d = sphmw_find_field(field);
+    if (!d) { sphmw_set_error("Variable %s does not exist!", field); return SPHMW_E_UNKNOWN_FIELD; }
+    if (ncomp != d->ncomp || n != c->n) { sphmw_set_error("download_raw: shape mismatch"); return SPHMW_E_INVALID; }
+    for (int k = 0; k < ncomp; ++k) {
+        int slot = d->slot + k;
+        if (c->allocated[slot] && c->stale[slot]) TRY(sphmw_materialize(c, slot));
+        if (!c->allocated[slot] || (c->grid.dim == 2 && ncomp == 3 && k == 2)) {
+            CUDA_TRY(cudaMemsetAsync(c->staging, 0, sizeof(double) * n, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(buf + (int64_t)k * n, c->staging, sizeof(double) * n,
+                                     cudaMemcpyDefault, c->stream));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(buf + (int64_t)k * n, c->cur.s[slot], sizeof(double) * n,
+                                     cudaMemcpyDefault, c->stream));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SPHMW_OK;
+}

@@ -347,8 +347,14 @@ __global__ void __launch_bounds__(256) k_unary(Fields f, Params c, int64_t n) {
 #define PF(slot) f.s[slot][p]
 #define QF(slot) f.s[slot][q]
 
+// particles outside the column range a pass covers (slab mode: ghost columns) are skipped
+struct PairOpBase {
+    template <int DIM>
+    static __device__ void skip(const Fields &, const Fields &, int64_t) {}
+};
+
 // compute_density!  wcsph_perturbed_witch.jl:226-228
-struct B_wcsph_density {
+struct B_wcsph_density : PairOpBase {
     double rho, hp;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &, int64_t p) {
@@ -372,7 +378,7 @@ struct MomentumState {
     double v0, v1, v2, hp, rho, prho, Pp, P;
 };
 
-struct B_wcsph_momentum {
+struct B_wcsph_momentum : PairOpBase {
     MomentumState s;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &c, int64_t p) {
@@ -428,7 +434,7 @@ struct B_wcsph_momentum {
 };
 
 // compute_pressure! (binary)  hopkins_perturbed_witch.jl:205-208
-struct B_hopkins_pressure {
+struct B_hopkins_pressure : PairOpBase {
     double P, hp;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &, int64_t p) {
@@ -448,7 +454,7 @@ struct B_hopkins_pressure {
 };
 
 // balance_of_momentum!  hopkins_total_witch.jl:233-264
-struct B_ht_momentum {
+struct B_ht_momentum : PairOpBase {
     MomentumState s;
     double A;
     template <int DIM>
@@ -510,7 +516,7 @@ struct B_ht_momentum {
 };
 
 // balance_of_mass!  collapse_dry.jl:112-115 (fixed h = kh, fixed mass m)
-struct B_dam_mass {
+struct B_dam_mass : PairOpBase {
     double drho, v0, v1, v2, rho;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &, int64_t p) {
@@ -534,7 +540,7 @@ struct B_dam_mass {
     }
 };
 // internal_force!  collapse_dry.jl:135-141
-struct B_dam_force {
+struct B_dam_force : PairOpBase {
     double dv0, dv1, dv2, v0, v1, v2, P, rho;
     bool fluid;
     template <int DIM>
@@ -573,7 +579,7 @@ struct B_dam_force {
 };
 // find_rho! / find_rho0!  test_collision_2d.jl:66-72
 template <int SLOT>
-struct B_col_rho {
+struct B_col_rho : PairOpBase {
     double acc;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &, int64_t p) { acc = PF(SLOT); }
@@ -588,7 +594,7 @@ struct B_col_rho {
     }
 };
 // internal_force!  test_collision_2d.jl:78-81
-struct B_col_force {
+struct B_col_force : PairOpBase {
     double dv0, dv1, dv2, P;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &, int64_t p) {
@@ -614,7 +620,7 @@ struct B_col_force {
     }
 };
 // accumulate_rho_pack!  new_packing.jl:11-15
-struct B_pack_rho {
+struct B_pack_rho : PairOpBase {
     double rho, hp;
     bool fluid;
     template <int DIM>
@@ -634,7 +640,7 @@ struct B_pack_rho {
     }
 };
 // balance_of_momentum_pack!  new_packing.jl:23-46
-struct B_pack_momentum {
+struct B_pack_momentum : PairOpBase {
     double dv0, dv1, dv2, hp, rho_i, Pi, y;
     bool fluid;
     template <int DIM>
@@ -672,7 +678,7 @@ struct B_pack_momentum {
 // reset_density! + compute_density! + finalize_density! + update_smoothing! +
 // compute_pressure!  (wcsph_perturbed_witch.jl:316-323) in one pass, plus the
 // per-particle invariants of the pair force.
-struct B_wcsph_density_fused {
+struct B_wcsph_density_fused : PairOpBase {
     double rho, hp;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &, int64_t p) {
@@ -710,8 +716,15 @@ struct B_wcsph_density_fused {
 // balance_of_momentum! + accelerate!  (wcsph_perturbed_witch.jl:330-331).
 // Dv starts at 0 (accelerate! zeroed it) and is never stored; the new velocity
 // goes to the `out` field set because other threads still read the old one.
-struct B_wcsph_momentum_fused {
+struct B_wcsph_momentum_fused : PairOpBase {
     double dv0, dv1, dv2, v0, v1, v2, hp, prho, pr2, cs;
+    // the velocity is double-buffered: a skipped (ghost) particle carries its value over
+    template <int DIM>
+    static __device__ void skip(const Fields &f, const Fields &out, int64_t p) {
+        out.s[S_V0][p] = f.s[S_V0][p];
+        out.s[S_V1][p] = f.s[S_V1][p];
+        if (DIM == 3) out.s[S_V2][p] = f.s[S_V2][p];
+    }
     template <int DIM>
     __device__ void init(const Fields &f, const Params &c, int64_t p) {
         dv0 = dv1 = dv2 = 0.0;
@@ -782,13 +795,20 @@ template <int DIM, class Op>
 __global__ void __launch_bounds__(128)
 k_binary(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
          const uint32_t *__restrict__ cell_start, int64_t n, int self,
-         unsigned long long *pair_counter) {
+         unsigned long long *pair_counter, int col_lo, int col_hi) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
+    const long long k0 = key[p];
+    if (col_lo > 0) {  // slab mode: only the columns [col_lo, col_hi] are evaluated
+        int col = (int)(k0 % g.lim[0]);
+        if (col < col_lo || col > col_hi) {
+            Op::template skip<DIM>(f, out, p);
+            return;
+        }
+    }
     Op op;
     op.template init<DIM>(f, prm, p);
     const double px = f.s[S_X0][p], py = f.s[S_X1][p], pz = DIM == 3 ? f.s[S_X2][p] : 0.0;
-    const long long k0 = key[p];
     unsigned long long cnt = 0;
     for (int d = 0; d < g.ndiff; ++d) {
         long long nk = k0 + g.key_diff[d];
@@ -814,8 +834,9 @@ k_binary(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ 
     if (self) op.template pair<DIM>(f, prm, p, p, 0.0, 0.0, 0.0, 0.0);  // core.jl:155-157
     op.template finish<DIM>(f, out, prm, p);
     if (pair_counter) {
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(__activemask(), cnt, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(pair_counter, cnt);
+        unsigned m = __activemask();
+        unsigned tot = __reduce_add_sync(m, (unsigned)cnt);
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(pair_counter, (unsigned long long)tot);
     }
 }
 
@@ -978,8 +999,11 @@ static int run_unary(sphmw_ctx *c, const char *name) {
     return SPHMW_OK;
 }
 
+// ghost_depth: how many ghost columns (from the owned range outwards) the pass must also
+// evaluate in slab mode; ignored for whole-domain contexts
 template <class Op>
-static int run_binary(sphmw_ctx *c, const char *name, int self, const Fields &out) {
+static int run_binary(sphmw_ctx *c, const char *name, int self, const Fields &out,
+                      int ghost_depth = GHOST_COLS) {
     if (!c->cell_list_valid) {
         sphmw_set_error("%s: create_cell_list must be called after positions change", name);
         return SPHMW_E_STATE;
@@ -987,13 +1011,18 @@ static int run_binary(sphmw_ctx *c, const char *name, int self, const Fields &ou
     if (c->n == 0) return SPHMW_OK;
     unsigned long long *pc = c->count_pairs ? c->d_counters : nullptr;
     if (pc) CUDA_TRY(cudaMemsetAsync(pc, 0, sizeof(unsigned long long), c->stream));
+    int col_lo = 0, col_hi = (int)c->grid.lim[0] - 1;
+    if (c->slab_lo >= 0 && ghost_depth < GHOST_COLS) {
+        col_lo = GHOST_COLS - ghost_depth;
+        col_hi = (int)c->grid.lim[0] - 1 - col_lo;
+    }
     TIMED(c, name);
     if (c->grid.dim == 2)
         k_binary<2, Op><<<grid_for(c->n, 128), 128, 0, c->stream>>>(
-            c->cur, out, c->prm, c->grid, c->key, c->cell_start, c->n, self, pc);
+            c->cur, out, c->prm, c->grid, c->key, c->cell_start, c->n, self, pc, col_lo, col_hi);
     else
         k_binary<3, Op><<<grid_for(c->n, 128), 128, 0, c->stream>>>(
-            c->cur, out, c->prm, c->grid, c->key, c->cell_start, c->n, self, pc);
+            c->cur, out, c->prm, c->grid, c->key, c->cell_start, c->n, self, pc, col_lo, col_hi);
     CUDA_TRY(cudaGetLastError());
     return SPHMW_OK;
 }
@@ -1150,7 +1179,7 @@ static int apply_seq(sphmw_ctx *c, std::initializer_list<const char *> ops) {
 // wcsph_perturbed_witch.jl:309-332 with the unary sweeps fused into the two pair
 // passes; the redundant second create_cell_list! (:320, positions unchanged —
 // SURVEY quirk 4) is skipped.
-static int step_wcsph_fused(sphmw_ctx *c) {
+static int step_wcsph_fused_pre(sphmw_ctx *c) {
     // accelerate! + move!  (:311-312)
     TRY(need_slots(c, SL(S_TYPE, S_RHO_P, S_RHO, S_X0, S_V0, S_M, S_H), SL(S_V0, S_X0)));
     if (!c->dv_zero) {
@@ -1168,23 +1197,47 @@ static int step_wcsph_fused(sphmw_ctx *c) {
     // diagnostics and per-step derived fields need not travel through the reorder
     for (int s : {S_RHO_BG, S_P_BG, S_P_P, S_P, S_T_P, S_T, S_TH_BG, S_TH_P, S_TH, S_PR2, S_CS})
         if (c->allocated[s]) c->stale[s] = true;
+    return SPHMW_OK;
+}
+
+// slab mode: the halo exchange sits between the two halves (after the drift, before the sort)
+static int step_wcsph_fused_post(sphmw_ctx *c) {
     TRY(sphmw_build_cell_list(c, nullptr));  // :313
     // :316-323
     for (int s : {S_RHO_BG, S_RHO_P, S_RHO, S_P_BG, S_P_P, S_P, S_PR2, S_CS}) {
         TRY(sphmw_ensure_slot(c, s));
         c->stale[s] = false;
     }
-    TRY((run_binary<B_wcsph_density_fused>(c, "wcsph.density_fused", 0, c->cur)));
+    // owned columns + the first ghost column (its sums are complete thanks to the second)
+    TRY((run_binary<B_wcsph_density_fused>(c, "wcsph.density_fused", 0, c->cur, 1)));
     // :326-327 find_temperature!/find_pot_temp! are diagnostics: left stale, rebuilt on demand
-    // :330-331
-    TRY((run_binary<B_wcsph_momentum_fused>(c, "wcsph.momentum_fused", 0, c->alt)));
+    // :330-331 — owned columns only
+    TRY(sphmw_ensure_slot(c, S_V0));
+    TRY((run_binary<B_wcsph_momentum_fused>(c, "wcsph.momentum_fused", 0, c->alt, 0)));
     std::swap(c->cur.s[S_V0], c->alt.s[S_V0]);
     std::swap(c->cur.s[S_V1], c->alt.s[S_V1]);
     if (c->grid.dim == 3) std::swap(c->cur.s[S_V2], c->alt.s[S_V2]);
     return SPHMW_OK;
 }
 
+static int step_wcsph_fused(sphmw_ctx *c) {
+    TRY(step_wcsph_fused_pre(c));
+    return step_wcsph_fused_post(c);
+}
+
+int sphmw_step_scheme_phase(sphmw_ctx *c, const char *scheme, int phase) {
+    if (strcmp(scheme, "wcsph")) {
+        sphmw_set_error("step_phase: only the fused 'wcsph' scheme runs on slabs");
+        return SPHMW_E_UNSUPPORTED_OP;
+    }
+    return phase == 0 ? step_wcsph_fused_pre(c) : step_wcsph_fused_post(c);
+}
+
 int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps) {
+    if (c->slab_lo >= 0 && nsteps > 0) {
+        sphmw_set_error("step: a slab context is stepped with step_phase around the halo exchange");
+        return SPHMW_E_STATE;
+    }
     for (int k = 0; k < nsteps; ++k) {
         if (!strcmp(scheme, "wcsph")) {
             TRY(step_wcsph_fused(c));

@@ -62,6 +62,15 @@ struct Grid {
     int dim;
 };
 
+// slab (multi-GPU) bookkeeping: local column c <-> global column slab_lo - GHOST_COLS + c
+#define GHOST_COLS 2
+#define TAG_OWNED 0u
+#define TAG_GHOST 1u
+#define TAG_DEAD 2u
+#define HALO_RECORD 13  // x0 x1 x2 v0 v1 v2 m h rho rho_p type idx kind
+#define HALO_KIND_MIGRANT 0.0
+#define HALO_KIND_GHOST 1.0
+
 struct TimingEntry {
     int name_id;
     cudaEvent_t a, b;
@@ -85,7 +94,12 @@ struct sphmw_ctx {
     bool dv_zero = true;     // Dv is known to be all-zero (never written since accelerate!)
 
     uint32_t *idx = nullptr, *idx_alt = nullptr;  // reference particle index of each position
-    uint32_t *pos_of_idx = nullptr;               // inverse map
+    uint32_t *pos_of_idx = nullptr;               // inverse map (whole-domain contexts only)
+    uint32_t *tag = nullptr, *tag_alt = nullptr;  // TAG_OWNED / TAG_GHOST / TAG_DEAD per position
+    int64_t n_owned = 0;                          // slab mode: resident particles this rank owns
+    uint32_t *halo_counters = nullptr;            // device: [0] left records [1] right records
+                                                  // [2] left migrants [3] right migrants [4] lost
+    uint32_t *h_halo_counters = nullptr;          // pinned mirror
     uint32_t *key = nullptr;         // cell key per position (key_max = dead bucket)
     uint32_t *rank = nullptr;        // arrival rank inside the cell
     uint32_t *src = nullptr;         // new position -> old position
@@ -154,6 +168,7 @@ int sphmw_ensure_slot(sphmw_ctx *c, int slot);
 // implemented in pair_ops.cu
 int sphmw_apply_named(sphmw_ctx *c, const char *op, int self);
 int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps);
+int sphmw_step_scheme_phase(sphmw_ctx *c, const char *scheme, int phase);
 int sphmw_materialize(sphmw_ctx *c, int slot);
 int64_t sphmw_list_ops(char *buf, int64_t cap);
 int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n);

@@ -2,26 +2,41 @@
 (one process per GPU; SURVEY.md §8e — the reference has no distributed path).
 
 Rank g owns the cell columns [X_g, X_{g+1}) of the global neighbour grid and keeps
-two ghost columns on each side.  Every step one halo exchange (torch.distributed
-send/recv over NCCL/NVLink) moves, between x-adjacent ranks only,
-  * migrants — particles whose cell column left the slab (full carried state), and
+two ghost columns on each side.  Every step ONE halo exchange (torch.distributed
+send/recv: NCCL over NVLink on the GPUs, gloo in the CPU tests) moves, between
+x-adjacent ranks only,
+  * migrants — particles whose cell column left the slab (the carried state), and
   * ghosts   — copies of the particles in the two outermost owned columns.
 Ghost density is recomputed locally (the second ghost column makes the first one's
 sums complete), so there is no second exchange before the force pass, and because
-neighbours are visited in (cell, global index) order the FP64 sums are bit-identical
-for any number of ranks.
+neighbours are visited in (cell, GLOBAL particle index) order the FP64 sums are
+bit-identical for any number of ranks.
+
+The transport (`exchange`) and the partition planning (`split_columns`, `plan_slab`,
+`global_indices`) are backend-neutral host logic; what packs, unpacks and computes is a
+backend: `LibSlabBackend` (libsphmw, CUDA) in production, an oracle-driven one in
+tests/test_slabs_gloo.py.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Tuple
 
 import numpy as np
 
-from . import cases
+from . import _capi, cases
+from ._capi import check
 from .schemes import wcsph_perturbed_witch as wpw
 
+GHOST_COLS = 2
+RECORD = 13  # x0 x1 x2 v0 v1 v2 m h rho rho_p type idx kind
+KIND_MIGRANT, KIND_GHOST = 0.0, 1.0
 
-def split_columns(ncols: int, world: int, weights: Optional[np.ndarray] = None):
+
+# ----------------------------------------------------------------------------- planning
+def split_columns(ncols: int, world: int, weights: Optional[np.ndarray] = None) -> List[Tuple[int, int]]:
     """Column ranges [lo, hi) per rank; equal widths for a uniform lattice, or
     balanced by per-column particle counts when `weights` is given."""
     if weights is None:
@@ -32,47 +47,300 @@ def split_columns(ncols: int, world: int, weights: Optional[np.ndarray] = None):
         edges = [int(np.searchsorted(c, t, side="left")) for t in target]
         edges[0], edges[-1] = 0, ncols
     for r in range(world):
-        if edges[r + 1] - edges[r] < 4:
-            raise ValueError("a slab must own at least 4 cell columns")
+        if edges[r + 1] - edges[r] < 2 * GHOST_COLS:
+            raise ValueError(f"a slab must own at least {2 * GHOST_COLS} cell columns")
     return [(edges[r], edges[r + 1]) for r in range(world)]
 
 
-class SlabRun:
-    """One rank's share of a mountain-wave run."""
+def key_tables(box_min, box_max, h: float):
+    """structs.jl:66-68"""
+    phase = [int(math.floor(box_min[a] / h)) for a in range(3)]
+    lim = [int(math.floor(box_max[a] / h)) - phase[a] + 1 for a in range(3)]
+    return phase, lim
 
-    def __init__(self, sys, rank: int, world: int, n_global: int, export=("v", "ρ", "P", "θ", "T", "type")):
+
+def column_of(x0: np.ndarray, h: float, phase0: int) -> np.ndarray:
+    """global cell column, with the reference's arithmetic (structs.jl:99)"""
+    return np.floor(x0 / h).astype(np.int64) - phase0
+
+
+@dataclass
+class SlabPlan:
+    rank: int
+    world: int
+    lo: int
+    hi: int
+    phase0: int
+    ncols: int
+    h: float
+
+    @property
+    def has_left(self):
+        return self.rank > 0
+
+    @property
+    def has_right(self):
+        return self.rank < self.world - 1
+
+    def x_clip(self, margin: float):
+        """a slightly generous x-interval containing every owned lattice site"""
+        xa = -1e300 if not self.has_left else (self.phase0 + self.lo) * self.h - margin
+        xb = 1e300 if not self.has_right else (self.phase0 + self.hi) * self.h + margin
+        return xa, xb
+
+    def owns(self, x0: np.ndarray) -> np.ndarray:
+        c = column_of(x0, self.h, self.phase0)
+        return (c >= self.lo) & (c < self.hi)
+
+
+def plan_slab(box_min, box_max, h: float, rank: int, world: int) -> SlabPlan:
+    phase, lim = key_tables(box_min, box_max, h)
+    lo, hi = split_columns(lim[0], world)[rank]
+    return SlabPlan(rank, world, lo, hi, phase[0], lim[0], h)
+
+
+def global_indices(group_counts_all: np.ndarray, rank: int) -> np.ndarray:
+    """Reference particle index (0-based) of this rank's particles.  The reference fills
+    sys.particles group by group (fluid, walls, mountain — wcsph_perturbed_witch.jl:162-164)
+    and plane by plane along x within a group; ranks own increasing x-ranges, so the index
+    of a local particle = all earlier groups + the same group on lower ranks + local order.
+    `group_counts_all[r, g]` = number of particles of group g owned by rank r."""
+    gc = np.asarray(group_counts_all, dtype=np.int64)
+    group_start = np.concatenate([[0], np.cumsum(gc.sum(axis=0))])
+    out = []
+    for g in range(gc.shape[1]):
+        first = group_start[g] + gc[:rank, g].sum()
+        out.append(first + np.arange(gc[rank, g], dtype=np.int64))
+    return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
+
+
+# ----------------------------------------------------------------------------- transport
+def exchange(plan: SlabPlan, send_left, send_right, migr_left: int, migr_right: int, empty: Callable):
+    """Move halo records to the x-adjacent ranks.  `send_*` are (count, RECORD) float64
+    tensors (or None when there is no neighbour); `empty(n)` allocates a receive tensor on
+    the right device.  Returns ((recv_from_left, n_migrants), (recv_from_right, n_migrants))."""
+    import torch
+    import torch.distributed as dist
+
+    if plan.world == 1:
+        return (None, 0), (None, 0)
+    dev = send_left.device if send_left is not None else send_right.device
+    peers = []
+    if plan.has_left:
+        peers.append((plan.rank - 1, send_left, migr_left))
+    if plan.has_right:
+        peers.append((plan.rank + 1, send_right, migr_right))
+    # 1. how many records / migrants are coming
+    heads_out = [torch.tensor([len(s), m], dtype=torch.int64, device=dev) for _, s, m in peers]
+    heads_in = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in peers]
+    ops = []
+    for (peer, _, _), ho, hi_ in zip(peers, heads_out, heads_in):
+        ops.append(dist.P2POp(dist.isend, ho, peer))
+        ops.append(dist.P2POp(dist.irecv, hi_, peer))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    heads = [h.tolist() for h in heads_in]
+    # 2. the records
+    recv = [empty(int(h[0])) for h in heads]
+    ops = []
+    for (peer, s, _), r in zip(peers, recv):
+        if len(s):
+            ops.append(dist.P2POp(dist.isend, s, peer))
+        if len(r):
+            ops.append(dist.P2POp(dist.irecv, r, peer))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    out = {peer: (r, int(h[1])) for (peer, _, _), r, h in zip(peers, recv, heads)}
+    return out.get(plan.rank - 1, (None, 0)), out.get(plan.rank + 1, (None, 0))
+
+
+# ----------------------------------------------------------------------------- CUDA backend
+class LibSlabBackend:
+    """pack / unpack / compute through libsphmw on this rank's GPU"""
+
+    def __init__(self, sys, plan: SlabPlan, cap_records: int):
+        import torch
+        self.sys, self.plan = sys, plan
+        self.cap = int(cap_records)
+        dev = torch.device("cuda", sys.device)
+        self.buf_l = torch.empty((self.cap, RECORD), dtype=torch.float64, device=dev) if plan.has_left else None
+        self.buf_r = torch.empty((self.cap, RECORD), dtype=torch.float64, device=dev) if plan.has_right else None
+        self.dev = dev
+        self.lost = 0
+
+    def empty(self, n: int):
+        import torch
+        return torch.empty((n, RECORD), dtype=torch.float64, device=self.dev)
+
+    def pre(self):
+        check(_capi.lib().sphmw_step_phase(self.sys.ctx, b"wcsph", 0))
+
+    def post(self):
+        check(_capi.lib().sphmw_step_phase(self.sys.ctx, b"wcsph", 1))
+
+    def build(self):
+        self.sys.create_cell_list(want_count=False)
+
+    def pack(self):
+        counts = (C.c_int64 * 5)()
+        pl = C.c_void_p(self.buf_l.data_ptr()) if self.buf_l is not None else None
+        pr = C.c_void_p(self.buf_r.data_ptr()) if self.buf_r is not None else None
+        check(_capi.lib().sphmw_halo_pack(self.sys.ctx, pl, pr, self.cap, counts))
+        self.lost += counts[4]
+        sl = self.buf_l[:counts[0]] if self.buf_l is not None else None
+        sr = self.buf_r[:counts[1]] if self.buf_r is not None else None
+        return sl, sr, int(counts[2]), int(counts[3])
+
+    def unpack(self, recv, n_migrants: int):
+        if recv is None or len(recv) == 0:
+            return
+        check(_capi.lib().sphmw_halo_unpack(self.sys.ctx, C.c_void_p(recv.data_ptr()), len(recv), n_migrants))
+
+    def counts(self):
+        a, b = C.c_int64(), C.c_int64()
+        check(_capi.lib().sphmw_slab_counts(self.sys.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+# ----------------------------------------------------------------------------- the run
+class SlabRun:
+    """One rank's share of a mountain-wave run (world == 1: the whole domain, no halo)."""
+
+    def __init__(self, sys, plan: Optional[SlabPlan], n_global: int, backend=None,
+                 export=("v", "ρ", "P", "θ", "T", "type")):
         self.sys = sys
-        self.rank, self.world = rank, world
+        self.plan = plan
+        self.backend = backend
         self.n_global = n_global
         self.export = export
+        self.case_info = {}
         self._pinned = None
+        self._owned_host = None
+
+    @property
+    def world(self):
+        return 1 if self.plan is None else self.plan.world
 
     # ------------------------------------------------------------------ construction
     @classmethod
     def bell_hill_3d(cls, nx, ny, nz, rank=0, world=1, device=0, stream=None, **kw):
+        """BASELINE config 4/5 split into x-slabs; every rank generates only its own lattice
+        planes, global particle indices are agreed on by an all-gather of group sizes."""
         if world == 1:
             case = cases.bell_hill_3d(nx, ny, nz, lean=True, **kw)
             sys = cases.to_system(case, device=device, stream=stream)
             sys._flush()
-            run = cls(sys, rank, world, case.n)
+            run = cls(sys, None, case.n)
             run.case_info = case.info
             return run
-        raise NotImplementedError("multi-rank slabs: see SlabRun.distributed")
+        import torch
+        import torch.distributed as dist
+        # the global bounding box is a function of the constants alone
+        k = wpw.Constants(n_y=float(ny), dim=3, grid="cubic")
+        k.dom_length, k.dom_width = nx * k.dr, nz * k.dr
+        w = k.bc_width
+        box_min = (-k.dom_length / 2.0 - w, 0.0 - w, -k.dom_width / 2.0 - w)
+        box_max = (k.dom_length / 2.0 + w, k.dom_height + w, k.dom_width / 2.0 + w)
+        plan = plan_slab(box_min, box_max, k.h0, rank, world)
+        case = cases.bell_hill_3d(nx, ny, nz, lean=True, clip=plan.x_clip(2 * k.dr), **kw)
+        assert tuple(case.box_min) == box_min and tuple(case.box_max) == box_max
+        keep = plan.owns(case.fields["x"][:, 0])
+        gc = np.asarray(case.info["group_counts"], dtype=np.int64)
+        edges = np.concatenate([[0], np.cumsum(gc)])
+        kept = np.array([int(keep[edges[g]:edges[g + 1]].sum()) for g in range(len(gc))], dtype=np.int64)
+        case.fields = {f: a[keep] for f, a in case.fields.items()}
+        t = torch.tensor(kept, dtype=torch.int64, device=torch.device("cuda", device))
+        allc = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allc, t)
+        allc = np.stack([a.cpu().numpy() for a in allc])
+        gidx = global_indices(allc, rank)
+        n_global = int(allc.sum())
+        n_own = case.n
+        ghost_est = int(n_own * 2 * GHOST_COLS / max(1, plan.hi - plan.lo) * 1.5) + 4096
+        sys = cases.to_system(case, device=device, stream=stream, slab=(plan.lo, plan.hi),
+                              capacity=int(n_own * 1.1) + 2 * ghost_est)
+        sys._flush()
+        check(_capi.lib().sphmw_set_index(sys.ctx, _capi.ptr(np.ascontiguousarray(gidx)), n_own))
+        run = cls(sys, plan, n_global, LibSlabBackend(sys, plan, ghost_est))
+        run.case_info = case.info
+        run._owned_host = (case.fields, gidx)
+        return run
+
+    @classmethod
+    def from_global_case(cls, case, rank: int, world: int, device: int = 0, stream=None):
+        """Slice a whole (small) case held on the host: reference indices are the positions in
+        `case.fields`.  Used by tests and by single-process multi-context runs."""
+        plan = plan_slab(case.box_min, case.box_max, case.h, rank, world)
+        own = plan.owns(case.fields["x"][:, 0])
+        gidx = np.nonzero(own)[0].astype(np.int64)
+        sub = cases.Case(case.name, case.scheme, case.dim, case.box_min, case.box_max, case.h,
+                         case.params, {f: a[own] for f, a in case.fields.items()}, dict(case.info))
+        n_own = sub.n
+        ghost_est = int(n_own * 2 * GHOST_COLS / max(1, plan.hi - plan.lo) * 2.0) + 4096
+        sys = cases.to_system(sub, device=device, stream=stream, slab=(plan.lo, plan.hi),
+                              capacity=int(n_own * 1.2) + 2 * ghost_est)
+        sys._flush()
+        if n_own:
+            check(_capi.lib().sphmw_set_index(sys.ctx, _capi.ptr(np.ascontiguousarray(gidx)), n_own))
+        run = cls(sys, plan, case.n, LibSlabBackend(sys, plan, ghost_est))
+        run.case_info = dict(case.info)
+        run._owned_host = (sub.fields, gidx)
+        return run
 
     # ------------------------------------------------------------------ stepping
     @property
     def n_owned(self) -> int:
-        return self.sys.n_device
+        return self.sys.n_device if self.backend is None else self.backend.counts()[1]
 
     @property
     def n_resident(self) -> int:
         return self.sys.n_device
 
+    def _halo(self):
+        b = self.backend
+        sl, sr, ml, mr = b.pack()
+        (rl, nml), (rr, nmr) = exchange(self.plan, sl, sr, ml, mr, b.empty)
+        b.unpack(rl, nml)
+        b.unpack(rr, nmr)
+
     def create_cell_list(self):
-        self.sys.create_cell_list()
+        """≙ create_cell_list!(sys): (halo exchange +) sort.  Ghosts exist from here on."""
+        if self.backend is None:
+            self.sys.create_cell_list()
+        else:
+            self._halo()
+            self.backend.build()
 
     def step(self, nsteps: int):
-        self.sys.step(nsteps)
+        if self.backend is None:
+            self.sys.step(nsteps)
+            return
+        for _ in range(nsteps):
+            self.backend.pre()
+            self._halo()
+            self.backend.post()
+
+    # ------------------------------------------------------------------ read-back (tests)
+    def owned_fields(self, names=("x", "v", "rho", "h")):
+        """(global indices, {field: array}) of the particles this rank owns"""
+        from .system import FIELD_NCOMP, canonical
+        lib = _capi.lib()
+        n = self.sys.n_device
+        if self.backend is None:
+            return np.arange(n, dtype=np.int64), {f: self.sys.field(f) for f in names}
+        gidx = np.empty(n, dtype=np.int64)
+        tag = np.empty(n, dtype=np.int32)
+        check(lib.sphmw_download_index(self.sys.ctx, _capi.ptr(gidx), _capi.ptr(tag), n))
+        own = tag == 0
+        out = {}
+        for f in names:
+            nc = FIELD_NCOMP[canonical(f)]
+            buf = np.empty((nc, n) if nc == 3 else n, dtype=np.float64)
+            check(lib.sphmw_download_raw(self.sys.ctx, canonical(f).encode(), _capi.ptr(buf), n, nc))
+            a = np.ascontiguousarray(buf.T) if nc == 3 else buf
+            out[f] = a[own]
+        return gidx[own], out
 
     # ------------------------------------------------------------------ end to end
     def e2e_cycle(self, cycles: int, barrier: Callable[[], None]):
@@ -83,33 +351,103 @@ class SlabRun:
         import time
 
         import torch
+        from .system import FIELD_NCOMP, canonical
         sys = self.sys
-        n = sys.n_device
-        dim3 = 3
-        carried = [f for f in wpw.CORE_FIELDS]
+        lib = _capi.lib()
+        carried = list(wpw.CORE_FIELDS)
+        out_fields = sorted(set(self.export) | {"x"})
         every = int(self.case_info.get("frame_every", 8))
+        slab = self.backend is not None
         if self._pinned is None:
             self._pinned = {}
-            for f in set(carried) | set(self.export) | {"x"}:
-                from .system import FIELD_NCOMP, canonical
+            if slab:
+                host, gidx = self._owned_host
+                n0 = len(gidx)
+                for f in carried:
+                    a = host[canonical(f)]
+                    t = torch.empty(a.T.shape if a.ndim == 2 else a.shape, dtype=torch.float64, pin_memory=True)
+                    t.copy_(torch.from_numpy(np.ascontiguousarray(a.T if a.ndim == 2 else a)))
+                    self._pinned[f] = t
+                self._gidx = np.ascontiguousarray(gidx)
+            else:
+                n0 = sys.n_device
+                for f in carried:
+                    nc = FIELD_NCOMP[canonical(f)]
+                    self._pinned[f] = torch.empty((nc, n0) if nc == 3 else (n0,), dtype=torch.float64,
+                                                  pin_memory=True)
+                    sys.download_ptr(f, self._pinned[f].data_ptr(), n0)
+            self._n0 = n0
+            cap = int(n0 * 1.5) + 65536
+            for f in out_fields:
                 nc = FIELD_NCOMP[canonical(f)]
-                self._pinned[f] = torch.empty((nc, n) if nc == 3 else (n,), dtype=torch.float64,
-                                              pin_memory=True)
-            for f in carried:
-                sys.download_ptr(f, self._pinned[f].data_ptr(), n)
+                self._pinned["out:" + f] = torch.empty((nc * cap,), dtype=torch.float64, pin_memory=True)
+        n0 = self._n0
         h2d = sum(self._pinned[f].numel() * 8 for f in carried)
-        d2h = sum(self._pinned[f].numel() * 8 for f in set(self.export) | {"x"})
+        d2h = 0
         barrier()
         t0 = time.perf_counter()
         for _ in range(cycles):
+            if slab:
+                check(lib.sphmw_resize(sys.ctx, 0))
+                check(lib.sphmw_resize(sys.ctx, n0))
             for f in carried:
-                sys.upload_ptr(f, self._pinned[f].data_ptr(), n)
-            sys.create_cell_list(want_count=False)
-            sys.step(every)
-            for f in set(self.export) | {"x"}:
-                sys.download_ptr(f, self._pinned[f].data_ptr(), n)
+                sys.upload_ptr(f, self._pinned[f].data_ptr(), n0)
+            if slab:
+                check(lib.sphmw_set_index(sys.ctx, _capi.ptr(self._gidx), n0))
+            self.create_cell_list()
+            self.step(every)
+            n = sys.n_device
+            for f in out_fields:
+                nc = FIELD_NCOMP[canonical(f)]
+                p = self._pinned["out:" + f].data_ptr()
+                if slab:
+                    check(lib.sphmw_download_raw(sys.ctx, canonical(f).encode(), C.c_void_p(p), n, nc))
+                else:
+                    sys.download_ptr(f, p, n)
+                d2h += nc * n * 8
         barrier()
         dt = time.perf_counter() - t0
-        return {"seconds": dt, "steps": cycles * every, "h2d_bytes": h2d * cycles, "d2h_bytes": d2h * cycles,
+        return {"seconds": dt, "steps": cycles * every, "h2d_bytes": h2d * cycles, "d2h_bytes": d2h,
                 "what": f"{cycles} x (upload {len(carried)} carried fields from pinned host, create_cell_list, "
                         f"{every} steps = one frame interval, download x + {len(self.export)} export fields)"}
+
+
+class LocalCluster:
+    """All ranks of a slab decomposition driven in lockstep by ONE process (loop-back
+    transport: the records are handed over as device tensors).  The kernels of different
+    contexts never wait on one another, so running them back to back on one GPU — or on
+    several GPUs of the box from a single host thread — is safe."""
+
+    def __init__(self, runs: List[SlabRun]):
+        self.runs = runs
+
+    def _halo(self):
+        packs = [r.backend.pack() for r in self.runs]
+        for r, run in enumerate(self.runs):
+            dev = run.backend.dev
+            if r > 0:
+                sl, sr, ml, mr = packs[r - 1]
+                run.backend.unpack(sr.to(dev), mr)      # my left neighbour's right-going records
+            if r < len(self.runs) - 1:
+                sl, sr, ml, mr = packs[r + 1]
+                run.backend.unpack(sl.to(dev), ml)      # my right neighbour's left-going records
+
+    def create_cell_list(self):
+        self._halo()
+        for r in self.runs:
+            r.backend.build()
+
+    def step(self, nsteps: int):
+        for _ in range(nsteps):
+            for r in self.runs:
+                r.backend.pre()
+            self._halo()
+            for r in self.runs:
+                r.backend.post()
+
+    def gather(self, names=("x", "v", "rho", "h")):
+        """fields of all owned particles in reference index order"""
+        parts = [r.owned_fields(names) for r in self.runs]
+        gidx = np.concatenate([p[0] for p in parts])
+        order = np.argsort(gidx, kind="stable")
+        return gidx[order], {f: np.concatenate([p[1][f] for p in parts])[order] for f in names}
