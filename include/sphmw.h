@@ -61,6 +61,14 @@ typedef struct sphmw_config {
 } sphmw_config;
 
 #define SPHMW_FLAG_NONE 0
+/* fused "wcsph" step only.  Default (0): strict arithmetic — no FMA contraction, IEEE
+ * division/sqrt, so every FP64 sum is bit-identical to an IEEE evaluation of the reference
+ * closures.  FAST_MATH: same neighbour set and summation order, but fused multiply-adds and
+ * reciprocals in the closure bodies (as the reference's own @fastmath kernels allow);
+ * fields agree with the strict path to ~1e-15 relative per step.  CELL_PAIRS: experimental
+ * cell-centric pair-parallel kernel (strict arithmetic, bit-identical results). */
+#define SPHMW_FLAG_FAST_MATH 1
+#define SPHMW_FLAG_CELL_PAIRS 2
 
 int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out);
 int sphmw_destroy(sphmw_ctx *ctx);

@@ -234,7 +234,9 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
 
     sphmw_ctx *c = new sphmw_ctx();
     c->device = cfg->device;
+    c->flags = cfg->flags;
     c->cap = cfg->capacity;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     Grid &g = c->grid;
     g.h = cfg->h;
     for (int a = 0; a < 3; ++a) {

@@ -78,6 +78,8 @@ struct TimingEntry {
 
 struct sphmw_ctx {
     int device = 0;
+    int flags = 0;
+    int sm_count = 148;
     Grid grid{};
     Params prm{};
     int64_t n = 0;       // particles resident (incl. ghosts in slab mode)

@@ -224,12 +224,12 @@ class SlabRun:
 
     # ------------------------------------------------------------------ construction
     @classmethod
-    def bell_hill_3d(cls, nx, ny, nz, rank=0, world=1, device=0, stream=None, **kw):
+    def bell_hill_3d(cls, nx, ny, nz, rank=0, world=1, device=0, stream=None, flags: int = 0, **kw):
         """BASELINE config 4/5 split into x-slabs; every rank generates only its own lattice
         planes, global particle indices are agreed on by an all-gather of group sizes."""
         if world == 1:
             case = cases.bell_hill_3d(nx, ny, nz, lean=True, **kw)
-            sys = cases.to_system(case, device=device, stream=stream)
+            sys = cases.to_system(case, device=device, stream=stream, flags=flags)
             sys._flush()
             run = cls(sys, None, case.n)
             run.case_info = case.info
@@ -259,7 +259,7 @@ class SlabRun:
         n_own = case.n
         ghost_est = int(n_own * 2 * GHOST_COLS / max(1, plan.hi - plan.lo) * 1.5) + 4096
         sys = cases.to_system(case, device=device, stream=stream, slab=(plan.lo, plan.hi),
-                              capacity=int(n_own * 1.1) + 2 * ghost_est)
+                              capacity=int(n_own * 1.1) + 2 * ghost_est, flags=flags)
         sys._flush()
         check(_capi.lib().sphmw_set_index(sys.ctx, _capi.ptr(np.ascontiguousarray(gidx)), n_own))
         run = cls(sys, plan, n_global, LibSlabBackend(sys, plan, ghost_est))
@@ -268,7 +268,7 @@ class SlabRun:
         return run
 
     @classmethod
-    def from_global_case(cls, case, rank: int, world: int, device: int = 0, stream=None):
+    def from_global_case(cls, case, rank: int, world: int, device: int = 0, stream=None, flags: int = 0):
         """Slice a whole (small) case held on the host: reference indices are the positions in
         `case.fields`.  Used by tests and by single-process multi-context runs."""
         plan = plan_slab(case.box_min, case.box_max, case.h, rank, world)
@@ -279,7 +279,7 @@ class SlabRun:
         n_own = sub.n
         ghost_est = int(n_own * 2 * GHOST_COLS / max(1, plan.hi - plan.lo) * 2.0) + 4096
         sys = cases.to_system(sub, device=device, stream=stream, slab=(plan.lo, plan.hi),
-                              capacity=int(n_own * 1.2) + 2 * ghost_est)
+                              capacity=int(n_own * 1.2) + 2 * ghost_est, flags=flags)
         sys._flush()
         if n_own:
             check(_capi.lib().sphmw_set_index(sys.ctx, _capi.ptr(np.ascontiguousarray(gidx)), n_own))

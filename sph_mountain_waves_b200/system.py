@@ -70,7 +70,7 @@ class ParticleSystem:
     """≙ ParticleSystem{T}(T, domain, h) — src/structs.jl:43-92."""
 
     def __init__(self, T: ParticleType, domain: Shape, h: float, *, params: Optional[dict] = None,
-                 capacity: Optional[int] = None, device: int = 0, slab=None, stream=None):
+                 capacity: Optional[int] = None, device: int = 0, slab=None, stream=None, flags: int = 0):
         # structs.jl:59-61
         assert h > 0.0, "invalid ParticleSystem declaration! (h must be a positive float)"
         assert isinstance(T, ParticleType), \
@@ -85,6 +85,7 @@ class ParticleSystem:
         self._capacity = capacity
         self._slab = slab
         self._stream = stream
+        self._flags = int(flags)
         self._ctx = None
         self._staged: Dict[str, list] = {}
         self._staged_n = 0
@@ -100,7 +101,7 @@ class ParticleSystem:
         cap = self._capacity if self._capacity is not None else max(1024, int(n_needed * 1.05) + 64)
         cfg.capacity = max(cap, n_needed)
         cfg.device = self.device
-        cfg.flags = 0
+        cfg.flags = self._flags
         cfg.slab_lo, cfg.slab_hi = (-1, -1) if self._slab is None else self._slab
         h = C.c_void_p()
         check(_capi.lib().sphmw_create(C.byref(cfg), C.byref(h)))

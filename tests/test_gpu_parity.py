@@ -306,3 +306,58 @@ def test_reductions(gpu):
     assert abs(s.reduce("avg_speed") - speed.mean()) <= 1e-12 * speed.mean()
     assert s.reduce("max_speed") == speed.max()
     assert s.reduce("count") == len(s)
+
+
+# ---------------------------------------------------------------------------------------
+# the alternative code paths of the fused step (include/sphmw.h SPHMW_FLAG_*)
+# ---------------------------------------------------------------------------------------
+FAST_MATH, CELL_PAIRS = 1, 2
+
+
+@pytest.mark.parametrize("name", ["static2d", "witch2d", "hill3d"])
+def test_cell_pairs_kernel_is_bitwise_identical(gpu, name):
+    """the cell-centric pair-parallel kernel adds the same contributions in the same order"""
+    case = CASES[name]()
+    a, b = load_gpu(case), load_gpu(case, flags=CELL_PAIRS)
+    for s in (a, b):
+        s.create_cell_list()
+        s.count_pairs(True)
+        s.step(4)
+    assert a.pair_count() == b.pair_count() > 0
+    for f in WCSPH_FIELDS:
+        assert bits_equal(a.field(f), b.field(f)), f
+
+
+@pytest.mark.parametrize("name", ["static2d", "witch2d", "hill3d"])
+def test_fast_math_within_north_star_tolerance(gpu, name):
+    """FAST_MATH keeps the neighbour set and the summation order; rho, v, x stay within
+    1e-10 relative per step of the oracle (measured: ~1e-15)"""
+    case = CASES[name]()
+    o, s, strict = load_oracle(case), load_gpu(case, flags=FAST_MATH), load_gpu(case)
+    for sysm in (o, s, strict):
+        sysm.create_cell_list()
+    s.count_pairs(True)
+    strict.count_pairs(True)
+    o.step("wcsph", 1)
+    s.step(1)
+    strict.step(1)
+    assert s.pair_count() == strict.pair_count() == o.pair_count()
+    for f in ("rho", "v", "x", "h", "P"):
+        assert rel_err(s.field(f), o.field(f)) <= TOL_STEP, f
+        assert rel_err(s.field(f), strict.field(f)) <= 1e-13, f
+    o.step("wcsph", 19)
+    s.step(19)
+    for f in ("rho", "v", "x", "h"):
+        assert rel_err(s.field(f), o.field(f)) <= 20 * TOL_STEP, f
+
+
+def test_fast_math_1000_steps_within_1e6(gpu):
+    case = cases.mountain_wave_2d(n_y=24.0, dom_length=40e3)
+    o, s = load_oracle(case), load_gpu(case, flags=FAST_MATH)
+    o.create_cell_list()
+    s.create_cell_list()
+    o.step("wcsph", 1000)
+    s.step(1000)
+    assert len(o) == len(s)
+    for f in ("rho", "v", "x"):
+        assert rel_err(s.field(f), o.field(f)) <= TOL_1000, f

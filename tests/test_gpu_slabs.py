@@ -18,12 +18,14 @@ def wide_3d():
     return cases.bell_hill_3d(48, 10, 8, h_m=3000.0, a=8e3, U=20.0)
 
 
-@pytest.mark.parametrize("make,world", [(wide_2d, 2), (wide_2d, 3), (wide_3d, 2), (wide_3d, 4)])
-def test_slabs_bitwise_equal_to_whole_domain(gpu, make, world):
+@pytest.mark.parametrize("make,world,flags", [(wide_2d, 2, 0), (wide_2d, 3, 0), (wide_3d, 2, 0), (wide_3d, 4, 0),
+                                              (wide_3d, 3, 1), (wide_2d, 2, 2)])
+def test_slabs_bitwise_equal_to_whole_domain(gpu, make, world, flags):
+    """flags: 0 strict, 1 FAST_MATH, 2 CELL_PAIRS — each path is rank-count independent"""
     case = make()
-    whole = load_gpu(case)
+    whole = load_gpu(case, flags=flags)
     whole.create_cell_list()
-    cluster = LocalCluster([SlabRun.from_global_case(case, r, world) for r in range(world)])
+    cluster = LocalCluster([SlabRun.from_global_case(case, r, world, flags=flags) for r in range(world)])
     cluster.create_cell_list()
     assert sum(r.n_owned for r in cluster.runs) == case.n
     nsteps = 25  # U = 20 m/s: particles do cross slab faces within these steps
