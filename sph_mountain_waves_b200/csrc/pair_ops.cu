@@ -13,6 +13,7 @@
 // so the FP64 sums are bit-identical to an IEEE evaluation of the reference
 // wherever no transcendental (exp, pow, cbrt) is involved.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -1151,6 +1152,9 @@ static int run_binary(sphmw_ctx *c, const char *name, int self, const Fields &ou
         col_lo = GHOST_COLS - ghost_depth;
         col_hi = (int)c->grid.lim[0] - 1 - col_lo;
     }
+    // Measured on B200 (profiles/r01_tuning.md): forcing 6 or 8 resident blocks per SM
+    // (64 registers), 64-thread blocks and software prefetch of the next candidate were all
+    // neutral or slower than this plain configuration.
     TIMED(c, name);
     if (c->grid.dim == 2)
         k_binary<2, Op><<<grid_for(c->n, 128), 128, 0, c->stream>>>(
