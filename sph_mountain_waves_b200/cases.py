@@ -91,6 +91,28 @@ def bell_hill_3d(nx: int, ny: int, nz: int, h_m: float = 100.0, a: float = 10e3,
     return c
 
 
+def hopkins_2d(variant: str = "hopkins", n_y: float = 20.0, dom_length: float = 60e3, **kw) -> Case:
+    """The pressure-entropy drivers on the same lattice: `variant` = "hopkins"
+    (src/current/hopkins_perturbed_witch.jl) or "hopkins_total" (hopkins_total_witch.jl).
+    Their constructors add A = P / rho^gamma and write m = rho * dr^2
+    (hopkins_perturbed_witch.jl:146-147, hopkins_total_witch.jl:118-119)."""
+    c = mountain_wave_2d(n_y=n_y, dom_length=dom_length, name=f"{variant}_2d_ny{n_y:g}", **kw)
+    gamma = c.params["gamma"]
+    dr = c.info["dr"]
+    f = c.fields
+    if variant == "hopkins":
+        f["m"] = f["rho"] * (dr * dr)
+    else:
+        f["m"] = f["rho"] * dr * dr
+    f["A"] = f["P"] / f["rho"] ** gamma
+    if variant == "hopkins_total":
+        # 11-field particle (hopkins_total_witch.jl:83-95)
+        for k in ("rho_bg", "rho_p", "P_bg", "P_p", "theta_bg", "theta_p", "T_bg", "T_p"):
+            f.pop(k)
+    c.scheme = variant
+    return c
+
+
 def collapse_dry(dr: float = 1.5e-2) -> Case:
     """BASELINE config 1 (C1) — sph_jl/examples/collapse_dry.jl:30-106."""
     # :42-62

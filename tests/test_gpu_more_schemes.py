@@ -1,0 +1,164 @@
+"""Second-priority operators: the Hopkins pressure-entropy passes,
+the packing operators, the device smoothing kernels and the pvd/vtp writer."""
+import re
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from sph_mountain_waves_b200 import cases, kernels, new_pvd_file, save_frame, save_pvd_file
+from util import load_gpu, load_oracle, n_mismatch, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.mark.parametrize("variant", ["hopkins", "hopkins_total"])
+def test_hopkins_steps_vs_oracle(gpu, variant):
+    """+1 binary pass with pow per pair (hopkins_perturbed_witch.jl:205-214,
+    hopkins_total_witch.jl:233-308)"""
+    case = cases.hopkins_2d(variant)
+    o, s = load_oracle(case), load_gpu(case)
+    o.create_cell_list()
+    s.create_cell_list()
+    for nsteps in (1, 9):
+        o.step(variant, nsteps)
+        s.step(nsteps, variant)
+        assert len(o) == len(s)
+        for f in ("x", "v", "rho", "P", "h", "theta", "T"):
+            assert rel_err(s.field(f), o.field(f)) <= 10 * TOL, (variant, nsteps, f)
+
+
+def test_hopkins_operator_by_operator(gpu):
+    case = cases.hopkins_2d("hopkins")
+    o, s = load_oracle(case), load_gpu(case)
+    o.create_cell_list()
+    s.create_cell_list()
+    seq = ["wcsph.accelerate", "wcsph.move", "create_cell_list", "wcsph.reset_density", "wcsph.compute_density",
+           "wcsph.finalize_density", "wcsph.update_smoothing", "create_cell_list", "hopkins.reset_pressure",
+           "hopkins.compute_pressure", "hopkins.finalize_pressure", "wcsph.find_temperature",
+           "wcsph.find_pot_temp", "wcsph.balance_of_momentum", "wcsph.accelerate"]
+    for op in seq:
+        if op == "create_cell_list":
+            assert o.create_cell_list() == s.create_cell_list()
+            continue
+        o.apply(op)
+        s.apply(op)
+        for f in ("x", "v", "Dv", "rho", "rho_p", "P", "P_p", "h", "T", "theta"):
+            assert rel_err(s.field(f), o.field(f)) <= TOL, (op, f)
+
+
+def test_packing_operators(gpu):
+    """one pseudo-step of packing! (src/utils/new_packing.jl:96-108)"""
+    case = cases.mountain_wave_2d(n_y=20.0, dom_length=60e3)
+    k = case.params
+    for name, val in (("dt_pack", 1.0 * k["dt"]), ("c_pack", 2.0 * k["c"]), ("zeta_pack", 1.0 * k["c"] / k["dt"])):
+        case.params[name] = val
+    o, s = load_oracle(case), load_gpu(case)
+    for sysm in (o, s):
+        sysm.create_cell_list()
+        for op in ("packing.reset_rho", "packing.accumulate_rho"):
+            sysm.apply(op)
+    for _ in range(3):
+        for sysm in (o, s):
+            sysm.apply("packing.accelerate")
+            sysm.apply("packing.move")
+            sysm.create_cell_list()
+            sysm.apply("packing.reset_rho")
+            sysm.apply("packing.accumulate_rho")
+            sysm.apply("packing.balance_of_momentum")
+            sysm.apply("packing.accelerate")
+    for f in ("x", "v", "rho"):
+        assert rel_err(s.field(f), o.field(f)) <= TOL, f
+    # the force acts along y only (new_packing.jl:44-45)
+    assert np.all(s.field("x")[:, 0] == case.fields["x"][:, 0])
+
+
+KERNELS = ["wendland1", "Dwendland1", "rDwendland1", "wendland2", "Dwendland2", "rDwendland2", "wendland3",
+           "Dwendland3", "rDwendland3", "DDwendland3", "spline23", "Dspline23", "rDspline23", "spline24",
+           "Dspline24", "rDspline24"]
+
+
+def test_device_kernels_bitwise_equal_oracle(gpu):
+    """no transcendental in any kernel: device == oracle bit for bit"""
+    h = np.array([0.42, 1.0, 624.0])[:, None]
+    r = np.concatenate([np.linspace(0.0, 1.3, 261), [1.0, 0.5, 0.2, 0.6]])[None, :] * h
+    for name in KERNELS:
+        got = getattr(kernels, name)(h, r)
+        ref = O.kernel(name, h, r)
+        assert n_mismatch(got, ref) == 0, name
+
+
+@pytest.mark.parametrize("dim,f,Df,rDf", [(1, "wendland1", "Dwendland1", "rDwendland1"),
+                                          (2, "wendland2", "Dwendland2", "rDwendland2"),
+                                          (3, "wendland3", "Dwendland3", "rDwendland3"),
+                                          (2, "spline23", "Dspline23", "rDspline23"),
+                                          (2, "spline24", "Dspline24", "rDspline24")])
+def test_device_kernel_properties(gpu, dim, f, Df, rDf):
+    """sph_jl/tests/test_kernels.jl:19-43 on the device functions"""
+    h = 0.42
+    F, DF, RDF = getattr(kernels, f), getattr(kernels, Df), getattr(kernels, rDf)
+    assert F(h, 4.0) == 0.0 and DF(h, 4.0) == 0.0 and RDF(h, 4.0) == 0.0
+    assert np.isfinite(F(h, 0.0)) and np.isfinite(DF(h, 0.0)) and np.isfinite(RDF(h, 0.0))
+    n = 1000
+    dx = h / n
+
+    def simpson(fun, a, b):  # test_kernels.jl:9-17, vectorised
+        step = (b - a) / n
+        i = np.arange(1, n)
+        _a = a + i * step
+        _b = a + (i + 1) * step
+        return float(np.sum(step / 6.0 * (fun(_a) + 4.0 * fun(0.5 * (_a + _b)) + fun(_b))))
+
+    w = {1: lambda r: 2.0 * F(h, r), 2: lambda r: 2.0 * np.pi * r * F(h, r),
+         3: lambda r: 4.0 * np.pi * r * r * F(h, r)}[dim]
+    assert simpson(w, 0.0, h) == pytest.approx(1.0, rel=0.01)
+    assert simpson(lambda r: DF(h, r), 0.2, 0.3) == pytest.approx(F(h, 0.3) - F(h, 0.2), rel=0.01)
+    assert RDF(h, 0.1) == pytest.approx(DF(h, 0.1) / 0.1, rel=0.01)
+
+
+def read_vtp(path):
+    """minimal reader of the appended-raw, zlib-compressed PolyData WriteVTK emits"""
+    raw = open(path, "rb").read()
+    head, _, rest = raw.partition(b'<AppendedData encoding="raw">')
+    blob = rest[rest.index(b"_") + 1:]
+    arrays = {}
+    for m in re.finditer(rb'<DataArray type="(\w+)" Name="([^"]+)" NumberOfComponents="(\d+)" format="appended" '
+                         rb'offset="(\d+)"/>', head):
+        typ, name, nc, off = m.group(1).decode(), m.group(2).decode(), int(m.group(3)), int(m.group(4))
+        hdr = np.frombuffer(blob, dtype=np.uint64, count=3, offset=off)
+        nb = int(hdr[0])
+        sizes = np.frombuffer(blob, dtype=np.uint64, count=nb, offset=off + 24)
+        pos = off + 24 + 8 * nb
+        out = b""
+        for sz in sizes:
+            out += zlib.decompress(blob[pos:pos + int(sz)])
+            pos += int(sz)
+        a = np.frombuffer(out, dtype=np.float64 if typ == "Float64" else np.int64)
+        arrays[name] = a.reshape(-1, nc) if nc > 1 else a
+    n = int(re.search(rb'NumberOfPoints="(\d+)"', head).group(1))
+    return n, arrays
+
+
+def test_pvd_frames_round_trip(gpu, tmp_path):
+    """≙ sph_jl/tests/test_IO.jl:32-60: what is written can be read back exactly"""
+    case = cases.mountain_wave_2d(n_y=20.0, dom_length=60e3, h_m=3000.0, a=10e3, U=20.0)
+    s = load_gpu(case)
+    s.create_cell_list()
+    out = new_pvd_file(str(tmp_path / "res"))
+    save_frame(out, s, "v", "ρ", "P", "θ", "T", "type")
+    s.step(8)
+    save_frame(out, s, "v", "ρ", "P", "θ", "T", "type")
+    save_pvd_file(out)
+    pvd = (tmp_path / "res" / "result.pvd").read_text()
+    assert 'timestep="0.0"' in pvd and 'timestep="1.0"' in pvd and "frame1.vtp" in pvd  # IO.jl:73
+    n, arr = read_vtp(tmp_path / "res" / "frame1.vtp")
+    assert n == len(s)
+    assert np.array_equal(arr["Points"], s.field("x"))
+    assert np.array_equal(arr["v"], s.field("v"))
+    for name in ("ρ", "P", "θ", "T", "type"):
+        assert np.array_equal(arr[name], s.field(name)), name
+    assert np.array_equal(arr["connectivity"], np.arange(n)) and np.array_equal(arr["offsets"], np.arange(1, n + 1))
+    n0, arr0 = read_vtp(tmp_path / "res" / "frame0.vtp")
+    assert np.array_equal(arr0["ρ"], case.fields["rho"])
