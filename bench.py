@@ -224,9 +224,20 @@ def run_ours(args):
         alg_bytes = run.n_resident * BYTES_3D["K_C"]
         achieved = alg_bytes / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
         total_kernel_ms = sum(v[0] for v in rep.values())
+        # DRAM traffic of that kernel per launch: from the committed ncu capture of this very
+        # workload/arithmetic on one GPU (never measured under the timed run), else null
+        traffic = None
+        try:
+            tj = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text())
+            rec = tj.get(args.workload, {}).get(f"flags{args.flags}")
+            if rec and world == rec["n_gpus"]:
+                traffic = (rec["dram_bytes_read"] + rec["dram_bytes_write"]) / 1e9
+        except Exception:
+            pass
         roofline = {
             "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-            "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak_gbs, "traffic": traffic, "traffic_unit": "GB per launch (ncu)",
+            "alg_gbytes_per_launch": alg_bytes / 1e9, "peak_source": peak_src,
             "alg_bytes_per_particle": BYTES_3D["K_C"], "ms_per_launch": per_launch_s * 1e3,
             "share_of_step": (k_ms / total_kernel_ms) if total_kernel_ms else None,
             "per_kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(rep.items())},
