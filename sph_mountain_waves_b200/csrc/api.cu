@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -285,13 +286,43 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
     if (g.lim[2] == 1) {
         g.dim = 2;
         for (int di = -1; di <= 1; ++di)
-            for (int dj = -1; dj <= 1; ++dj) g.key_diff[g.ndiff++] = (int)(di + g.lim[0] * dj);
+            for (int dj = -1; dj <= 1; ++dj) {
+                g.nb_di[g.ndiff] = di;
+                g.nb_drest[g.ndiff] = dj;
+                g.key_diff[g.ndiff++] = (int)(di + g.lim[0] * dj);
+            }
     } else {
         g.dim = 3;
         for (int di = -1; di <= 1; ++di)
             for (int dj = -1; dj <= 1; ++dj)
-                for (int dk = -1; dk <= 1; ++dk)
+                for (int dk = -1; dk <= 1; ++dk) {
+                    g.nb_di[g.ndiff] = di;
+                    g.nb_drest[g.ndiff] = (int)(dj + g.lim[1] * dk);
                     g.key_diff[g.ndiff++] = (int)(di + g.lim[0] * (dj + g.lim[1] * dk));
+                }
+    }
+    // physical x-chunking.  A pass needs three x-y planes of cells at a time; the chunk width
+    // is chosen so that three chunk-planes (~6 particles x ~100 B per cell) stay near 40 MB,
+    // well inside the 126 MB L2: Cx ~ 22000 / Ly columns (256 for the 64 M case; measured
+    // best of 32..2048 there, profiles/r01_tuning.md).  2D grids need no chunking.
+    {
+        long long want = g.dim == 3 ? 22000 / (g.lim[1] > 0 ? g.lim[1] : 1) : (1LL << 30);
+        g.cx_shift = 5;
+        while ((1LL << (g.cx_shift + 1)) <= want && g.cx_shift < 30) ++g.cx_shift;
+        // never pad the column count by more than 2x
+        while (g.cx_shift > 0 && (1LL << g.cx_shift) >= 2 * g.lim[0]) --g.cx_shift;
+    }
+    if (getenv("SPHMW_CX_SHIFT")) g.cx_shift = atoi(getenv("SPHMW_CX_SHIFT"));
+    g.rows = g.lim[1] * g.lim[2];
+    {
+        long long cx = 1LL << g.cx_shift;
+        long long nchunks = (g.lim[0] + cx - 1) / cx;
+        g.pkey_max = nchunks * cx * g.rows;
+    }
+    if (g.pkey_max >= (long long)0x7FFFFFF0) {
+        delete c;
+        sphmw_set_error("too many cells (%lld)", g.pkey_max);
+        return SPHMW_E_INVALID;
     }
     {
         // exact threshold for the cut-off test (sqrt is monotone and correctly rounded on
@@ -314,9 +345,11 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
         CUDA_TRY(cudaMalloc(&c->halo_counters, sizeof(uint32_t) * 8));
         CUDA_TRY(cudaMallocHost(&c->h_halo_counters, sizeof(uint32_t) * 8));
         CUDA_TRY(cudaMalloc(&c->key, sizeof(uint32_t) * c->cap));
+        CUDA_TRY(cudaMalloc(&c->cellx, sizeof(uint32_t) * c->cap));
+        CUDA_TRY(cudaMalloc(&c->cellx_alt, sizeof(uint32_t) * c->cap));
         CUDA_TRY(cudaMalloc(&c->rank, sizeof(uint32_t) * c->cap));
         CUDA_TRY(cudaMalloc(&c->src, sizeof(uint32_t) * c->cap));
-        CUDA_TRY(cudaMalloc(&c->cell_start, sizeof(uint32_t) * (g.key_max + 2)));
+        CUDA_TRY(cudaMalloc(&c->cell_start, sizeof(uint32_t) * (g.pkey_max + 2)));
         c->removed_cap = 1 << 20;
         CUDA_TRY(cudaMalloc(&c->removed, sizeof(uint32_t) * (c->removed_cap + 1)));
         CUDA_TRY(cudaMallocHost(&c->h_removed, sizeof(uint32_t) * (c->removed_cap + 1)));
@@ -346,7 +379,7 @@ extern "C" int sphmw_destroy(sphmw_ctx *c) {
     cudaFree(c->idx); cudaFree(c->idx_alt); cudaFree(c->pos_of_idx);
     cudaFree(c->tag); cudaFree(c->tag_alt); cudaFree(c->halo_counters);
     if (c->h_halo_counters) cudaFreeHost(c->h_halo_counters);
-    cudaFree(c->key); cudaFree(c->rank); cudaFree(c->src);
+    cudaFree(c->key); cudaFree(c->rank); cudaFree(c->src); cudaFree(c->cellx); cudaFree(c->cellx_alt);
     cudaFree(c->cell_start); cudaFree(c->scan_tmp); cudaFree(c->removed);
     cudaFree(c->mv_old); cudaFree(c->mv_new);
     cudaFree(c->d_counters); cudaFree(c->staging); cudaFree(c->reduce_tmp);

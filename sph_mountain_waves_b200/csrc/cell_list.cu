@@ -29,12 +29,12 @@ __global__ void k_keys(const double *__restrict__ x0, const double *__restrict__
                        const double *__restrict__ x2, int64_t n, Grid g,
                        uint32_t *__restrict__ key, uint32_t *__restrict__ removed,
                        uint32_t removed_cap, const uint32_t *__restrict__ idx,
-                       const uint32_t *__restrict__ tag) {
+                       const uint32_t *__restrict__ tag, uint32_t *__restrict__ cellx) {
     int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (SLAB) {
         bool live = pos < n;
         bool dead = false;
-        uint32_t k = 0;
+        uint32_t k = 0, ci = 0;
         if (live) {
             double x = x0[pos], y = x1[pos], z = DIM == 3 ? x2[pos] : 0.0;
             bool inside = tag[pos] != TAG_DEAD && g.box[0] <= x && x <= g.box[3] && g.box[1] <= y &&
@@ -44,13 +44,17 @@ __global__ void k_keys(const double *__restrict__ x0, const double *__restrict__
                 long long j = (long long)floor(y / g.h) - g.phase[1];
                 long long kk = DIM == 3 ? (long long)floor(z / g.h) - g.phase[2] : 0;
                 if (i < 0 || i >= g.lim[0]) inside = false;
-                k = (uint32_t)(i + g.lim[0] * (j + g.lim[1] * kk));
+                else {
+                    k = pkey_of(g, (int)i, (int)(j + g.lim[1] * kk));
+                    ci = (uint32_t)i;
+                }
             }
             if (!inside) {
-                k = (uint32_t)g.key_max;
+                k = (uint32_t)g.pkey_max;
                 dead = true;
             }
             key[pos] = k;
+            cellx[pos] = ci;
         }
         unsigned m = __ballot_sync(0xffffffffu, dead);
         if ((threadIdx.x & 31) == 0 && m) atomicAdd(&removed[0], (uint32_t)__popc(m));
@@ -61,23 +65,23 @@ __global__ void k_keys(const double *__restrict__ x0, const double *__restrict__
     // geometry.jl:24-30 — closed intervals; NaN fails every comparison
     bool inside = g.box[0] <= x && x <= g.box[3] && g.box[1] <= y && y <= g.box[4] &&
                   g.box[2] <= z && z <= g.box[5];
-    uint32_t k;
+    uint32_t k, ci = 0;
     if (inside) {
         // structs.jl:99-102 — IEEE division, then floor (never a reciprocal multiply)
         long long i = (long long)floor(x / g.h) - g.phase[0];
         long long j = (long long)floor(y / g.h) - g.phase[1];
         long long kk = DIM == 3 ? (long long)floor(z / g.h) - g.phase[2] : 0;
-        if (i < 0 || i >= g.lim[0]) {
-            inside = false;  // slab mode: left the owned+ghost columns (host migrates first)
-        }
-        k = (uint32_t)(i + g.lim[0] * (j + g.lim[1] * kk));
+        // structs.jl:102 gives the reference key i + Lx*(j + Ly*k); stored is its physical image
+        k = pkey_of(g, (int)i, (int)(j + g.lim[1] * kk));
+        ci = (uint32_t)i;
     }
     if (!inside) {
-        k = (uint32_t)g.key_max;  // dead bucket: sorted behind every live cell
+        k = (uint32_t)g.pkey_max;  // dead bucket: sorted behind every live cell
         uint32_t slot = atomicAdd(&removed[0], 1u);
         if (slot < removed_cap) removed[1 + slot] = idx[pos];
     }
     key[pos] = k;
+    cellx[pos] = ci;
 }
 
 // ---------------------------------------------------------------------------
@@ -222,7 +226,8 @@ __global__ void k_gather(GatherList gl, const uint32_t *__restrict__ src,
                          const uint32_t *__restrict__ idx, uint32_t *__restrict__ idx_out,
                          uint32_t *__restrict__ pos_of_idx, const uint32_t *__restrict__ key,
                          uint32_t *__restrict__ key_out, const uint32_t *__restrict__ tag,
-                         uint32_t *__restrict__ tag_out, int64_t n_new) {
+                         uint32_t *__restrict__ tag_out, const uint32_t *__restrict__ cellx,
+                         uint32_t *__restrict__ cellx_out, int64_t n_new) {
     int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (slot >= n_new) return;
     uint32_t s = src[slot];
@@ -231,6 +236,7 @@ __global__ void k_gather(GatherList gl, const uint32_t *__restrict__ src,
     if (pos_of_idx) pos_of_idx[id] = (uint32_t)slot;
     key_out[slot] = key[s];
     tag_out[slot] = tag[s];
+    cellx_out[slot] = cellx[s];
     for (int f = 0; f < gl.count; ++f) gl.to[f][slot] = gl.from[f][s];
 }
 
@@ -270,7 +276,7 @@ static void replay_swap_removal(int64_t N, std::vector<uint32_t> &removed,
 int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     const Grid &g = c->grid;
     const int64_t n = c->n;
-    const int64_t ncells = g.key_max;  // + 1 dead bucket
+    const int64_t ncells = g.pkey_max;  // + 1 dead bucket
     if (n == 0) {
         CUDA_TRY(cudaMemsetAsync(c->cell_start, 0, sizeof(uint32_t) * (ncells + 2), c->stream));
         c->cell_list_valid = true;
@@ -292,7 +298,7 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
         const bool slab = c->slab_lo >= 0;
         const unsigned gr = grid_for(n, 256);
 #define KEYS_ARGS c->cur.s[S_X0], c->cur.s[S_X1], c->cur.s[S_X2], n, g, c->key, c->removed, \
-                  (uint32_t)c->removed_cap, c->idx, c->tag
+                  (uint32_t)c->removed_cap, c->idx, c->tag, c->cellx
         if (g.dim == 2 && !slab) k_keys<2, false><<<gr, 256, 0, c->stream>>>(KEYS_ARGS);
         else if (g.dim == 2) k_keys<2, true><<<gr, 256, 0, c->stream>>>(KEYS_ARGS);
         else if (!slab) k_keys<3, false><<<gr, 256, 0, c->stream>>>(KEYS_ARGS);
@@ -365,13 +371,14 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
         TIMED(c, "cell_gather");
         k_gather<<<grid_for(n_new, 256), 256, 0, c->stream>>>(gl, c->src, c->idx, c->idx_alt,
                                                               c->pos_of_idx, c->key, c->rank, c->tag,
-                                                              c->tag_alt, n_new);
+                                                              c->tag_alt, c->cellx, c->cellx_alt, n_new);
     }
     CUDA_TRY(cudaGetLastError());
     for (int f = 0; f < gl.count; ++f) std::swap(c->cur.s[gathered[f]], c->alt.s[gathered[f]]);
     std::swap(c->idx, c->idx_alt);
     std::swap(c->key, c->rank);
     std::swap(c->tag, c->tag_alt);
+    std::swap(c->cellx, c->cellx_alt);
     c->n = n_new;
     if (c->slab_lo < 0) c->n_owned = n_new;
     c->cell_list_valid = true;
@@ -382,10 +389,15 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
 // ---------------------------------------------------------------------------
 // test hooks
 // ---------------------------------------------------------------------------
-__global__ void k_keys_by_index(const uint32_t *__restrict__ key, const uint32_t *__restrict__ idx,
-                                int64_t n, long long *__restrict__ out) {
+// the REFERENCE key (structs.jl:102, 0-based) of every particle, in particle index order
+__global__ void k_keys_by_index(const uint32_t *__restrict__ key, const uint32_t *__restrict__ cellx,
+                                const uint32_t *__restrict__ idx, int64_t n, Grid g,
+                                long long *__restrict__ out) {
     int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (pos < n) out[idx[pos]] = (long long)key[pos];
+    if (pos < n) {
+        CellCoord c = cell_of(g, key[pos], cellx[pos]);
+        out[idx[pos]] = c.i + g.lim[0] * (long long)c.rest;
+    }
 }
 
 extern "C" int sphmw_cell_keys(sphmw_ctx *c, int64_t *keys, int64_t n) {
@@ -397,7 +409,7 @@ extern "C" int sphmw_cell_keys(sphmw_ctx *c, int64_t *keys, int64_t n) {
     long long *d = (long long *)c->staging;  // 3*cap doubles >= n int64
     {
         TIMED(c, "keys_by_index");
-        k_keys_by_index<<<grid_for(n, 256), 256, 0, c->stream>>>(c->key, c->idx, n, d);
+        k_keys_by_index<<<grid_for(n, 256), 256, 0, c->stream>>>(c->key, c->cellx, c->idx, n, c->grid, d);
     }
     CUDA_TRY(cudaMemcpyAsync(keys, d, sizeof(int64_t) * n, cudaMemcpyDefault, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -410,7 +422,8 @@ extern "C" int sphmw_cell_entries(sphmw_ctx *c, int64_t key, int64_t *out, int64
     if (!c->cell_list_valid) { sphmw_set_error("cell list is not built"); return SPHMW_E_STATE; }
     if (key < 0 || key >= c->grid.key_max) { sphmw_set_error("cell key out of range"); return SPHMW_E_INVALID; }
     uint32_t be[2];
-    CUDA_TRY(cudaMemcpyAsync(be, c->cell_start + key, sizeof(be), cudaMemcpyDeviceToHost, c->stream));
+    const long long pk = pkey_of(c->grid, (int)(key % c->grid.lim[0]), (int)(key / c->grid.lim[0]));
+    CUDA_TRY(cudaMemcpyAsync(be, c->cell_start + pk, sizeof(be), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     int64_t cnt = (int64_t)be[1] - (int64_t)be[0];
     *n = cnt;

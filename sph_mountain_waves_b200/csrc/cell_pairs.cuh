@@ -175,7 +175,8 @@ struct CPWarpShared {
 template <int DIM, class OP>
 __global__ void __launch_bounds__(CP_WARPS * 32)
 k_cell_pairs(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ cell_start,
-             int col_lo, int col_hi, unsigned long long *pair_counter) {
+             const uint32_t *__restrict__ cellx, int col_lo, int col_hi,
+             unsigned long long *pair_counter) {
     __shared__ CPWarpShared<OP> shared[CP_WARPS];
     const unsigned lane = threadIdx.x & 31;
     const unsigned ltmask = (1u << lane) - 1u;
@@ -183,13 +184,13 @@ k_cell_pairs(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restric
     const long long nwarps = (long long)gridDim.x * CP_WARPS;
     unsigned long long npairs = 0;
 
-    for (long long cell = (long long)blockIdx.x * CP_WARPS + (threadIdx.x >> 5); cell < g.key_max;
+    for (long long cell = (long long)blockIdx.x * CP_WARPS + (threadIdx.x >> 5); cell < g.pkey_max;
          cell += nwarps) {
         const uint32_t hb = cell_start[cell], he = cell_start[cell + 1];
         if (hb == he) continue;
+        const CellCoord home = cell_of(g, (unsigned)cell, cellx[hb]);
         if (col_lo > 0) {  // slab mode: ghost columns outside the pass are carried over
-            int col = (int)(cell % g.lim[0]);
-            if (col < col_lo || col > col_hi) {
+            if (home.i < col_lo || home.i > col_hi) {
                 for (uint32_t p = hb + lane; p < he; p += 32) OP::template skip<DIM>(f, out, p);
                 continue;
             }
@@ -197,8 +198,8 @@ k_cell_pairs(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restric
         // the neighbour cells' runs, lane d <-> key_diff[d]  (structs.jl:73-81 order)
         uint32_t rb = 0, len = 0;
         if ((int)lane < g.ndiff) {
-            long long nk = cell + g.key_diff[lane];
-            if (nk >= 0 && nk < g.key_max) {  // core.jl:98 — no per-axis wrap check
+            unsigned nk;
+            if (neighbour_pkey(g, home, (int)lane, nk)) {  // core.jl:98 — no per-axis wrap check
                 rb = cell_start[nk];
                 len = cell_start[nk + 1] - rb;
             }

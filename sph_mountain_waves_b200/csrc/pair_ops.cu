@@ -930,14 +930,13 @@ struct B_wcsph_momentum_fast : PairOpBase {
 template <int DIM, class Op>
 __global__ void __launch_bounds__(128)
 k_binary(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
-         const uint32_t *__restrict__ cell_start, int64_t n, int self,
-         unsigned long long *pair_counter, int col_lo, int col_hi) {
+         const uint32_t *__restrict__ cellx, const uint32_t *__restrict__ cell_start, int64_t n,
+         int self, unsigned long long *pair_counter, int col_lo, int col_hi) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const long long k0 = key[p];
+    const CellCoord home = cell_of(g, key[p], cellx[p]);
     if (col_lo > 0) {  // slab mode: only the columns [col_lo, col_hi] are evaluated
-        int col = (int)(k0 % g.lim[0]);
-        if (col < col_lo || col > col_hi) {
+        if (home.i < col_lo || home.i > col_hi) {
             Op::template skip<DIM>(f, out, p);
             return;
         }
@@ -947,8 +946,8 @@ k_binary(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ 
     const double px = f.s[S_X0][p], py = f.s[S_X1][p], pz = DIM == 3 ? f.s[S_X2][p] : 0.0;
     unsigned long long cnt = 0;
     for (int d = 0; d < g.ndiff; ++d) {
-        long long nk = k0 + g.key_diff[d];
-        if (nk < 0 || nk >= g.key_max) continue;  // core.jl:98 — no per-axis wrap check
+        unsigned nk;
+        if (!neighbour_pkey(g, home, d, nk)) continue;  // core.jl:98 — no per-axis wrap check
         uint32_t b = cell_start[nk], e = cell_start[nk + 1];
         for (uint32_t q = b; q < e; ++q) {
             // dist(p,q) — core.jl:8-10, algebra.jl:49-60: left-to-right, no FMA
@@ -979,7 +978,7 @@ k_binary(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ 
 // accepted pairs in traversal order (test hook)
 template <int DIM>
 __global__ void k_pairs(Fields f, Grid g, const uint32_t *__restrict__ key,
-                        const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ idx,
+                        const uint32_t *__restrict__ cellx, const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ idx,
                         const uint32_t *__restrict__ pos_of_idx, int64_t n,
                         const unsigned long long *__restrict__ offsets, long long *pi, long long *pj,
                         long long cap, unsigned long long *counts) {
@@ -987,12 +986,12 @@ __global__ void k_pairs(Fields f, Grid g, const uint32_t *__restrict__ key,
     if (i >= n) return;
     int64_t p = pos_of_idx[i];
     const double px = f.s[S_X0][p], py = f.s[S_X1][p], pz = DIM == 3 ? f.s[S_X2][p] : 0.0;
-    const long long k0 = key[p];
+    const CellCoord home = cell_of(g, key[p], cellx[p]);
     unsigned long long cnt = 0;
     unsigned long long base = offsets ? offsets[i] : 0;
     for (int d = 0; d < g.ndiff; ++d) {
-        long long nk = k0 + g.key_diff[d];
-        if (nk < 0 || nk >= g.key_max) continue;
+        unsigned nk;
+        if (!neighbour_pkey(g, home, d, nk)) continue;
         uint32_t b = cell_start[nk], e = cell_start[nk + 1];
         for (uint32_t q = b; q < e; ++q) {
             double dx = px - f.s[S_X0][q];
@@ -1036,11 +1035,11 @@ int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_
     CUDA_TRY(cudaMalloc(&counts, sizeof(unsigned long long) * (n + 1)));
     int rc = [&]() -> int {
         if (c->grid.dim == 2)
-            k_pairs<2><<<grid_for(n, 128), 128, 0, c->stream>>>(c->cur, c->grid, c->key, c->cell_start,
+            k_pairs<2><<<grid_for(n, 128), 128, 0, c->stream>>>(c->cur, c->grid, c->key, c->cellx, c->cell_start,
                                                                c->idx, c->pos_of_idx, n, nullptr,
                                                                nullptr, nullptr, 0, counts);
         else
-            k_pairs<3><<<grid_for(n, 128), 128, 0, c->stream>>>(c->cur, c->grid, c->key, c->cell_start,
+            k_pairs<3><<<grid_for(n, 128), 128, 0, c->stream>>>(c->cur, c->grid, c->key, c->cellx, c->cell_start,
                                                                c->idx, c->pos_of_idx, n, nullptr,
                                                                nullptr, nullptr, 0, counts);
         k_scan_u64_serial<<<1, 1, 0, c->stream>>>(counts, n, counts + n);
@@ -1053,11 +1052,11 @@ int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_
         CUDA_TRY(cudaMalloc(&dpi, sizeof(long long) * m));
         CUDA_TRY(cudaMalloc(&dpj, sizeof(long long) * m));
         if (c->grid.dim == 2)
-            k_pairs<2><<<grid_for(n, 128), 128, 0, c->stream>>>(c->cur, c->grid, c->key, c->cell_start,
+            k_pairs<2><<<grid_for(n, 128), 128, 0, c->stream>>>(c->cur, c->grid, c->key, c->cellx, c->cell_start,
                                                                c->idx, c->pos_of_idx, n, counts, dpi,
                                                                dpj, m, nullptr);
         else
-            k_pairs<3><<<grid_for(n, 128), 128, 0, c->stream>>>(c->cur, c->grid, c->key, c->cell_start,
+            k_pairs<3><<<grid_for(n, 128), 128, 0, c->stream>>>(c->cur, c->grid, c->key, c->cellx, c->cell_start,
                                                                c->idx, c->pos_of_idx, n, counts, dpi,
                                                                dpj, m, nullptr);
         CUDA_TRY(cudaGetLastError());
@@ -1158,10 +1157,10 @@ static int run_binary(sphmw_ctx *c, const char *name, int self, const Fields &ou
     TIMED(c, name);
     if (c->grid.dim == 2)
         k_binary<2, Op><<<grid_for(c->n, 128), 128, 0, c->stream>>>(
-            c->cur, out, c->prm, c->grid, c->key, c->cell_start, c->n, self, pc, col_lo, col_hi);
+            c->cur, out, c->prm, c->grid, c->key, c->cellx, c->cell_start, c->n, self, pc, col_lo, col_hi);
     else
         k_binary<3, Op><<<grid_for(c->n, 128), 128, 0, c->stream>>>(
-            c->cur, out, c->prm, c->grid, c->key, c->cell_start, c->n, self, pc, col_lo, col_hi);
+            c->cur, out, c->prm, c->grid, c->key, c->cellx, c->cell_start, c->n, self, pc, col_lo, col_hi);
     CUDA_TRY(cudaGetLastError());
     return SPHMW_OK;
 }
@@ -1182,17 +1181,17 @@ static int run_cell_pairs(sphmw_ctx *c, const char *name, const Fields &out, int
         col_hi = (int)c->grid.lim[0] - 1 - col_lo;
     }
     // persistent grid: a multiple of the SM count, warps stride over the cells
-    const long long warps_needed = (c->grid.key_max + 0);
+    const long long warps_needed = c->grid.pkey_max;
     long long blocks = (warps_needed + CP_WARPS - 1) / CP_WARPS;
     const long long max_blocks = (long long)c->sm_count * 8;
     if (blocks > max_blocks) blocks = max_blocks;
     TIMED(c, name);
     if (c->grid.dim == 2)
         k_cell_pairs<2, OP><<<(unsigned)blocks, CP_WARPS * 32, 0, c->stream>>>(
-            c->cur, out, c->prm, c->grid, c->cell_start, col_lo, col_hi, pc);
+            c->cur, out, c->prm, c->grid, c->cell_start, c->cellx, col_lo, col_hi, pc);
     else
         k_cell_pairs<3, OP><<<(unsigned)blocks, CP_WARPS * 32, 0, c->stream>>>(
-            c->cur, out, c->prm, c->grid, c->cell_start, col_lo, col_hi, pc);
+            c->cur, out, c->prm, c->grid, c->cell_start, c->cellx, col_lo, col_hi, pc);
     CUDA_TRY(cudaGetLastError());
     return SPHMW_OK;
 }

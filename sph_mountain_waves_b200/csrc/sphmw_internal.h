@@ -60,7 +60,54 @@ struct Grid {
     int key_diff[27];
     int ndiff;
     int dim;
+    // PHYSICAL cell order.  The reference key is i + Lx*(j + Ly*k) (structs.jl:102): x fastest
+    // over the whole domain length, so one x-y plane of cells can be tens of MB and the three
+    // planes a pass needs do not stay in L2.  Physically the cells are therefore ordered in
+    // x-chunks of 2^cx_shift columns: pkey = ((i >> s)*rows + rest << s) + (i & mask), with
+    // rest = j + Ly*k and rows = Ly*Lz.  Only the storage order changes: neighbour cells are
+    // still visited in the reference's key_diff order (nb_di/nb_drest hold each offset's
+    // column and row part), so every sum keeps its order.
+    int cx_shift;
+    long long rows;
+    long long pkey_max;
+    int nb_di[27];
+    int nb_drest[27];
 };
+
+#ifdef __CUDACC__
+// 32-bit cell arithmetic (all quantities < 2^31: sphmw_create checks pkey_max)
+struct CellCoord {
+    int i, rest;
+};
+__host__ __device__ __forceinline__ unsigned pkey_of(const Grid &g, int i, int rest) {
+    return ((((unsigned)(i >> g.cx_shift) * (unsigned)g.rows) + (unsigned)rest) << g.cx_shift) +
+           ((unsigned)i & ((1u << g.cx_shift) - 1u));
+}
+// column i is stored per particle (cellx), the row part follows from the physical key
+__host__ __device__ __forceinline__ CellCoord cell_of(const Grid &g, unsigned pk, unsigned i) {
+    CellCoord c;
+    c.i = (int)i;
+    c.rest = (int)((pk >> g.cx_shift) - (i >> g.cx_shift) * (unsigned)g.rows);
+    return c;
+}
+// neighbour cell number d of the reference's key_diff table (structs.jl:73-81).  The
+// reference only checks 1 <= key + dkey <= key_max (core.jl:98), so a column overflow wraps
+// into the adjacent row exactly as the linear key arithmetic does.
+__device__ __forceinline__ bool neighbour_pkey(const Grid &g, const CellCoord &c, int d, unsigned &pk) {
+    int i = c.i + g.nb_di[d], rest = c.rest + g.nb_drest[d];
+    const int lx = (int)g.lim[0];
+    if (i < 0) {
+        i += lx;
+        rest -= 1;
+    } else if (i >= lx) {
+        i -= lx;
+        rest += 1;
+    }
+    if (rest < 0 || rest >= (int)g.rows) return false;
+    pk = pkey_of(g, i, rest);
+    return true;
+}
+#endif
 
 // slab (multi-GPU) bookkeeping: local column c <-> global column slab_lo - GHOST_COLS + c
 #define GHOST_COLS 2
@@ -102,7 +149,8 @@ struct sphmw_ctx {
     uint32_t *halo_counters = nullptr;            // device: [0] left records [1] right records
                                                   // [2] left migrants [3] right migrants [4] lost
     uint32_t *h_halo_counters = nullptr;          // pinned mirror
-    uint32_t *key = nullptr;         // cell key per position (key_max = dead bucket)
+    uint32_t *key = nullptr;         // physical cell key per position (pkey_max = dead bucket)
+    uint32_t *cellx = nullptr, *cellx_alt = nullptr;  // cell column i of each position
     uint32_t *rank = nullptr;        // arrival rank inside the cell
     uint32_t *src = nullptr;         // new position -> old position
     uint32_t *cell_start = nullptr;  // key_max + 2 entries
