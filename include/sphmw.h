@@ -153,6 +153,19 @@ int sphmw_pvd_open(sphmw_ctx *ctx, const char *dir);
 int sphmw_pvd_save_frame(sphmw_ctx *ctx, const char *const *fields, int32_t nfields);
 int sphmw_pvd_close(sphmw_ctx *ctx);
 
+/* ≙ the file half of import_particles!(sys, path, ctor) — src/IO.jl:83-122 (ReadVTK.jl): a
+ * host-only reader of the PolyData files WriteVTK (and sphmw_pvd_save_frame) writes.  Array 0
+ * is "Points"; values come back as doubles, interleaved per point as stored. */
+typedef struct sphmw_vtp sphmw_vtp;
+int sphmw_vtp_open(const char *path, sphmw_vtp **out);
+int sphmw_vtp_close(sphmw_vtp *vtp);
+int sphmw_vtp_info(sphmw_vtp *vtp, int64_t *n_points, int32_t *n_arrays);
+int sphmw_vtp_array(sphmw_vtp *vtp, int32_t i, char *name, int64_t cap, int32_t *ncomp);
+int sphmw_vtp_read(sphmw_vtp *vtp, const char *name, double *out, int64_t n_values);
+/* stand-alone writer of the same format (what save_frame! emits for one frame) */
+int sphmw_vtp_write(const char *path, int64_t n, const double *points3n, int32_t nfields,
+                    const char *const *names, const int32_t *ncomps, const double *const *data);
+
 /* Per-kernel device timings accumulated since the last reset (CUDA events on the
  * context's stream).  names: newline-separated, ms/calls: one entry per name. */
 int sphmw_timing_enable(sphmw_ctx *ctx, int32_t enable);

@@ -746,6 +746,28 @@ static void ht_balance_of_momentum(particle *p, const particle *q, double r,
     for (int a = 0; a < 3; ++a) p->Dv[a] += f * x_pq[a];
     if (dot_product < 0.0) monaghan_av(p, q, r, s, x_pq, dot_product);
 }
+/* full_hopkins_perturbed_witch.jl:284-326 — total minus background pressure gradient */
+static void hf_balance_of_momentum(particle *p, const particle *q, double r,
+                                   const orc_system *s) {
+    const params *c = &s->prm;
+    double x_pq[3], v_pq[3];
+    for (int a = 0; a < 3; ++a) { x_pq[a] = p->x[a] - q->x[a]; v_pq[a] = p->v[a] - q->v[a]; }
+    double dot_product = dot3(x_pq, v_pq);
+    double prefac = q->m * pow(p->A * q->A, 1 / c->gamma);
+    double expfac = 1.0 - 2.0 / c->gamma;
+    double ker_i = rDW(s, p->h, r);
+    double ker_j = rDW(s, q->h, r);
+    double pP = fmax(c->P_floor, p->P);
+    double qP = fmax(c->P_floor, q->P);
+    double f_tot = -prefac * (pow(pP, expfac) * ker_i + pow(qP, expfac) * ker_j);
+    double prefac_bg = q->m * pow(p->A_bg * q->A_bg, 1 / c->gamma);
+    double pP_bg = fmax(c->P_floor, p->P_bg);
+    double qP_bg = fmax(c->P_floor, q->P_bg);
+    double f_bg = -prefac_bg * (pow(pP_bg, expfac) * ker_i + pow(qP_bg, expfac) * ker_j);
+    /* p.Dv += a_tot - a_bg  (vectors) */
+    for (int a = 0; a < 3; ++a) p->Dv[a] += f_tot * x_pq[a] - f_bg * x_pq[a];
+    if (dot_product < 0.0) monaghan_av(p, q, r, s, x_pq, dot_product);
+}
 /* hopkins_total_witch.jl:270-277 — NOT type-gated; gravity :225-228 */
 static void ht_move(particle *p, const orc_system *s) {
     for (int a = 0; a < 3; ++a) p->x[a] += s->prm.dt * p->v[a];
@@ -917,6 +939,7 @@ static const op_desc OPS[] = {
     {"hopkins_total.find_pot_temp", ht_find_pot_temp, NULL},
     {"hopkins_total.reset_density", ht_reset_density, NULL},
     {"hopkins_total.balance_of_momentum", NULL, ht_balance_of_momentum},
+    {"hopkins_full.balance_of_momentum", NULL, hf_balance_of_momentum},
     {"hopkins_total.move", ht_move, NULL},
     {"hopkins_total.accelerate", ht_accelerate, NULL},
     {"dambreak.balance_of_mass", NULL, d_balance_of_mass},
@@ -998,6 +1021,24 @@ static void verlet_hopkins(orc_system *s) {
     apply_binary(s, w_balance_of_momentum);
     apply_unary(s, w_accelerate);
 }
+/* full_hopkins_perturbed_witch.jl:350-374 (same sequence, its own momentum closure) */
+static void verlet_hopkins_full(orc_system *s) {
+    apply_unary(s, w_accelerate);
+    apply_unary(s, w_move);
+    orc_create_cell_list(s);
+    apply_unary(s, w_reset_density);
+    apply_binary(s, w_compute_density);
+    apply_unary(s, w_finalize_density);
+    apply_unary(s, w_update_smoothing);
+    orc_create_cell_list(s);
+    apply_unary(s, h_reset_pressure);
+    apply_binary(s, h_compute_pressure);
+    apply_unary(s, h_finalize_pressure);
+    apply_unary(s, w_find_temperature);
+    apply_unary(s, w_find_pot_temp);
+    apply_binary(s, hf_balance_of_momentum);
+    apply_unary(s, w_accelerate);
+}
 /* hopkins_total_witch.jl:283-308 */
 static void verlet_hopkins_total(orc_system *s) {
     apply_unary(s, ht_accelerate);
@@ -1045,6 +1086,7 @@ int orc_step(orc_system *s, const char *scheme, int nsteps) {
     if (!strcmp(scheme, "wcsph")) f = verlet_wcsph;
     else if (!strcmp(scheme, "hopkins")) f = verlet_hopkins;
     else if (!strcmp(scheme, "hopkins_total")) f = verlet_hopkins_total;
+    else if (!strcmp(scheme, "hopkins_full")) f = verlet_hopkins_full;
     else if (!strcmp(scheme, "dambreak")) f = step_dambreak;
     else if (!strcmp(scheme, "collision")) f = step_collision;
     if (!f) return -1;

@@ -12,7 +12,7 @@ from .grids import (BodycenteredGrid, CubicGrid, DiamondGrid, FacecenteredGrid, 
                     Squaregrid, covering, dimension)
 from .system import (DataStorage, Operator, ParticleField, ParticleSystem, ParticleType, apply,  # noqa: F401
                      apply_binary, apply_unary, create_cell_list, generate_particles, new_pvd_file,
-                     op_menu, save_frame, save_pvd_file)
+                     import_particles, op_menu, read_vtp, save_frame, save_pvd_file, write_vtp)
 from . import kernels  # noqa: F401
 
 __version__ = "0.1.0"

@@ -73,6 +73,13 @@ _SIGS = {
     "sphmw_pvd_open": (C.c_int, [_P, C.c_char_p]),
     "sphmw_pvd_save_frame": (C.c_int, [_P, C.POINTER(C.c_char_p), C.c_int32]),
     "sphmw_pvd_close": (C.c_int, [_P]),
+    "sphmw_vtp_open": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "sphmw_vtp_close": (C.c_int, [_P]),
+    "sphmw_vtp_info": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "sphmw_vtp_array": (C.c_int, [_P, C.c_int32, C.c_char_p, C.c_int64, C.POINTER(C.c_int32)]),
+    "sphmw_vtp_read": (C.c_int, [_P, C.c_char_p, C.c_void_p, C.c_int64]),
+    "sphmw_vtp_write": (C.c_int, [C.c_char_p, C.c_int64, C.c_void_p, C.c_int32, C.POINTER(C.c_char_p),
+                                  C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]),
     "sphmw_timing_enable": (C.c_int, [_P, C.c_int32]),
     "sphmw_timing_reset": (C.c_int, [_P]),
     "sphmw_timing_report": (C.c_int64, [_P, C.c_char_p, C.c_int64, C.POINTER(C.c_double),

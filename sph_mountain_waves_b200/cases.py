@@ -93,18 +93,21 @@ def bell_hill_3d(nx: int, ny: int, nz: int, h_m: float = 100.0, a: float = 10e3,
 
 def hopkins_2d(variant: str = "hopkins", n_y: float = 20.0, dom_length: float = 60e3, **kw) -> Case:
     """The pressure-entropy drivers on the same lattice: `variant` = "hopkins"
-    (src/current/hopkins_perturbed_witch.jl) or "hopkins_total" (hopkins_total_witch.jl).
+    (src/current/hopkins_perturbed_witch.jl), "hopkins_full" (full_hopkins_perturbed_witch.jl,
+    adds A_bg = P_bg / rho_bg^gamma, :198-203) or "hopkins_total" (hopkins_total_witch.jl).
     Their constructors add A = P / rho^gamma and write m = rho * dr^2
     (hopkins_perturbed_witch.jl:146-147, hopkins_total_witch.jl:118-119)."""
     c = mountain_wave_2d(n_y=n_y, dom_length=dom_length, name=f"{variant}_2d_ny{n_y:g}", **kw)
     gamma = c.params["gamma"]
     dr = c.info["dr"]
     f = c.fields
-    if variant == "hopkins":
+    if variant in ("hopkins", "hopkins_full"):
         f["m"] = f["rho"] * (dr * dr)
     else:
         f["m"] = f["rho"] * dr * dr
     f["A"] = f["P"] / f["rho"] ** gamma
+    if variant == "hopkins_full":
+        f["A_bg"] = f["P_bg"] / f["rho_bg"] ** gamma
     if variant == "hopkins_total":
         # 11-field particle (hopkins_total_witch.jl:83-95)
         for k in ("rho_bg", "rho_p", "P_bg", "P_p", "theta_bg", "theta_p", "T_bg", "T_p"):

@@ -517,6 +517,74 @@ struct B_ht_momentum : PairOpBase {
     }
 };
 
+// balance_of_momentum!  full_hopkins_perturbed_witch.jl:284-326
+struct B_hf_momentum : PairOpBase {
+    MomentumState s;
+    double A, A_bg, P_bg;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &c, int64_t p) {
+        s.dv0 = PF(S_DV0);
+        s.dv1 = PF(S_DV1);
+        s.dv2 = DIM == 3 ? PF(S_DV2) : 0.0;
+        s.v0 = PF(S_V0);
+        s.v1 = PF(S_V1);
+        s.v2 = DIM == 3 ? PF(S_V2) : 0.0;
+        s.hp = PF(S_H);
+        s.rho = PF(S_RHO);
+        s.prho = jl_max(s.rho, c.rho_floor);
+        s.P = PF(S_P);
+        A = PF(S_A);
+        A_bg = PF(S_A_BG);
+        P_bg = PF(S_P_BG);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        double vx = s.v0 - QF(S_V0), vy = s.v1 - QF(S_V1);
+        double dot_product = dx * vx + dy * vy;
+        if (DIM == 3) {
+            double vz = s.v2 - QF(S_V2);
+            dot_product = dot_product + dz * vz;
+        }
+        double qm = QF(S_M), qh = QF(S_H), qPraw = QF(S_P);
+        double prefac = qm * pow(A * QF(S_A), 1 / c.gamma);
+        double expfac = 1.0 - 2.0 / c.gamma;
+        double ker_i = sph_rDW<DIM>(s.hp, r);
+        double ker_j = sph_rDW<DIM>(qh, r);
+        double pP = jl_max(c.P_floor, s.P);
+        double qP = jl_max(c.P_floor, qPraw);
+        double f_tot = -prefac * (pow(pP, expfac) * ker_i + pow(qP, expfac) * ker_j);
+        double prefac_bg = qm * pow(A_bg * QF(S_A_BG), 1 / c.gamma);
+        double pP_bg = jl_max(c.P_floor, P_bg);
+        double qP_bg = jl_max(c.P_floor, QF(S_P_BG));
+        double f_bg = -prefac_bg * (pow(pP_bg, expfac) * ker_i + pow(qP_bg, expfac) * ker_j);
+        s.dv0 += f_tot * dx - f_bg * dx;  // p.Dv += a_tot - a_bg
+        s.dv1 += f_tot * dy - f_bg * dy;
+        if (DIM == 3) s.dv2 += f_tot * dz - f_bg * dz;
+        if (dot_product < 0.0) {
+            double h_ij = 0.5 * (s.hp + qh);
+            double ker_ij = sph_rDW<DIM>(h_ij, r);
+            double qrho = jl_max(QF(S_RHO), c.rho_floor);
+            double c_i = sqrt(c.gamma * s.P / s.prho);
+            double c_j = sqrt(c.gamma * qPraw / qrho);
+            double c_ij = 0.5 * (c_i + c_j);
+            double rho_ij = 0.5 * (s.prho + qrho);
+            double mu_ij = (h_ij * dot_product) / (r * r + c.eps * h_ij * h_ij);
+            double pi_ij = (-c.alpha * c_ij * mu_ij + c.beta * mu_ij * mu_ij) / rho_ij;
+            double fv = -qm * pi_ij * ker_ij;
+            s.dv0 += fv * dx;
+            s.dv1 += fv * dy;
+            if (DIM == 3) s.dv2 += fv * dz;
+        }
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_DV0) = s.dv0;
+        PF(S_DV1) = s.dv1;
+        if (DIM == 3) PF(S_DV2) = s.dv2;
+    }
+};
+
 // balance_of_mass!  collapse_dry.jl:112-115 (fixed h = kh, fixed mass m)
 struct B_dam_mass : PairOpBase {
     double drho, v0, v1, v2, rho;
@@ -1245,6 +1313,8 @@ static const OpEntry OPS[] = {
     UNARY_ENTRY("hopkins_total.reset_density", U_ht_reset_density, SL(S_TYPE), SL(S_RHO), ),
     BINARY_ENTRY("hopkins_total.balance_of_momentum", B_ht_momentum,
                  SL(S_X0, S_V0, S_H, S_M, S_RHO, S_P, S_A), SL(S_DV0), c->dv_zero = false),
+    BINARY_ENTRY("hopkins_full.balance_of_momentum", B_hf_momentum,
+                 SL(S_X0, S_V0, S_H, S_M, S_RHO, S_P, S_P_BG, S_A, S_A_BG), SL(S_DV0), c->dv_zero = false),
     UNARY_ENTRY("hopkins_total.move", U_ht_move, SL(S_V0), SL(S_X0), c->cell_list_valid = false),
     UNARY_ENTRY("hopkins_total.accelerate", U_ht_accelerate, SL(S_X0, S_DV0), SL(S_V0, S_DV0),
                 c->dv_zero = true),
@@ -1436,6 +1506,15 @@ int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps) {
                               "hopkins.reset_pressure", "hopkins.compute_pressure",
                               "hopkins.finalize_pressure", "wcsph.find_temperature",
                               "wcsph.find_pot_temp", "wcsph.balance_of_momentum",
+                              "wcsph.accelerate"}));
+        } else if (!strcmp(scheme, "hopkins_full")) {
+            // full_hopkins_perturbed_witch.jl:350-374
+            TRY(apply_seq(c, {"wcsph.accelerate", "wcsph.move", "create_cell_list",
+                              "wcsph.reset_density", "wcsph.compute_density",
+                              "wcsph.finalize_density", "wcsph.update_smoothing",
+                              "hopkins.reset_pressure", "hopkins.compute_pressure",
+                              "hopkins.finalize_pressure", "wcsph.find_temperature",
+                              "wcsph.find_pot_temp", "hopkins_full.balance_of_momentum",
                               "wcsph.accelerate"}));
         } else if (!strcmp(scheme, "hopkins_total")) {
             // hopkins_total_witch.jl:283-308

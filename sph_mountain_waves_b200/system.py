@@ -418,3 +418,52 @@ def save_pvd_file(data: DataStorage):
     """≙ save_pvd_file(data) — src/IO.jl:33-35"""
     if data.sys is not None:
         check(_capi.lib().sphmw_pvd_close(data.sys.ctx))
+
+
+def read_vtp(path: str) -> Dict[str, np.ndarray]:
+    """All arrays of a PolyData .vtp file: "Points" (N,3) plus every PointData array,
+    (N,) or (N,ncomp).  Host-only (libsphmw's reader, no GPU)."""
+    lib = _capi.lib()
+    h = C.c_void_p()
+    check(lib.sphmw_vtp_open(path.encode(), C.byref(h)))
+    try:
+        n, na = C.c_int64(), C.c_int32()
+        check(lib.sphmw_vtp_info(h, C.byref(n), C.byref(na)))
+        out = {}
+        for i in range(na.value):
+            name = C.create_string_buffer(256)
+            nc = C.c_int32()
+            check(lib.sphmw_vtp_array(h, i, name, 256, C.byref(nc)))
+            a = np.empty(n.value * nc.value, dtype=np.float64)
+            check(lib.sphmw_vtp_read(h, name.value, _capi.ptr(a), a.size))
+            out[name.value.decode()] = a.reshape(n.value, nc.value) if nc.value > 1 else a
+        return out
+    finally:
+        lib.sphmw_vtp_close(h)
+
+
+def write_vtp(path: str, points: np.ndarray, fields: Dict[str, np.ndarray]):
+    """One frame in WriteVTK's layout (what save_frame! writes), from host arrays."""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    names = list(fields)
+    arrs = [np.ascontiguousarray(fields[k], dtype=np.float64) for k in names]
+    nc = (C.c_int32 * len(names))(*[1 if a.ndim == 1 else a.shape[1] for a in arrs])
+    cn = (C.c_char_p * len(names))(*[k.encode() for k in names])
+    dp = (C.c_void_p * len(names))(*[a.ctypes.data for a in arrs])
+    check(_capi.lib().sphmw_vtp_write(path.encode(), len(pts), _capi.ptr(pts), len(names), cn, nc, dp))
+
+
+def import_particles(sys: ParticleSystem, path: str, particle_constructor: Callable):
+    """≙ import_particles!(sys, path, ctor) — src/IO.jl:83-122: particles are created by
+    `ctor(x)` at the file's points, then every field whose name matches a PointData array is
+    overwritten with the file's values; the new particles are appended to `sys`."""
+    data = read_vtp(path)
+    x = data["Points"]
+    fields = dict(particle_constructor(x))
+    fields["x"] = x
+    for name in sys.T.fields:
+        for key in (name, ALIASES_INV.get(name)):
+            if key is not None and key in data and name != "x":
+                fields[name] = data[key]
+    sys.append(fields)
+    return len(x)

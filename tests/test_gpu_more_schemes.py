@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
 
-@pytest.mark.parametrize("variant", ["hopkins", "hopkins_total"])
+@pytest.mark.parametrize("variant", ["hopkins", "hopkins_full", "hopkins_total"])
 def test_hopkins_steps_vs_oracle(gpu, variant):
     """+1 binary pass with pow per pair (hopkins_perturbed_witch.jl:205-214,
     hopkins_total_witch.jl:233-308)"""
@@ -162,3 +162,33 @@ def test_pvd_frames_round_trip(gpu, tmp_path):
     assert np.array_equal(arr["connectivity"], np.arange(n)) and np.array_equal(arr["offsets"], np.arange(1, n + 1))
     n0, arr0 = read_vtp(tmp_path / "res" / "frame0.vtp")
     assert np.array_equal(arr0["ρ"], case.fields["rho"])
+
+
+def test_import_particles_restart(gpu, tmp_path):
+    """≙ sph_jl/tests/test_IO.jl:45-60: what save_frame! wrote is imported back exactly, and
+    importing twice doubles the particle count (IO.jl:87-89)"""
+    from sph_mountain_waves_b200 import import_particles
+    from sph_mountain_waves_b200.schemes import wcsph_perturbed_witch as w
+    case = cases.mountain_wave_2d(n_y=16.0, dom_length=40e3, h_m=2000.0, a=8e3, U=15.0)
+    s = load_gpu(case)
+    s.create_cell_list()
+    s.step(6)
+    out = new_pvd_file(str(tmp_path / "chk"))
+    names = ("h", "m", "v", "ρ", "ρ′", "type")
+    save_frame(out, s, *names)
+    save_pvd_file(out)
+    k = w.Constants(n_y=16.0, dom_length=40e3, h_m=2000.0, a=8e3, U=15.0)
+    s2 = cases.to_system(cases.Case(case.name, case.scheme, 2, case.box_min, case.box_max, case.h,
+                                    case.params, {f: a[:0] for f, a in case.fields.items()}))
+    n = import_particles(s2, str(tmp_path / "chk" / "frame0.vtp"), w.particle_ctor(k, 0.0, w.FLUID))
+    assert n == len(s) == len(s2)
+    for f in ("x",) + names:
+        assert np.array_equal(s2.field(f), s.field(f)), f
+    # a restarted run continues exactly like the original (carried state is complete)
+    s2.create_cell_list()
+    s.step(5)
+    s2.step(5)
+    for f in ("x", "v", "ρ"):
+        assert np.array_equal(s2.field(f), s.field(f)), f
+    import_particles(s2, str(tmp_path / "chk" / "frame0.vtp"), w.particle_ctor(k, 0.0, w.FLUID))
+    assert len(s2) == 2 * n
