@@ -82,7 +82,8 @@ int sphmw_sync(sphmw_ctx *ctx);
 /* Driver constants, ≙ the module-level `const`s of a driver
  * (src/current/wcsph_perturbed_witch.jl:25-75; collapse_dry.jl:30-66).
  * Names: dt g c gamma alpha beta eps eta rho0 R_mass R_gas T_bg rho_floor P_floor
- * z_t z_b gamma_r fluid m nu mu gx gy gz kh dt_pack c_pack zeta_pack */
+ * z_t z_b gamma_r fluid m nu mu gx gy gz kh dt_pack c_pack zeta_pack
+ * U_max cp bc_width x_inflow dr inflow */
 int sphmw_set_param(sphmw_ctx *ctx, const char *name, double value);
 int sphmw_get_param(sphmw_ctx *ctx, const char *name, double *value);
 
@@ -119,9 +120,17 @@ int64_t sphmw_op_list(char *buf, int64_t cap);
 
 /* Fused fast path ≙ `for k in 1:nsteps verlet_step!(sys) end`
  * (wcsph_perturbed_witch.jl:309-332, :371-373).  scheme: "wcsph" | "hopkins" |
- * "hopkins_total" | "dambreak" | "collision".  Must leave the same state as the
+ * "hopkins_full" | "hopkins_total" | "dambreak" | "collision" | "flow".  Must leave the same state as the
  * operator-by-operator sequence. */
 int sphmw_step(sphmw_ctx *ctx, const char *scheme, int32_t nsteps);
+
+/* ≙ add_new_particles!(sys) of the constant-U flow drivers —
+ * src/legacy/isothermal_flow_witch.jl:175-186: every INFLOW particle that has entered the
+ * domain (x[1] >= x_inflow) becomes FLUID and a new INFLOW particle is appended bc_width
+ * upstream of it, built like the driver's Particle constructor (:72-82).  New particles get
+ * the next indices in the order the reference's loop would create them.  Parameters used:
+ * inflow, fluid, x_inflow, bc_width, U_max, dr, rho0, g, R_mass, R_gas, cp, T_bg. */
+int sphmw_flow_add_new_particles(sphmw_ctx *ctx, int64_t *n_added);
 
 /* Test hooks for bit-exact cell assignment / neighbour-pair parity. */
 /* 0-based cell key of every particle, reference index order (structs.jl:97-106) */

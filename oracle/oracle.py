@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
         l.orc_pairs.argtypes = [P, C.c_void_p, C.c_void_p, C.c_int64]
         l.orc_apply.argtypes = [P, C.c_char_p, C.c_int]
         l.orc_step.argtypes = [P, C.c_char_p, C.c_int]
+        l.orc_flow_add_new_particles.restype = C.c_int64
+        l.orc_flow_add_new_particles.argtypes = [P]
         for k in ("wendland1", "Dwendland1", "rDwendland1", "wendland2", "Dwendland2", "rDwendland2",
                   "wendland3", "Dwendland3", "rDwendland3", "DDwendland3", "spline23", "Dspline23",
                   "rDspline23", "spline24", "Dspline24", "rDspline24"):
@@ -169,6 +171,9 @@ class OracleSystem:
     def step(self, scheme: str, nsteps: int = 1):
         if lib().orc_step(self._h, scheme.encode(), nsteps) != 0:
             raise KeyError(f"oracle has no scheme {scheme!r}")
+
+    def flow_add_new_particles(self) -> int:
+        return int(lib().orc_flow_add_new_particles(self._h))
 
     def cell_keys(self) -> np.ndarray:
         k = np.empty(self.n, dtype=np.int64)

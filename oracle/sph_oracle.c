@@ -82,6 +82,8 @@ typedef struct {
     double rho_floor, P_floor, z_t, z_b, gamma_r, fluid;
     double m, nu, mu, gx, gy, gz, kh; /* fixed-mass / fixed-h examples */
     double dt_pack, c_pack, zeta_pack; /* utils/new_packing.jl:1-3 */
+    /* legacy flow drivers: src/legacy/isothermal_flow_witch.jl:24-60 */
+    double U_max, cp, bc_width, x_inflow, dr, inflow;
 } params;
 
 typedef struct {
@@ -99,7 +101,9 @@ static const param_desc PARAMS[] = {
     {"fluid", POFF(fluid)},     {"m", POFF(m)},         {"nu", POFF(nu)},
     {"mu", POFF(mu)},           {"gx", POFF(gx)},       {"gy", POFF(gy)},
     {"gz", POFF(gz)},           {"kh", POFF(kh)},       {"dt_pack", POFF(dt_pack)},
-    {"c_pack", POFF(c_pack)},   {"zeta_pack", POFF(zeta_pack)}, {NULL, 0}};
+    {"c_pack", POFF(c_pack)},   {"zeta_pack", POFF(zeta_pack)}, {"U_max", POFF(U_max)},
+    {"cp", POFF(cp)},           {"bc_width", POFF(bc_width)},   {"x_inflow", POFF(x_inflow)},
+    {"dr", POFF(dr)},           {"inflow", POFF(inflow)},       {NULL, 0}};
 
 /* structs.jl:22-26 — cell = growable index vector + lock */
 typedef struct {
@@ -912,6 +916,93 @@ static void p_move(particle *p, const orc_system *s) {
 }
 
 /* ------------------------------------------------------------------------- */
+/* src/legacy/isothermal_flow_witch.jl — constant-U flow over the mountain    */
+/* with inflow re-seeding.  Field u is stored in v, Du in Dv.  */
+/* T is the driver's constant temperature (params.T_bg), h its fixed kernel   */
+/* radius (params.kh).                                                        */
+/* ------------------------------------------------------------------------- */
+/* :140-143 */
+static void f_balance_of_mass(particle *p, const particle *q, double r, const orc_system *s) {
+    double ker = q->m * orc_rDwendland2(s->prm.kh, r);
+    double x_pq[3], u_pq[3];
+    for (int a = 0; a < 3; ++a) { x_pq[a] = p->x[a] - q->x[a]; u_pq[a] = p->v[a] - q->v[a]; }
+    p->Drho += ker * dot3(x_pq, u_pq);
+}
+/* :145-150 */
+static void f_internal_force(particle *p, const particle *q, double r, const orc_system *s) {
+    const params *c = &s->prm;
+    double ker = q->m * orc_rDwendland2(c->kh, r);
+    double x_pq[3], u_pq[3];
+    for (int a = 0; a < 3; ++a) { x_pq[a] = p->x[a] - q->x[a]; u_pq[a] = p->v[a] - q->v[a]; }
+    double a1 = -ker * (p->P / pow2(p->rho) + q->P / pow2(q->rho));
+    for (int a = 0; a < 3; ++a) p->Dv[a] += a1 * x_pq[a];
+    double a2 = 8.0 * ker * c->mu / (p->rho * q->rho) * dot3(u_pq, x_pq) / (r * r + 0.01 * c->kh * c->kh);
+    for (int a = 0; a < 3; ++a) p->Dv[a] += a2 * x_pq[a];
+}
+/* :156-160 */
+static void f_find_pressure(particle *p, const orc_system *s) {
+    const params *c = &s->prm;
+    p->rho += p->Drho * c->dt;
+    p->Drho = 0.0;
+    p->P = p->rho * c->R_mass * c->T_bg;
+}
+/* :162-164 */
+static void f_set_density(particle *p, const orc_system *s) {
+    const params *c = &s->prm;
+    p->rho = c->rho0 * exp(-p->x[1] * c->g / (c->R_mass * c->T_bg));
+}
+/* :167-169 */
+static void f_find_pot_temp(particle *p, const orc_system *s) {
+    const params *c = &s->prm;
+    p->th = c->T_bg * pow((c->T_bg * c->R_gas * c->rho0) / p->P, c->R_gas / c->cp);
+}
+/* :204-209 */
+static void f_move(particle *p, const orc_system *s) {
+    const params *c = &s->prm;
+    p->Dv[0] = p->Dv[1] = p->Dv[2] = 0.0;
+    if (p->type == c->fluid || p->type == c->inflow)
+        for (int a = 0; a < 3; ++a) p->x[a] += c->dt * p->v[a];
+}
+/* :211-215 with damping_structure :192-198 (a positive scalar here) */
+static void f_accelerate(particle *p, const orc_system *s) {
+    const params *c = &s->prm;
+    if (p->type == c->fluid) {
+        static const double ey[3] = {0.0, 1.0, 0.0};
+        double damp = 0.0;
+        if (p->x[1] >= (c->z_t - c->z_b)) {
+            double sn = sin(M_PI / 2 * (1 - (c->z_t - c->z_b) / c->z_b));
+            damp = c->gamma_r * (sn * sn);
+        }
+        for (int a = 0; a < 3; ++a) p->v[a] += 0.5 * c->dt * (p->Dv[a] - c->g * ey[a] - damp * ey[a]);
+    }
+}
+/* :175-186 add_new_particles! with the Particle constructor :72-82 */
+int64_t orc_flow_add_new_particles(orc_system *s) {
+    const params *c = &s->prm;
+    int64_t n0 = s->n, added = 0;
+    for (int64_t i = 0; i < n0; ++i) {
+        particle *p = s->p[i];
+        if (p->type == c->inflow && p->x[0] >= c->x_inflow) {
+            p->type = c->fluid;
+            orc_append(s, 1);
+            particle *q = s->p[s->n - 1];
+            static const double ex[3] = {1.0, 0.0, 0.0};
+            for (int a = 0; a < 3; ++a) {
+                q->x[a] = p->x[a] - c->bc_width * ex[a];
+                q->v[a] = c->U_max * ex[a];
+            }
+            q->type = c->inflow;
+            q->rho = c->rho0 * exp(-q->x[1] * c->g / (c->R_mass * c->T_bg));
+            q->m = q->rho * pow2(c->dr);
+            q->P = q->rho * c->T_bg * c->R_mass;
+            q->th = c->T_bg * pow((c->T_bg * c->R_gas * c->rho0) / q->P, c->R_gas / c->cp);
+            ++added;
+        }
+    }
+    return added;
+}
+
+/* ------------------------------------------------------------------------- */
 /* operator menu (names shared with the product's enum so tests read alike)   */
 /* ------------------------------------------------------------------------- */
 typedef struct {
@@ -955,6 +1046,13 @@ static const op_desc OPS[] = {
     {"collision.reset_rho", c_reset_rho, NULL},
     {"collision.move", c_move, NULL},
     {"collision.accelerate", c_accelerate, NULL},
+    {"flow.balance_of_mass", NULL, f_balance_of_mass},
+    {"flow.internal_force", NULL, f_internal_force},
+    {"flow.find_pressure", f_find_pressure, NULL},
+    {"flow.set_density", f_set_density, NULL},
+    {"flow.find_pot_temp", f_find_pot_temp, NULL},
+    {"flow.move", f_move, NULL},
+    {"flow.accelerate", f_accelerate, NULL},
     {"packing.reset_rho", p_reset_rho, NULL},
     {"packing.accumulate_rho", NULL, p_accumulate_rho},
     {"packing.balance_of_momentum", NULL, p_balance_of_momentum},
@@ -1068,6 +1166,18 @@ static void step_dambreak(orc_system *s) {
     apply_binary(s, d_internal_force);
     apply_unary(s, d_accelerate);
 }
+/* isothermal_flow_witch.jl:221-232 */
+static void step_flow(orc_system *s) {
+    apply_unary(s, f_accelerate);
+    apply_unary(s, f_move);
+    orc_flow_add_new_particles(s);
+    orc_create_cell_list(s);
+    apply_binary(s, f_balance_of_mass);
+    apply_unary(s, f_find_pressure);
+    apply_unary(s, f_find_pot_temp);
+    apply_binary(s, f_internal_force);
+    apply_unary(s, f_accelerate);
+}
 /* test_collision_2d.jl:106-116 */
 static void step_collision(orc_system *s) {
     apply_unary(s, c_accelerate);
@@ -1089,6 +1199,7 @@ int orc_step(orc_system *s, const char *scheme, int nsteps) {
     else if (!strcmp(scheme, "hopkins_full")) f = verlet_hopkins_full;
     else if (!strcmp(scheme, "dambreak")) f = step_dambreak;
     else if (!strcmp(scheme, "collision")) f = step_collision;
+    else if (!strcmp(scheme, "flow")) f = step_flow;
     if (!f) return -1;
     for (int k = 0; k < nsteps; ++k) f(s);
     return 0;

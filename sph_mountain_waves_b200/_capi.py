@@ -63,6 +63,7 @@ _SIGS = {
     "sphmw_apply": (C.c_int, [_P, C.c_char_p, C.c_int32]),
     "sphmw_op_list": (C.c_int64, [C.c_char_p, C.c_int64]),
     "sphmw_step": (C.c_int, [_P, C.c_char_p, C.c_int32]),
+    "sphmw_flow_add_new_particles": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "sphmw_cell_keys": (C.c_int, [_P, C.c_void_p, C.c_int64]),
     "sphmw_cell_entries": (C.c_int, [_P, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "sphmw_pairs_dump": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),

@@ -116,6 +116,62 @@ def hopkins_2d(variant: str = "hopkins", n_y: float = 20.0, dom_length: float = 
     return c
 
 
+def flow_2d(n_y: float = 100.0, dom_length: float = 100e3, h_m: float = 13e3, a: float = 10e3,
+            U_max: float = 20.0) -> Case:
+    """The constant-U flow driver with inflow re-seeding and outflow by domain removal —
+    src/legacy/isothermal_flow_witch.jl:24-134 (the spec of SURVEY §8 f2).  That file cannot be
+    loaded in the reference (it includes a missing packing module); the packing pre-step
+    (:120) is therefore skipped here, everything else of make_system() is reproduced:
+    square lattice, FLUID / MOUNTAIN / INFLOW / WALL groups in that order, OUTFLOW particles
+    filtered out (:122), initialize_system!, set_density!, find_pressure!, find_pot_temp!."""
+    dom_height = 26e3
+    dr = dom_height / n_y
+    h = 1.8 * dr
+    bc_width = 6 * dr
+    rho0, mu = 1.393, 15.98e-6
+    c = math.sqrt(65e3 * (7 / 5) / rho0)
+    N = math.sqrt(0.0196)
+    g, R_mass, R_gas = 9.81, 287.05, 8.314
+    cp = 7 * R_gas / 2
+    T = 250.0
+    dt = 0.01 * h / c
+    FLUID, INFLOW, OUTFLOW, WALL, MOUNTAIN = 0.0, 1.0, 2.0, 3.0, 4.0
+    grid = Grid(dr, "square")
+    L2 = dom_length / 2.0
+    domain = Rectangle(-L2, 0.0, L2, dom_height)
+    fence = BoundaryLayer(domain, grid, bc_width)
+    ground = Specification(fence, lambda x: x[:, 1] < 0)
+    sky = Specification(fence, lambda x: x[:, 1] > dom_height)
+    wind = Specification(fence, lambda x: (x[:, 0] <= -L2) & (x[:, 1] >= 0) & (x[:, 1] <= dom_height))
+    sink = Specification(fence, lambda x: (x[:, 0] >= L2) & (x[:, 1] >= 0) & (x[:, 1] <= dom_height))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mountain = Specification(domain, lambda x: x[:, 1] <= (h_m * a ** 2) / (x[:, 0] ** 2 + a ** 2))
+        groups = [(covering(grid, domain - mountain), FLUID), (covering(grid, mountain), MOUNTAIN),
+                  (covering(grid, wind), INFLOW), (covering(grid, sink), OUTFLOW),
+                  (covering(grid, ground + sky), WALL)]
+    x = np.concatenate([g_[0] for g_ in groups])
+    typ = np.concatenate([np.full(len(g_[0]), g_[1]) for g_ in groups])
+    keep = typ != OUTFLOW                       # :122 filter!
+    x, typ = x[keep], typ[keep]
+    n = len(x)
+    # Particle constructor :72-82, then :124-128
+    rho = rho0 * np.exp(-x[:, 1] * g / (R_mass * T))
+    m = rho * (dr * dr)
+    u = np.zeros((n, 3))
+    u[(typ == FLUID) | (typ == INFLOW), 0] = U_max      # initialize_system! :140-146
+    rho = rho0 * np.exp(-x[:, 1] * g / (R_mass * T))    # set_density!
+    P = rho * R_mass * T                                # find_pressure! (Drho = 0)
+    theta = T * ((T * R_gas * rho0) / P) ** (R_gas / cp)
+    fields = {"x": x, "v": u, "Dv": np.zeros((n, 3)), "rho": rho, "Drho": np.zeros(n), "m": m, "P": P,
+              "theta": theta, "type": typ}
+    params = dict(dt=dt, g=g, c=c, rho0=rho0, R_mass=R_mass, R_gas=R_gas, T_bg=T, mu=mu, kh=h,
+                  z_t=dom_height, z_b=12e3, gamma_r=10 * N, fluid=FLUID, inflow=INFLOW, U_max=U_max, cp=cp,
+                  bc_width=bc_width, x_inflow=-L2, dr=dr)
+    box = (domain + fence).boundarybox()
+    return Case("flow_2d", "flow", 2, (box.x1_min, box.x2_min, 0.0), (box.x1_max, box.x2_max, 0.0), h, params,
+                fields, dict(dr=dr, dt=dt))
+
+
 def collapse_dry(dr: float = 1.5e-2) -> Case:
     """BASELINE config 1 (C1) — sph_jl/examples/collapse_dry.jl:30-106."""
     # :42-62

@@ -78,7 +78,9 @@ static const ParamDesc PARAM_TABLE[] = {
     {"fluid", POFF(fluid)},     {"m", POFF(m)},         {"nu", POFF(nu)},
     {"mu", POFF(mu)},           {"gx", POFF(gx)},       {"gy", POFF(gy)},
     {"gz", POFF(gz)},           {"kh", POFF(kh)},       {"dt_pack", POFF(dt_pack)},
-    {"c_pack", POFF(c_pack)},   {"zeta_pack", POFF(zeta_pack)}, {nullptr, 0}};
+    {"c_pack", POFF(c_pack)},   {"zeta_pack", POFF(zeta_pack)}, {"U_max", POFF(U_max)},
+    {"cp", POFF(cp)},           {"bc_width", POFF(bc_width)},   {"x_inflow", POFF(x_inflow)},
+    {"dr", POFF(dr)},           {"inflow", POFF(inflow)},       {nullptr, 0}};
 
 static void derive_params(Params &p) {
     // damping_structure, wcsph_perturbed_witch.jl:245-251: a constant vector.
@@ -709,6 +711,11 @@ extern "C" int sphmw_step_phase(sphmw_ctx *c, const char *scheme, int32_t phase)
     if (!c || !scheme) { sphmw_set_error("bad argument"); return SPHMW_E_INVALID; }
     CUDA_TRY(cudaSetDevice(c->device));
     return sphmw_step_scheme_phase(c, scheme, phase);
+}
+extern "C" int sphmw_flow_add_new_particles(sphmw_ctx *c, int64_t *n_added) {
+    if (!c) return SPHMW_E_INVALID;
+    CUDA_TRY(cudaSetDevice(c->device));
+    return sphmw_flow_add_particles(c, n_added);
 }
 extern "C" int sphmw_pairs_dump(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n) {
     if (!c || !n) return SPHMW_E_INVALID;

@@ -183,6 +183,17 @@ static int exclusive_scan(sphmw_ctx *c, uint32_t *data, int64_t n, uint32_t *tmp
     return SPHMW_OK;
 }
 
+int sphmw_exclusive_scan_u32(sphmw_ctx *c, uint32_t *data, int64_t n) {
+    int64_t need = n / SCAN_TILE * 2 + 4096;
+    if (!c->scan_tmp || c->scan_tmp_len < need) {
+        cudaFree(c->scan_tmp);
+        c->scan_tmp = nullptr;
+        c->scan_tmp_len = std::max<int64_t>(need, (c->grid.pkey_max + 2) / SCAN_TILE * 2 + 4096);
+        CUDA_TRY(cudaMalloc(&c->scan_tmp, sizeof(uint32_t) * c->scan_tmp_len));
+    }
+    return exclusive_scan(c, data, n, c->scan_tmp, c->scan_tmp_len);
+}
+
 // ---------------------------------------------------------------------------
 // scatter, in-cell ordering, gather
 // ---------------------------------------------------------------------------
@@ -287,7 +298,9 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
         sphmw_set_error("create_cell_list: field x has not been set");
         return SPHMW_E_STATE;
     }
-    if (!c->scan_tmp) {
+    if (!c->scan_tmp || c->scan_tmp_len < (ncells + 2) / SCAN_TILE * 2 + 4096) {
+        cudaFree(c->scan_tmp);
+        c->scan_tmp = nullptr;
         c->scan_tmp_len = (ncells + 2) / SCAN_TILE * 2 + 4096;
         CUDA_TRY(cudaMalloc(&c->scan_tmp, sizeof(uint32_t) * c->scan_tmp_len));
     }

@@ -333,6 +333,58 @@ struct U_pack_move {
         }
     }
 };
+// ---- src/legacy/isothermal_flow_witch.jl (u stored in v, Du in Dv, T = T_bg, h = kh) ----
+// find_pressure!  :156-160
+struct U_flow_find_pressure {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        double rho = FLD(S_RHO) + FLD(S_DRHO) * c.dt;
+        FLD(S_RHO) = rho;
+        FLD(S_DRHO) = 0.0;
+        FLD(S_P) = rho * c.R_mass * c.T_bg;
+    }
+};
+// set_density!  :162-164
+struct U_flow_set_density {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        FLD(S_RHO) = c.rho0 * exp(-FLD(S_X1) * c.g / (c.R_mass * c.T_bg));
+    }
+};
+// find_pot_temp!  :167-169
+struct U_flow_find_pot_temp {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        FLD(S_TH) = c.T_bg * pow((c.T_bg * c.R_gas * c.rho0) / FLD(S_P), c.R_gas / c.cp);
+    }
+};
+// move!  :204-209
+struct U_flow_move {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        FLD(S_DV0) = 0.0;
+        FLD(S_DV1) = 0.0;
+        if (DIM == 3) FLD(S_DV2) = 0.0;
+        double t = FLD(S_TYPE);
+        if (t == c.fluid || t == c.inflow) {
+            FLD(S_X0) += c.dt * FLD(S_V0);
+            FLD(S_X1) += c.dt * FLD(S_V1);
+            if (DIM == 3) FLD(S_X2) += c.dt * FLD(S_V2);
+        }
+    }
+};
+// accelerate!  :211-215, damping_structure :192-198 (positive scalar; sponge_y = -that)
+struct U_flow_accelerate {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        if (FLD(S_TYPE) == c.fluid) {
+            double damp = FLD(S_X1) >= c.sponge_z0 ? -c.sponge_y : 0.0;
+            FLD(S_V0) += 0.5 * c.dt * (FLD(S_DV0) - c.g * 0.0 - damp * 0.0);
+            FLD(S_V1) += 0.5 * c.dt * (FLD(S_DV1) - c.g * 1.0 - damp * 1.0);
+            if (DIM == 3) FLD(S_V2) += 0.5 * c.dt * (FLD(S_DV2) - c.g * 0.0 - damp * 0.0);
+        }
+    }
+};
 #undef FLD
 
 template <int DIM, class Op>
@@ -639,6 +691,66 @@ struct B_dam_force : PairOpBase {
         dv0 += a2 * (v0 - QF(S_V0));
         dv1 += a2 * (v1 - QF(S_V1));
         if (DIM == 3) dv2 += a2 * (v2 - QF(S_V2));
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_DV0) = dv0;
+        PF(S_DV1) = dv1;
+        if (DIM == 3) PF(S_DV2) = dv2;
+    }
+};
+// balance_of_mass!  isothermal_flow_witch.jl:140-143
+struct B_flow_mass : PairOpBase {
+    double drho, v0, v1, v2;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &, int64_t p) {
+        drho = PF(S_DRHO);
+        v0 = PF(S_V0);
+        v1 = PF(S_V1);
+        v2 = DIM == 3 ? PF(S_V2) : 0.0;
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        double ker = QF(S_M) * rDwendland2(c.kh, r);
+        double d = dx * (v0 - QF(S_V0)) + dy * (v1 - QF(S_V1));
+        if (DIM == 3) d = d + dz * (v2 - QF(S_V2));
+        drho += ker * d;
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_DRHO) = drho;
+    }
+};
+// internal_force!  isothermal_flow_witch.jl:145-150
+struct B_flow_force : PairOpBase {
+    double dv0, dv1, dv2, v0, v1, v2, P, rho;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &, int64_t p) {
+        dv0 = PF(S_DV0);
+        dv1 = PF(S_DV1);
+        dv2 = DIM == 3 ? PF(S_DV2) : 0.0;
+        v0 = PF(S_V0);
+        v1 = PF(S_V1);
+        v2 = DIM == 3 ? PF(S_V2) : 0.0;
+        P = PF(S_P);
+        rho = PF(S_RHO);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        double ker = QF(S_M) * rDwendland2(c.kh, r);
+        double qrho = QF(S_RHO);
+        double a1 = -ker * (P / sph_pow2(rho) + QF(S_P) / sph_pow2(qrho));
+        dv0 += a1 * dx;
+        dv1 += a1 * dy;
+        if (DIM == 3) dv2 += a1 * dz;
+        double d = (v0 - QF(S_V0)) * dx + (v1 - QF(S_V1)) * dy;  // dot(p.u - q.u, x_pq)
+        if (DIM == 3) d = d + (v2 - QF(S_V2)) * dz;
+        double a2 = 8.0 * ker * c.mu / (rho * qrho) * d / (r * r + 0.01 * c.kh * c.kh);
+        dv0 += a2 * dx;
+        dv1 += a2 * dy;
+        if (DIM == 3) dv2 += a2 * dz;
     }
     template <int DIM>
     __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
@@ -1334,6 +1446,15 @@ static const OpEntry OPS[] = {
     UNARY_ENTRY("collision.reset_rho", U_col_reset_rho, SL(S_X0), SL(S_RHO), ),
     UNARY_ENTRY("collision.move", U_col_move, SL(S_V0), SL(S_X0), c->cell_list_valid = false),
     UNARY_ENTRY("collision.accelerate", U_col_accelerate, SL(S_DV0), SL(S_V0), ),
+    BINARY_ENTRY("flow.balance_of_mass", B_flow_mass, SL(S_X0, S_V0, S_M), SL(S_DRHO), ),
+    BINARY_ENTRY("flow.internal_force", B_flow_force, SL(S_X0, S_V0, S_M, S_P, S_RHO), SL(S_DV0),
+                 c->dv_zero = false),
+    UNARY_ENTRY("flow.find_pressure", U_flow_find_pressure, SL(S_DRHO), SL(S_RHO, S_DRHO, S_P), ),
+    UNARY_ENTRY("flow.set_density", U_flow_set_density, SL(S_X0), SL(S_RHO), ),
+    UNARY_ENTRY("flow.find_pot_temp", U_flow_find_pot_temp, SL(S_P), SL(S_TH), ),
+    UNARY_ENTRY("flow.move", U_flow_move, SL(S_TYPE, S_V0), SL(S_X0, S_DV0),
+                (c->cell_list_valid = false, c->dv_zero = true)),
+    UNARY_ENTRY("flow.accelerate", U_flow_accelerate, SL(S_TYPE, S_X0, S_DV0), SL(S_V0), ),
     UNARY_ENTRY("packing.reset_rho", U_pack_reset_rho, SL(S_TYPE), SL(S_RHO), ),
     BINARY_ENTRY("packing.accumulate_rho", B_pack_rho, SL(S_X0, S_M, S_H, S_TYPE), SL(S_RHO), ),
     BINARY_ENTRY("packing.balance_of_momentum", B_pack_momentum,
@@ -1400,6 +1521,91 @@ int sphmw_materialize(sphmw_ctx *c, int slot) {
         sphmw_set_error("internal: slot %d is stale and has no rule", slot);
         return SPHMW_E_STATE;
     }
+    return SPHMW_OK;
+}
+
+// ===========================================================================
+// add_new_particles!  src/legacy/isothermal_flow_witch.jl:175-186
+// ===========================================================================
+template <int DIM>
+__global__ void k_flow_flag(Fields f, Params c, const uint32_t *__restrict__ idx, int64_t n,
+                            uint32_t *__restrict__ flag_by_idx) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    flag_by_idx[idx[p]] = (f.s[S_TYPE][p] == c.inflow && f.s[S_X0][p] >= c.x_inflow) ? 1u : 0u;
+}
+
+// One thread per old particle; a converting particle creates its successor at index
+// n + (number of converting particles with a smaller index): the order of the reference's loop.
+template <int DIM>
+__global__ void k_flow_spawn(Fields f, Params c, uint32_t *__restrict__ idx,
+                             uint32_t *__restrict__ pos_of_idx, uint32_t *__restrict__ tag, int64_t n,
+                             const uint32_t *__restrict__ rank_by_idx) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    if (!(f.s[S_TYPE][p] == c.inflow && f.s[S_X0][p] >= c.x_inflow)) return;
+    f.s[S_TYPE][p] = c.fluid;
+    const int64_t s = n + rank_by_idx[idx[p]];
+    // Particle(x - bc_width*VECX, U_max*VECX, INFLOW), constructor :72-82
+    const double y = f.s[S_X1][p] - c.bc_width * 0.0;
+    f.s[S_X0][s] = f.s[S_X0][p] - c.bc_width * 1.0;
+    f.s[S_X1][s] = y;
+    if (DIM == 3) f.s[S_X2][s] = f.s[S_X2][p] - c.bc_width * 0.0;
+    f.s[S_V0][s] = c.U_max * 1.0;
+    f.s[S_V1][s] = c.U_max * 0.0;
+    if (DIM == 3) f.s[S_V2][s] = c.U_max * 0.0;
+    const double rho = c.rho0 * exp(-y * c.g / (c.R_mass * c.T_bg));
+    const double P = rho * c.T_bg * c.R_mass;
+    f.s[S_RHO][s] = rho;
+    f.s[S_M][s] = rho * sph_pow2(c.dr);
+    f.s[S_P][s] = P;
+    f.s[S_TH][s] = c.T_bg * pow((c.T_bg * c.R_gas * c.rho0) / P, c.R_gas / c.cp);
+    f.s[S_TYPE][s] = c.inflow;
+    idx[s] = (uint32_t)s;
+    pos_of_idx[s] = (uint32_t)s;
+    tag[s] = TAG_OWNED;
+}
+
+int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added) {
+    if (n_added) *n_added = 0;
+    if (c->slab_lo >= 0) { sphmw_set_error("add_new_particles: whole-domain contexts only"); return SPHMW_E_STATE; }
+    const int64_t n = c->n;
+    if (n == 0) return SPHMW_OK;
+    TRY(need_slots(c, SL(S_X0, S_V0, S_TYPE, S_RHO, S_M, S_P, S_TH), SL(S_X0, S_V0, S_TYPE, S_RHO, S_M, S_P, S_TH)));
+    uint32_t *flags = c->rank;  // scratch of the cell-list build, free between builds
+    {
+        TIMED(c, "flow.flag_inflow");
+        if (c->grid.dim == 2) k_flow_flag<2><<<grid_for(n, 256), 256, 0, c->stream>>>(c->cur, c->prm, c->idx, n, flags);
+        else k_flow_flag<3><<<grid_for(n, 256), 256, 0, c->stream>>>(c->cur, c->prm, c->idx, n, flags);
+    }
+    // total = last flag + its exclusive prefix
+    uint32_t last_flag = 0, last_rank = 0;
+    CUDA_TRY(cudaMemcpyAsync(&last_flag, flags + n - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    TRY(sphmw_exclusive_scan_u32(c, flags, n));
+    CUDA_TRY(cudaMemcpyAsync(&last_rank, flags + n - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const int64_t m = (int64_t)last_flag + last_rank;
+    if (m == 0) return SPHMW_OK;
+    if (n + m > c->cap) {
+        sphmw_set_error("add_new_particles: %lld + %lld particles exceed capacity %lld", (long long)n,
+                        (long long)m, (long long)c->cap);
+        return SPHMW_E_CAPACITY;
+    }
+    // every other field of a new particle is the constructor's zero
+    for (int s = 0; s < NSLOT; ++s)
+        if (c->allocated[s]) CUDA_TRY(cudaMemsetAsync(c->cur.s[s] + n, 0, sizeof(double) * m, c->stream));
+    {
+        TIMED(c, "flow.spawn_inflow");
+        if (c->grid.dim == 2)
+            k_flow_spawn<2><<<grid_for(n, 256), 256, 0, c->stream>>>(c->cur, c->prm, c->idx, c->pos_of_idx, c->tag, n, flags);
+        else
+            k_flow_spawn<3><<<grid_for(n, 256), 256, 0, c->stream>>>(c->cur, c->prm, c->idx, c->pos_of_idx, c->tag, n, flags);
+    }
+    CUDA_TRY(cudaGetLastError());
+    c->n = n + m;
+    c->n_owned = c->n;
+    c->cell_list_valid = false;
+    if (n_added) *n_added = m;
     return SPHMW_OK;
 }
 
@@ -1529,6 +1735,12 @@ int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps) {
             TRY(apply_seq(c, {"dambreak.accelerate", "dambreak.move", "create_cell_list",
                               "dambreak.balance_of_mass", "dambreak.find_pressure", "dambreak.move",
                               "create_cell_list", "dambreak.internal_force", "dambreak.accelerate"}));
+        } else if (!strcmp(scheme, "flow")) {
+            // isothermal_flow_witch.jl:221-232
+            TRY(apply_seq(c, {"flow.accelerate", "flow.move"}));
+            TRY(sphmw_flow_add_particles(c, nullptr));
+            TRY(apply_seq(c, {"create_cell_list", "flow.balance_of_mass", "flow.find_pressure",
+                              "flow.find_pot_temp", "flow.internal_force", "flow.accelerate"}));
         } else if (!strcmp(scheme, "collision")) {
             // test_collision_2d.jl:106-116
             TRY(apply_seq(c, {"collision.accelerate", "collision.move", "create_cell_list",

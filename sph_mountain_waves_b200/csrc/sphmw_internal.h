@@ -42,6 +42,7 @@ struct Params {
     double rho_floor, P_floor, z_t, z_b, gamma_r, fluid;
     double m, nu, mu, gx, gy, gz, kh;
     double dt_pack, c_pack, zeta_pack;
+    double U_max, cp, bc_width, x_inflow, dr, inflow;  // legacy flow drivers (isothermal_flow_witch.jl:24-60)
     // derived on the host when a parameter changes
     double sponge_y;  // -gamma_r*sin(pi/2*(1-(z_t-z_b)/z_b))^2  (:245-251)
     double sponge_z0; // z_t - z_b
@@ -222,6 +223,9 @@ int sphmw_step_scheme_phase(sphmw_ctx *c, const char *scheme, int phase);
 int sphmw_materialize(sphmw_ctx *c, int slot);
 int64_t sphmw_list_ops(char *buf, int64_t cap);
 int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n);
+int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added);
+// implemented in cell_list.cu
+int sphmw_exclusive_scan_u32(sphmw_ctx *c, uint32_t *data, int64_t n);
 // implemented in frame_io.cpp
 int sphmw_write_vtp(const char *path, int64_t n, const double *points3n, int nfields,
                     const char *const *names, const int *ncomps, const double *const *data);

@@ -262,6 +262,13 @@ class ParticleSystem:
         self._flush()
         check(_capi.lib().sphmw_step(self.ctx, (scheme or self.T.scheme).encode(), nsteps))
 
+    def flow_add_new_particles(self) -> int:
+        """≙ add_new_particles!(sys) — src/legacy/isothermal_flow_witch.jl:175-186"""
+        self._flush()
+        n = C.c_int64()
+        check(_capi.lib().sphmw_flow_add_new_particles(self.ctx, C.byref(n)))
+        return n.value
+
     def sync(self):
         if self._ctx is not None:
             check(_capi.lib().sphmw_sync(self._ctx))
