@@ -34,6 +34,8 @@ WORKLOADS = {
     "bell_hill_3d_64M": (1920, 150, 192),
     "bell_hill_3d_8M": (960, 75, 96),
     "bell_hill_3d_1M": (480, 38, 48),
+    # BASELINE config 3: 2D Witch of Agnesi, dr = 26 km / 510 (one GPU only)
+    "witch_2d_4M": None,
 }
 
 
@@ -46,6 +48,7 @@ def parse():
     ap.add_argument("--workload", default="bell_hill_3d_64M", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strict", action="store_true")
     ap.add_argument("--cpu-sample", default="bell_hill_3d_1M")
     ap.add_argument("--flags", type=int, default=1,
                     help="SPHMW_FLAG_*: 0 strict (bit-identical sums), 1 FAST_MATH (default), 2 CELL_PAIRS")
@@ -172,13 +175,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nx, ny, nz = WORKLOADS[args.workload]
+    is2d = WORKLOADS[args.workload] is None
+    nx, ny, nz = (0, 0, 0) if is2d else WORKLOADS[args.workload]
+    BYTES = BYTES_2D if is2d else BYTES_3D
     peak_gbs, peak_src = measured_peaks()
 
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
-        run = SlabRun.bell_hill_3d(nx, ny, nz, rank=rank, world=world, device=local,
-                                   stream=stream.cuda_stream, flags=args.flags)
+        if is2d:
+            assert world == 1, "the 2D workload is a single-GPU configuration (BASELINE config 3)"
+            run = SlabRun.whole(cases.witch_2d(), device=local, stream=stream.cuda_stream, flags=args.flags)
+        else:
+            run = SlabRun.bell_hill_3d(nx, ny, nz, rank=rank, world=world, device=local,
+                                       stream=stream.cuda_stream, flags=args.flags)
         run.create_cell_list()
         n_local = run.n_owned
         n_total = run.n_global
@@ -221,7 +230,7 @@ def run_ours(args):
         kname = "wcsph.momentum_fused"
         k_ms, k_calls = rep.get(kname, (0.0, 0))
         per_launch_s = (k_ms / max(k_calls, 1)) * 1e-3
-        alg_bytes = run.n_resident * BYTES_3D["K_C"]
+        alg_bytes = run.n_resident * BYTES["K_C"]
         achieved = alg_bytes / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
         total_kernel_ms = sum(v[0] for v in rep.values())
         # DRAM traffic of that kernel per launch: from the committed ncu capture of this very
@@ -238,11 +247,28 @@ def run_ours(args):
             "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
             "frac": achieved / peak_gbs, "traffic": traffic, "traffic_unit": "GB per launch (ncu)",
             "alg_gbytes_per_launch": alg_bytes / 1e9, "peak_source": peak_src,
-            "alg_bytes_per_particle": BYTES_3D["K_C"], "ms_per_launch": per_launch_s * 1e3,
+            "alg_bytes_per_particle": BYTES["K_C"], "ms_per_launch": per_launch_s * 1e3,
             "share_of_step": (k_ms / total_kernel_ms) if total_kernel_ms else None,
             "per_kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(rep.items())},
-            "step_bytes_frac": (run.n_resident * BYTES_3D["step"] * args.steps / (ms * 1e-3) / 1e9) / peak_gbs,
+            "step_bytes_frac": (run.n_resident * BYTES["step"] * args.steps / (ms * 1e-3) / 1e9) / peak_gbs,
         }
+
+        # ---- the same step with strict arithmetic (bit-identical sums), for reference ----
+        strict_ms = None
+        if args.flags == 1 and not args.no_strict:
+            run.sys.set_flags(0)
+            run.step(1)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            run.step(3)
+            s1.record(stream)
+            barrier()
+            ts = torch.tensor([s0.elapsed_time(s1) / 3], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            strict_ms = float(ts.item())
+            run.sys.set_flags(args.flags)
 
         # ---- end to end through the public API with HOST buffers ------------------
         e2e = None
@@ -271,7 +297,8 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (lattice-initialised, deterministic)",
             "config": {"workload": args.workload, "particles": n_total, "fluid_cells": [nx, ny, nz],
-                       "scheme": "wcsph_perturbed_witch verlet_step!, 3D extrusion (wendland3)",
+                       "scheme": "wcsph_perturbed_witch verlet_step!" +
+                                 (" (2D, wendland2)" if is2d else ", 3D extrusion (wendland3)"),
                        "parallelism": f"x-slabs x{world}",
                        "arithmetic": {0: "strict (no FMA, IEEE div/sqrt; sums bit-identical to the oracle)",
                                       1: "fast (FMA + reciprocals in the closure bodies; exact neighbour set; "
@@ -280,7 +307,8 @@ def run_ours(args):
                        "l2": "inputs (>= 80 B x particles) far exceed the 126 MB L2; no flush needed",
                        "pair_interactions_per_s": pairs_force * 2 / (ms_max * 1e-3 / args.steps)
                        if pairs_force else None,
-                       "pairs_per_binary_pass": pairs_force},
+                       "pairs_per_binary_pass": pairs_force,
+                       "strict_arithmetic_ms_per_step": strict_ms},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clk.summary(),
         }

@@ -78,6 +78,8 @@ const char *sphmw_version(void);
 /* Use the caller's CUDA stream (cudaStream_t as void*); NULL = context's own. */
 int sphmw_set_stream(sphmw_ctx *ctx, void *cuda_stream);
 int sphmw_sync(sphmw_ctx *ctx);
+/* switch the arithmetic / kernel variant of the fused step (SPHMW_FLAG_*) */
+int sphmw_set_flags(sphmw_ctx *ctx, int32_t flags);
 
 /* Driver constants, ≙ the module-level `const`s of a driver
  * (src/current/wcsph_perturbed_witch.jl:25-75; collapse_dry.jl:30-66).

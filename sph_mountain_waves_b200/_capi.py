@@ -51,6 +51,7 @@ _SIGS = {
     "sphmw_version": (C.c_char_p, []),
     "sphmw_set_stream": (C.c_int, [_P, C.c_void_p]),
     "sphmw_sync": (C.c_int, [_P]),
+    "sphmw_set_flags": (C.c_int, [_P, C.c_int32]),
     "sphmw_set_param": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "sphmw_get_param": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double)]),
     "sphmw_key_tables": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64),

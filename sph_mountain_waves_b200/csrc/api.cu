@@ -401,6 +401,11 @@ extern "C" int sphmw_set_stream(sphmw_ctx *c, void *s) {
     c->stream = s ? (cudaStream_t)s : c->own_stream;
     return SPHMW_OK;
 }
+extern "C" int sphmw_set_flags(sphmw_ctx *c, int32_t flags) {
+    if (!c) return SPHMW_E_INVALID;
+    c->flags = flags;
+    return SPHMW_OK;
+}
 extern "C" int sphmw_sync(sphmw_ctx *c) {
     if (!c) return SPHMW_E_INVALID;
     CUDA_TRY(cudaSetDevice(c->device));

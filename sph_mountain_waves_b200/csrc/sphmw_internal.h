@@ -170,8 +170,6 @@ struct sphmw_ctx {
 
     bool cell_list_valid = false;
     bool count_pairs = false;
-    int64_t last_pair_count = 0;
-    bool scheme_first_step = true;
 
     // pvd output (IO.jl:9-13)
     std::string pvd_dir;

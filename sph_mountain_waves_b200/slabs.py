@@ -268,6 +268,15 @@ class SlabRun:
         return run
 
     @classmethod
+    def whole(cls, case, device=0, stream=None, flags: int = 0):
+        """any case on one GPU (no slabs)"""
+        sys = cases.to_system(case, device=device, stream=stream, flags=flags)
+        sys._flush()
+        run = cls(sys, None, case.n)
+        run.case_info = dict(case.info)
+        return run
+
+    @classmethod
     def from_global_case(cls, case, rank: int, world: int, device: int = 0, stream=None, flags: int = 0):
         """Slice a whole (small) case held on the host: reference indices are the positions in
         `case.fields`.  Used by tests and by single-process multi-context runs."""

@@ -269,6 +269,10 @@ class ParticleSystem:
         check(_capi.lib().sphmw_flow_add_new_particles(self.ctx, C.byref(n)))
         return n.value
 
+    def set_flags(self, flags: int):
+        self._flags = int(flags)
+        check(_capi.lib().sphmw_set_flags(self.ctx, int(flags)))
+
     def sync(self):
         if self._ctx is not None:
             check(_capi.lib().sphmw_sync(self._ctx))
