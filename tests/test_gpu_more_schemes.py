@@ -260,3 +260,18 @@ def test_packing_driver_loop(gpu):
             o.apply(op)
     for f in ("x", "rho"):
         assert rel_err(s.field(f), o.field(f)) <= TOL, f
+
+
+def test_dambreak_validation_at_reference_resolution(gpu):
+    """BASELINE config 1 at the reference's own resolution (dr = 1.5e-2, 10 363 particles,
+    ~9 500 steps to t* = 3.2) on the device: surge front within 2 % of Violeau's curve."""
+    from dambreak_validation import deviation, run_dambreak
+    case = cases.collapse_dry()
+    s = load_gpu(case)
+    s.create_cell_list()
+    s.apply("dambreak.internal_force")
+    ts, X, H = run_dambreak(s, case, lambda n: s.step(n, "dambreak"), every=100)
+    assert deviation("X_Violeau", ts, X)[0] < 0.02          # measured 1.5 %
+    assert deviation("H_Violeau", ts, H, t_max=2.6)[0] < 0.04   # measured 3.0 %
+    assert deviation("H_Violeau", ts, H)[0] < 0.12          # the last digitised point (t* = 3): 9 %
+    assert len(s) == case.n
