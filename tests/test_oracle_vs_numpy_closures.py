@@ -1,0 +1,134 @@
+"""The oracle's driver closures against an INDEPENDENT numpy restatement of the same Julia source
+(brute-force O(N^2) neighbour search, vectorised formulas, no cell list).  The summation order
+differs, so agreement is to rounding (1e-12), which is what a transcription slip in either
+restatement would break by many orders of magnitude."""
+import numpy as np
+import pytest
+
+from sph_mountain_waves_b200 import cases
+from util import load_oracle, rel_err
+
+
+def neighbours(x, h):
+    d = x[:, None, :] - x[None, :, :]
+    r = np.sqrt((d * d).sum(-1))
+    mask = (r <= h) & ~np.eye(len(x), dtype=bool)        # core.jl:105
+    return d, r, mask
+
+
+def wendland2(h, r):                                      # kernels.jl:108-115
+    x = r / h
+    return np.where(x > 1.0, 0.0, 7 / np.pi * (1 - x) ** 4 * (1 + 4 * x) / h ** 2)
+
+
+def rDwendland2(h, r):                                    # kernels.jl:140-147
+    x = r / h
+    return np.where(x > 1.0, 0.0, -140 / np.pi * (1 - x) ** 3 / h ** 4)
+
+
+def wendland3(h, r):                                      # kernels.jl:156-163
+    x = r / h
+    return np.where(x > 1.0, 0.0, 21 / (2 * np.pi) * (1 - x) ** 4 * (1 + 4 * x) / h ** 3)
+
+
+def rDwendland3(h, r):                                    # kernels.jl:188-195
+    x = r / h
+    return np.where(x > 1.0, 0.0, -210 / np.pi * (1 - x) ** 3 / h ** 5)
+
+
+def numpy_wcsph_step(case):
+    """verlet_step!, src/current/wcsph_perturbed_witch.jl:309-332, on plain arrays"""
+    p = case.params
+    f = {k: v.copy() for k, v in case.fields.items()}
+    dim3 = case.dim == 3
+    W, rDW = (wendland3, rDwendland3) if dim3 else (wendland2, rDwendland2)
+    fluid = f["type"] == p["fluid"]
+    ey = np.array([0.0, 1.0, 0.0])
+
+    def accelerate(Dv):                                   # :298-303, :245-256
+        buoy = -p["g"] * ey[None, :] * (f["rho_p"] / f["rho"])[:, None]
+        sn = np.sin(np.pi / 2 * (1 - (p["z_t"] - p["z_b"]) / p["z_b"]))
+        damp = np.where((f["x"][:, 1] >= p["z_t"] - p["z_b"])[:, None], -p["gamma_r"] * sn ** 2 * ey[None, :], 0.0)
+        f["v"] = np.where(fluid[:, None], f["v"] + 0.5 * p["dt"] * (Dv + buoy + damp), f["v"])
+
+    accelerate(f["Dv"])
+    f["x"] = np.where(fluid[:, None], f["x"] + p["dt"] * f["v"], f["x"])            # move! :292-296
+    d, r, mask = neighbours(f["x"], case.h)
+    # compute_density! :226-228 (no self term), finalize_density! :230-233, update_smoothing! :235-238
+    f["rho"] = (mask * f["m"][None, :] * W(f["h"][:, None], r)).sum(1)
+    rho_bg = p["rho0"] * np.exp(-f["x"][:, 1] * p["g"] / (p["R_mass"] * p["T_bg"]))   # :177-179
+    f["rho_p"] = f["rho"] - rho_bg
+    rfl = np.maximum(f["rho"], p["rho_floor"])
+    f["h"] = p["eta"] * (np.cbrt(f["m"] / rfl) if dim3 else np.sqrt(f["m"] / rfl))
+    # compute_pressure! :195-199
+    P_p = p["c"] ** 2 * f["rho_p"]
+    P = p["R_mass"] * p["T_bg"] * rho_bg + P_p
+    # balance_of_momentum! :261-286
+    v_pq = f["v"][:, None, :] - f["v"][None, :, :]
+    dot = (d * v_pq).sum(-1)
+    h_ij = 0.5 * (f["h"][:, None] + f["h"][None, :])
+    ker = rDW(h_ij, r)
+    pr = P_p / rfl ** 2
+    fc = -f["m"][None, :] * (pr[:, None] + pr[None, :]) * ker
+    cs = np.sqrt(p["gamma"] * P / rfl)
+    c_ij = 0.5 * (cs[:, None] + cs[None, :])
+    rho_ij = 0.5 * (rfl[:, None] + rfl[None, :])
+    mu = h_ij * dot / (r * r + p["eps"] * h_ij * h_ij)
+    pi_ij = (-p["alpha"] * c_ij * mu + p["beta"] * mu * mu) / rho_ij
+    fv = np.where(dot < 0.0, -f["m"][None, :] * pi_ij * ker, 0.0)
+    Dv = ((mask * (fc + fv))[:, :, None] * d).sum(1)
+    accelerate(Dv)
+    f["P"], f["P_p"], f["Dv_last"] = P, P_p, Dv
+    return f, int(mask.sum())
+
+
+@pytest.mark.parametrize("make", [
+    lambda: cases.mountain_wave_2d(n_y=12.0, dom_length=30e3, h_m=3000.0, a=6e3, U=25.0),
+    lambda: cases.bell_hill_3d(10, 8, 6, h_m=3000.0, a=4e3, U=25.0),
+])
+def test_wcsph_step_against_numpy_restatement(make):
+    case = make()
+    # perturb the lattice so that the artificial-viscosity branch and varying h are exercised
+    rng = np.random.default_rng(11)
+    fluid = case.fields["type"] == 0.0
+    case.fields["v"] = case.fields["v"] + fluid[:, None] * rng.normal(scale=8.0, size=(case.n, 3)) * \
+        np.array([1.0, 1.0, 1.0 if case.dim == 3 else 0.0])
+    case.fields["h"] = case.fields["h"] * rng.uniform(0.9, 1.3, case.n)
+    o = load_oracle(case)
+    o.create_cell_list()
+    o.step("wcsph", 1)
+    ref, npairs = numpy_wcsph_step(case)
+    assert o.pair_count() == npairs > 0
+    for name in ("x", "v", "rho", "rho_p", "h", "P", "P_p"):
+        assert rel_err(o.field(name), ref[name]) < 1e-12, name
+
+
+def test_hopkins_pressure_and_total_force_against_numpy():
+    """hopkins_perturbed_witch.jl:205-214 and hopkins_total_witch.jl:233-264"""
+    case = cases.hopkins_2d("hopkins_total", n_y=12.0, dom_length=30e3)
+    rng = np.random.default_rng(5)
+    case.fields["v"] = case.fields["v"] + rng.normal(scale=5.0, size=(case.n, 3)) * np.array([1.0, 1.0, 0.0])
+    p, f = case.params, case.fields
+    o = load_oracle(case)
+    o.create_cell_list()
+    for op in ("hopkins_total.reset_pressure", "hopkins.compute_pressure", "hopkins_total.finalize_pressure",
+               "hopkins_total.balance_of_momentum"):
+        o.apply(op)
+    d, r, mask = neighbours(f["x"], case.h)
+    g = p["gamma"]
+    h_ij = 0.5 * (f["h"][:, None] + f["h"][None, :])
+    P = ((mask * f["m"][None, :] * (f["A"] ** (1 / g))[None, :] * wendland2(h_ij, r)).sum(1)) ** g
+    assert rel_err(o.field("P"), P) < 1e-12
+    v_pq = f["v"][:, None, :] - f["v"][None, :, :]
+    dot = (d * v_pq).sum(-1)
+    prefac = f["m"][None, :] * (f["A"][:, None] * f["A"][None, :]) ** (1 / g)
+    e = 1.0 - 2.0 / g
+    Pf = np.maximum(p["P_floor"], P)
+    fc = -prefac * ((Pf ** e)[:, None] * rDwendland2(f["h"][:, None], r) + (Pf ** e)[None, :] * rDwendland2(f["h"][None, :], r))
+    rfl = np.maximum(f["rho"], p["rho_floor"])
+    cs = np.sqrt(g * P / rfl)
+    mu = h_ij * dot / (r * r + p["eps"] * h_ij * h_ij)
+    pi_ij = (-p["alpha"] * 0.5 * (cs[:, None] + cs[None, :]) * mu + p["beta"] * mu * mu) / (0.5 * (rfl[:, None] + rfl[None, :]))
+    fv = np.where(dot < 0.0, -f["m"][None, :] * pi_ij * rDwendland2(h_ij, r), 0.0)
+    Dv = ((mask * (fc + fv))[:, :, None] * d).sum(1)
+    assert rel_err(o.field("Dv"), Dv) < 1e-12
