@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strict", action="store_true")
+    ap.add_argument("--device-gen", action="store_true",
+                    help="generate the lattice on the GPU (sphmw_generate_mountain_wave) instead of numpy")
     ap.add_argument("--cpu-sample", default="bell_hill_3d_1M")
     ap.add_argument("--flags", type=int, default=1,
                     help="SPHMW_FLAG_*: 0 strict (bit-identical sums), 1 FAST_MATH (default), 2 CELL_PAIRS")
@@ -187,7 +189,8 @@ def run_ours(args):
             run = SlabRun.whole(cases.witch_2d(), device=local, stream=stream.cuda_stream, flags=args.flags)
         else:
             run = SlabRun.bell_hill_3d(nx, ny, nz, rank=rank, world=world, device=local,
-                                       stream=stream.cuda_stream, flags=args.flags)
+                                       stream=stream.cuda_stream, flags=args.flags,
+                                       device_gen=args.device_gen)
         run.create_cell_list()
         n_local = run.n_owned
         n_total = run.n_global
@@ -295,7 +298,8 @@ def run_ours(args):
             "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic (lattice-initialised, deterministic)",
+            "data": "synthetic (lattice-initialised, deterministic" +
+                    (", generated on the device)" if args.device_gen else ", generated on the host)"),
             "config": {"workload": args.workload, "particles": n_total, "fluid_cells": [nx, ny, nz],
                        "scheme": "wcsph_perturbed_witch verlet_step!" +
                                  (" (2D, wendland2)" if is2d else ", 3D extrusion (wendland3)"),

@@ -126,6 +126,30 @@ int64_t sphmw_op_list(char *buf, int64_t cap);
  * operator-by-operator sequence. */
 int sphmw_step(sphmw_ctx *ctx, const char *scheme, int32_t nsteps);
 
+/* ≙ make_system() of the mountain-wave drivers on the device —
+ * src/current/wcsph_perturbed_witch.jl:152-170 with src/grids.jl:50-93,176-196 (square,
+ * hexagonal, cubic lattices) and src/geometry.jl:15-43,176-232 (Rectangle/Box domain,
+ * BoundaryLayer fence, mountain Specification).  Appends, in the reference's particle order
+ * (fluid bulk, wall fence, mountain; lattice index i outermost), the particles of
+ *   domain - mountain (type_fluid, v = U x̂), fence (type_wall), mountain (type_mountain)
+ * with the fields the step carries (h, x, m, v, rho, rho', type) set as the driver's Particle
+ * constructor does (:103-145; rho0, g, R_mass, T_bg from sphmw_set_param).  mountain: 0 none,
+ * 1 Witch of Agnesi y <= h_m a^2/(x^2+a^2) (2D), 2 bell hill y <= h_m/(1+(x^2+z^2)/a^2)^1.5.
+ * On a slab context only the sites of the owned cell columns are generated. */
+typedef struct sphmw_lattice_setup {
+    int32_t grid;     /* 0 :square, 1 :hexagonal, 2 :cubic */
+    int32_t mountain;
+    double dr;
+    double dom_min[3];
+    double dom_max[3];
+    double bc_width;
+    double h_m, a, U;
+    double type_fluid, type_wall, type_mountain;
+    double h0;
+} sphmw_lattice_setup;
+int sphmw_generate_mountain_wave(sphmw_ctx *ctx, const sphmw_lattice_setup *setup, int64_t *n_out,
+                                 int64_t group_counts[3]);
+
 /* ≙ add_new_particles!(sys) of the constant-U flow drivers —
  * src/legacy/isothermal_flow_witch.jl:175-186: every INFLOW particle that has entered the
  * domain (x[1] >= x_inflow) becomes FLUID and a new INFLOW particle is appended bc_width

@@ -41,6 +41,16 @@ class Config(C.Structure):
     ]
 
 
+class LatticeSetup(C.Structure):
+    _fields_ = [
+        ("grid", C.c_int32), ("mountain", C.c_int32), ("dr", C.c_double),
+        ("dom_min", C.c_double * 3), ("dom_max", C.c_double * 3), ("bc_width", C.c_double),
+        ("h_m", C.c_double), ("a", C.c_double), ("U", C.c_double),
+        ("type_fluid", C.c_double), ("type_wall", C.c_double), ("type_mountain", C.c_double),
+        ("h0", C.c_double),
+    ]
+
+
 _lib = None
 
 _P = C.c_void_p
@@ -64,6 +74,8 @@ _SIGS = {
     "sphmw_apply": (C.c_int, [_P, C.c_char_p, C.c_int32]),
     "sphmw_op_list": (C.c_int64, [C.c_char_p, C.c_int64]),
     "sphmw_step": (C.c_int, [_P, C.c_char_p, C.c_int32]),
+    "sphmw_generate_mountain_wave": (C.c_int, [_P, C.POINTER(LatticeSetup), C.POINTER(C.c_int64),
+                                               C.POINTER(C.c_int64)]),
     "sphmw_flow_add_new_particles": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "sphmw_cell_keys": (C.c_int, [_P, C.c_void_p, C.c_int64]),
     "sphmw_cell_entries": (C.c_int, [_P, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),

@@ -161,7 +161,46 @@ def witch_profile(k: Constants, x, z=None):
     with np.errstate(invalid="ignore", divide="ignore"):
         if z is None:
             return (k.h_m * k.a ** 2) / (x ** 2 + k.a ** 2)
-        return k.h_m / (1 + (x ** 2 + z ** 2) / k.a ** 2) ** 1.5
+        t = 1 + (x ** 2 + z ** 2) / k.a ** 2
+        return k.h_m / (t * np.sqrt(t))   # t^(3/2) in IEEE operations only (same bits on the device)
+
+
+def make_system_on_device(k: Optional[Constants] = None, capacity: Optional[int] = None,
+                          **sys_kw) -> ParticleSystem:
+    """make_system() with the lattice, the CSG classification and the Particle constructor
+    evaluated on the GPU (sphmw_generate_mountain_wave): same particles in the same order as
+    `make_system(k, lean=True)`; rho and m agree to an ulp (CUDA exp vs libm exp)."""
+    from .._capi import LatticeSetup
+    k = k or Constants()
+    w = k.bc_width
+    if k.dim == 2:
+        dmin, dmax = (-k.dom_length / 2.0, 0.0, 0.0), (k.dom_length / 2.0, k.dom_height, 0.0)
+        bmin, bmax = (dmin[0] - w, dmin[1] - w, 0.0), (dmax[0] + w, dmax[1] + w, 0.0)
+    else:
+        dmin = (-k.dom_length / 2.0, 0.0, -k.dom_width / 2.0)
+        dmax = (k.dom_length / 2.0, k.dom_height, k.dom_width / 2.0)
+        bmin, bmax = tuple(v - w for v in dmin), tuple(v + w for v in dmax)
+    grid_id = {"square": 0, "hexagonal": 1, "cubic": 2}[k.grid if k.dim == 2 else "cubic"]
+    if capacity is None:
+        if grid_id == 1:
+            sx, sy = (4 / 3) ** (1 / 4) * k.dr, (3 / 4) ** (1 / 4) * k.dr
+        else:
+            sx = sy = k.dr
+        ni = math.ceil(bmax[0] / sx) - math.floor(bmin[0] / sx) + 3
+        nj = math.ceil(bmax[1] / sy) - math.floor(bmin[1] / sy) + 1
+        nk = (math.ceil(bmax[2] / k.dr) - math.floor(bmin[2] / k.dr) + 1) if k.dim == 3 else 1
+        capacity = ni * nj * nk + 1024
+    from ..geometry import Box
+    sys = ParticleSystem(LeanParticle, Box(bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2]), k.h0,
+                         params=k.params(), capacity=capacity, **sys_kw)
+    su = LatticeSetup()
+    su.grid, su.mountain, su.dr = grid_id, (1 if k.dim == 2 else 2), k.dr
+    su.dom_min[:], su.dom_max[:] = dmin, dmax
+    su.bc_width, su.h_m, su.a, su.U = w, k.h_m, k.a, k.U
+    su.type_fluid, su.type_wall, su.type_mountain, su.h0 = FLUID, WALL, k.mountain_type, k.h0
+    sys.group_counts = list(sys.generate_mountain_wave(su))
+    sys.constants = k
+    return sys
 
 
 def make_system(k: Optional[Constants] = None, lean: bool = False, clip=None,

@@ -224,9 +224,13 @@ class SlabRun:
 
     # ------------------------------------------------------------------ construction
     @classmethod
-    def bell_hill_3d(cls, nx, ny, nz, rank=0, world=1, device=0, stream=None, flags: int = 0, **kw):
+    def bell_hill_3d(cls, nx, ny, nz, rank=0, world=1, device=0, stream=None, flags: int = 0,
+                     device_gen: bool = False, **kw):
         """BASELINE config 4/5 split into x-slabs; every rank generates only its own lattice
-        planes, global particle indices are agreed on by an all-gather of group sizes."""
+        planes (on the host, or on the GPU with `device_gen`), global particle indices are agreed
+        on by an all-gather of group sizes."""
+        if device_gen:
+            return cls._bell_hill_3d_device(nx, ny, nz, rank, world, device, stream, flags, **kw)
         if world == 1:
             case = cases.bell_hill_3d(nx, ny, nz, lean=True, **kw)
             sys = cases.to_system(case, device=device, stream=stream, flags=flags)
@@ -265,6 +269,49 @@ class SlabRun:
         run = cls(sys, plan, n_global, LibSlabBackend(sys, plan, ghost_est))
         run.case_info = case.info
         run._owned_host = (case.fields, gidx)
+        return run
+
+    @classmethod
+    def _bell_hill_3d_device(cls, nx, ny, nz, rank, world, device, stream, flags, h_m=100.0, a=10e3, U=20.0):
+        """the same particle set, generated by sphmw_generate_mountain_wave on each rank's GPU"""
+        k = wpw.Constants(n_y=float(ny), h_m=h_m, a=a, U=U, dim=3, grid="cubic",
+                          mountain_type=wpw.MOUNTAIN if h_m else wpw.FLUID)
+        k.dom_length, k.dom_width = nx * k.dr, nz * k.dr
+        info = dict(dr=k.dr, dt=k.dt, frame_every=int(round(k.dt_frame / k.dt)))
+        if world == 1:
+            sys = wpw.make_system_on_device(k, device=device, stream=stream, flags=flags)
+            run = cls(sys, None, sys.n_device)
+            run.case_info = info
+            return run
+        import torch
+        import torch.distributed as dist
+        w = k.bc_width
+        box_min = (-k.dom_length / 2.0 - w, 0.0 - w, -k.dom_width / 2.0 - w)
+        box_max = (k.dom_length / 2.0 + w, k.dom_height + w, k.dom_width / 2.0 + w)
+        plan = plan_slab(box_min, box_max, k.h0, rank, world)
+        sites = (nx + 14) * (ny + 14) * (nz + 14)
+        own_est = int(sites * (plan.hi - plan.lo + 1) / plan.ncols) + 65536
+        ghost_est = int(own_est * 2 * GHOST_COLS / max(1, plan.hi - plan.lo) * 1.5) + 4096
+        sys = wpw.make_system_on_device(k, capacity=int(own_est * 1.1) + 2 * ghost_est, device=device,
+                                        stream=stream, flags=flags, slab=(plan.lo, plan.hi))
+        n_own = sys.n_device
+        t = torch.tensor(list(sys.group_counts), dtype=torch.int64, device=torch.device("cuda", device))
+        allc = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allc, t)
+        allc = np.stack([a_.cpu().numpy() for a_ in allc])
+        gidx = global_indices(allc, rank)
+        check(_capi.lib().sphmw_set_index(sys.ctx, _capi.ptr(np.ascontiguousarray(gidx)), n_own))
+        run = cls(sys, plan, int(allc.sum()), LibSlabBackend(sys, plan, ghost_est))
+        run.case_info = info
+        # host copies of the carried state for the end-to-end cycle (read back once)
+        from .system import FIELD_NCOMP, canonical
+        host = {}
+        for f in wpw.CORE_FIELDS:
+            nc = FIELD_NCOMP[canonical(f)]
+            buf = np.empty((nc, n_own) if nc == 3 else n_own, dtype=np.float64)
+            check(_capi.lib().sphmw_download_raw(sys.ctx, canonical(f).encode(), _capi.ptr(buf), n_own, nc))
+            host[canonical(f)] = np.ascontiguousarray(buf.T) if nc == 3 else buf
+        run._owned_host = (host, gidx)
         return run
 
     @classmethod

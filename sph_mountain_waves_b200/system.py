@@ -262,6 +262,14 @@ class ParticleSystem:
         self._flush()
         check(_capi.lib().sphmw_step(self.ctx, (scheme or self.T.scheme).encode(), nsteps))
 
+    def generate_mountain_wave(self, setup) -> tuple:
+        """device-side make_system() (sphmw_generate_mountain_wave); returns the three group sizes"""
+        self._flush()
+        n = C.c_int64()
+        gc = (C.c_int64 * 3)()
+        check(_capi.lib().sphmw_generate_mountain_wave(self.ctx, C.byref(setup), C.byref(n), gc))
+        return tuple(gc)
+
     def flow_add_new_particles(self) -> int:
         """≙ add_new_particles!(sys) — src/legacy/isothermal_flow_witch.jl:175-186"""
         self._flush()
