@@ -34,6 +34,8 @@ WORKLOADS = {
     "bell_hill_3d_64M": (1920, 150, 192),
     "bell_hill_3d_8M": (960, 75, 96),
     "bell_hill_3d_1M": (480, 38, 48),
+    # BASELINE config 5 (scaling sweep, large end): ~264 M particles; use --device-gen
+    "bell_hill_3d_256M": (3100, 240, 320),
     # BASELINE config 3: 2D Witch of Agnesi, dr = 26 km / 510 (one GPU only)
     "witch_2d_4M": None,
 }
