@@ -303,16 +303,21 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
                     g.key_diff[g.ndiff++] = (int)(di + g.lim[0] * (dj + g.lim[1] * dk));
                 }
     }
-    // physical x-chunking.  A pass needs three x-y planes of cells at a time; the chunk width
-    // is chosen so that three chunk-planes (~6 particles x ~100 B per cell) stay near 40 MB,
-    // well inside the 126 MB L2: Cx ~ 22000 / Ly columns (256 for the 64 M case; measured
-    // best of 32..2048 there, profiles/r01_tuning.md).  2D grids need no chunking.
+    // physical x-chunking.  A pass needs three x-y planes of cells at a time; chunks are sized
+    // so that three chunk-planes (~6 particles x ~100 B per cell) stay near 40 MB, well inside
+    // the 126 MB L2: about 22000 / Ly columns (measured on the 64 M case, profiles/r01_tuning.md:
+    // 256 columns best of 32..2048).  Grids up to 1.5x that wide, and 2D grids, stay one chunk
+    // (plain x-fastest rows); wider ones are cut into equal-looking power-of-two chunks.
     {
-        long long want = g.dim == 3 ? 22000 / (g.lim[1] > 0 ? g.lim[1] : 1) : (1LL << 30);
-        g.cx_shift = 5;
-        while ((1LL << (g.cx_shift + 1)) <= want && g.cx_shift < 30) ++g.cx_shift;
-        // never pad the column count by more than 2x
-        while (g.cx_shift > 0 && (1LL << g.cx_shift) >= 2 * g.lim[0]) --g.cx_shift;
+        const long long lx = g.lim[0];
+        const long long want = g.dim == 3 ? std::max<long long>(32, 22000 / std::max<long long>(1, g.lim[1])) : lx;
+        long long cols = lx;
+        if (2 * lx > 3 * want) {
+            const long long nchunks = (lx + want - 1) / want;
+            cols = (lx + nchunks - 1) / nchunks;
+        }
+        g.cx_shift = 0;
+        while ((1LL << g.cx_shift) < cols) ++g.cx_shift;
     }
     if (getenv("SPHMW_CX_SHIFT")) g.cx_shift = atoi(getenv("SPHMW_CX_SHIFT"));
     g.rows = g.lim[1] * g.lim[2];
