@@ -69,6 +69,17 @@ typedef struct sphmw_config {
  * cell-centric pair-parallel kernel (strict arithmetic, bit-identical results). */
 #define SPHMW_FLAG_FAST_MATH 1
 #define SPHMW_FLAG_CELL_PAIRS 2
+/* Pair list (no reference equivalent; results are unchanged bit for bit).  By default the first
+ * binary pass after a create_cell_list! records each particle's candidates in traversal order
+ * when the previous cell list saw two or more binary passes (always inside the fused "wcsph"
+ * step), and later passes on the same cell list read that list instead of walking the 9/27
+ * neighbour cells again.  NO_PAIR_LIST: always walk the cells.  PAIR_LIST_EAGER: record on the
+ * first pass of every cell list.  NO_F32_FILTER: the recording pass tests candidates in FP64
+ * only (default: conservative FP32 pre-test on a mirror of the positions, exact FP64 test for
+ * the survivors). */
+#define SPHMW_FLAG_NO_PAIR_LIST 4
+#define SPHMW_FLAG_PAIR_LIST_EAGER 8
+#define SPHMW_FLAG_NO_F32_FILTER 16
 
 int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out);
 int sphmw_destroy(sphmw_ctx *ctx);
@@ -169,6 +180,11 @@ int sphmw_pairs_dump(sphmw_ctx *ctx, int64_t *pi, int64_t *pj, int64_t cap, int6
 /* accepted pairs of the last binary pass (needs sphmw_count_pairs(ctx,1)) */
 int sphmw_count_pairs(sphmw_ctx *ctx, int32_t enable);
 int sphmw_pair_count(sphmw_ctx *ctx, int64_t *n);
+
+/* pair-list bookkeeping: out[0] entries per particle (stride), out[1] lists built so far,
+ * out[2] particles whose candidates did not fit the stride (they walk the cells instead),
+ * out[3] bytes of device memory held by the list.  Blocks. */
+int sphmw_pair_list_info(sphmw_ctx *ctx, int64_t out[4]);
 
 /* ≙ avg_velocity / max_velocity / length(sys.particles)
  * (wcsph_perturbed_witch.jl:338-350,377).  what: "avg_speed" | "max_speed" |

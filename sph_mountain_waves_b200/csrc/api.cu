@@ -3,6 +3,7 @@
 // ParticleField (src/structs.jl:118-125), diagnostics of the drivers
 // (src/current/wcsph_perturbed_witch.jl:338-350), smoothing kernels (src/kernels.jl).
 #include <math.h>
+#include <cmath>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -339,6 +340,24 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
         while (sqrt(nextafter(t, INFINITY)) <= g.h) t = nextafter(t, INFINITY);
         g.r2_max = t;
     }
+    {
+        // FP32 pre-test of the pair-list recording pass (pair_list.cuh).  The mirror stores
+        // float(x - box_min): |error| <= ext * 2^-24 per coordinate.  For a true pair
+        // (|dx| <= h) the FP32 difference is off by at most eps, hence r2_f <= T below
+        // (the (1 + 8u) factor covers the roundings of the three products and two sums).
+        double ext = 0.0;
+        for (int a = 0; a < 3; ++a) ext = std::max(ext, cfg->box_max[a] - cfg->box_min[a]);
+        const double u = ldexp(1.0, -24);
+        const double delta = ext * u * 1.001;
+        const double eps = 2.0 * delta + u * (g.h + 2.0 * delta) * 1.001;
+        const double T = (g.h * g.h + 3.0 * (2.0 * g.h * eps + eps * eps)) * (1.0 + 8.0 * u);
+        float tf = (float)T;
+        while ((double)tf < T) tf = nextafterf(tf, INFINITY);
+        tf = nextafterf(tf, INFINITY);
+        c->pl.r2f_max = tf;
+        // worth it only while the margin stays thin (else too many false candidates)
+        c->f32_filter_ok = std::isfinite(T) && T < 1.02 * g.h * g.h && (double)tf < 3.0e38 && T > 1e-30;
+    }
     memset(&c->prm, 0, sizeof(Params));
 
     int rc = [&]() -> int {
@@ -363,6 +382,8 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
         CUDA_TRY(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8));
         CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 8, c->stream));
         CUDA_TRY(cudaMallocHost(&c->h_counters, sizeof(unsigned long long) * 8));
+        CUDA_TRY(cudaMalloc(&c->xf, sizeof(float4) * (c->cap + 4)));  // +4: pair_list.cuh reads past a run
+        CUDA_TRY(cudaMemsetAsync(c->xf, 0, sizeof(float4) * (c->cap + 4), c->stream));
         CUDA_TRY(cudaMalloc(&c->staging, sizeof(double) * 3 * c->cap));
         CUDA_TRY(cudaMalloc(&c->reduce_tmp, sizeof(double) * 4096));
         return SPHMW_OK;
@@ -390,6 +411,7 @@ extern "C" int sphmw_destroy(sphmw_ctx *c) {
     cudaFree(c->cell_start); cudaFree(c->scan_tmp); cudaFree(c->removed);
     cudaFree(c->mv_old); cudaFree(c->mv_new);
     cudaFree(c->d_counters); cudaFree(c->staging); cudaFree(c->reduce_tmp);
+    cudaFree(c->xf); cudaFree(c->pl.list); cudaFree(c->pl.cnt);
     if (c->h_removed) cudaFreeHost(c->h_removed);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto &t : c->timing_pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -732,6 +754,11 @@ extern "C" int sphmw_pairs_dump(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t 
     CUDA_TRY(cudaSetDevice(c->device));
     if (c->slab_lo >= 0) { sphmw_set_error("pairs_dump is a whole-domain test hook"); return SPHMW_E_STATE; }
     return sphmw_dump_pairs(c, pi, pj, cap, n);
+}
+extern "C" int sphmw_pair_list_info(sphmw_ctx *c, int64_t out[4]) {
+    if (!c || !out) return SPHMW_E_INVALID;
+    CUDA_TRY(cudaSetDevice(c->device));
+    return sphmw_pair_list_stats(c, out);
 }
 extern "C" int sphmw_count_pairs(sphmw_ctx *c, int32_t enable) {
     if (!c) return SPHMW_E_INVALID;

@@ -231,6 +231,10 @@ struct GatherList {
     const double *from[NSLOT];
     double *to[NSLOT];
     int count;
+    // FP32 mirror of the sorted positions relative to the box origin (pair_list.cuh)
+    int xpos[3];  // entry of x0/x1/x2 in the lists above (-1: no such component)
+    double org[3];
+    float4 *xf;
 };
 
 __global__ void k_gather(GatherList gl, const uint32_t *__restrict__ src,
@@ -248,7 +252,15 @@ __global__ void k_gather(GatherList gl, const uint32_t *__restrict__ src,
     key_out[slot] = key[s];
     tag_out[slot] = tag[s];
     cellx_out[slot] = cellx[s];
-    for (int f = 0; f < gl.count; ++f) gl.to[f][slot] = gl.from[f][s];
+    float m[3] = {0.f, 0.f, 0.f};
+    for (int f = 0; f < gl.count; ++f) {
+        const double v = gl.from[f][s];
+        gl.to[f][slot] = v;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (f == gl.xpos[a]) m[a] = (float)(v - gl.org[a]);
+    }
+    gl.xf[slot] = make_float4(m[0], m[1], m[2], 0.f);
 }
 
 __global__ void k_renumber(uint32_t *__restrict__ idx, const uint32_t *__restrict__ pos_of_idx,
@@ -288,6 +300,11 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     const Grid &g = c->grid;
     const int64_t n = c->n;
     const int64_t ncells = g.pkey_max;  // + 1 dead bucket
+    // a new generation: the pair list of the previous one is void; record a new one if the
+    // previous cell list was used by two or more binary passes
+    c->cell_gen += 1;
+    c->want_list = c->passes_this_gen >= 2;
+    c->passes_this_gen = 0;
     if (n == 0) {
         CUDA_TRY(cudaMemsetAsync(c->cell_start, 0, sizeof(uint32_t) * (ncells + 2), c->stream));
         c->cell_list_valid = true;
@@ -373,11 +390,17 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     GatherList gl;
     gl.count = 0;
     int gathered[NSLOT];
+    gl.xf = c->xf;
+    for (int a = 0; a < 3; ++a) {
+        gl.xpos[a] = -1;
+        gl.org[a] = g.box[a];
+    }
     for (int s = 0; s < NSLOT; ++s)
         if (c->allocated[s] && !c->stale[s]) {
             gl.from[gl.count] = c->cur.s[s];
             gl.to[gl.count] = c->alt.s[s];
             gathered[gl.count] = s;
+            if (s >= S_X0 && s <= S_X2) gl.xpos[s - S_X0] = gl.count;
             ++gl.count;
         }
     if (n_new > 0) {

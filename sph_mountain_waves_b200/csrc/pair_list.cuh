@@ -1,0 +1,227 @@
+// Pair-list kernels: _apply_binary! (src/core.jl:94-112) split into a recording pass and
+// replaying passes.  See PairList in sphmw_internal.h for the layout and the invariants.
+//
+//   k_binary_build  walks the 9/27 neighbour cells in key_diff order (structs.jl:73-81) with a
+//                   cheap cut-off test (FP32 on the position mirror, or the exact FP64 one), queues
+//                   the survivors per thread in shared memory, then — with the lanes of a warp
+//                   compacted onto ~26 survivors instead of ~157 candidates — runs the exact test
+//                   `r > sys.h` (core.jl:104-105) and the closure body, and streams the queue
+//                   to the list.
+//   k_binary_list   replays a recorded list: exact test + closure body per entry.
+//
+// Both visit accepted neighbours in exactly the order of k_binary (pair_ops.cu), so every FP64
+// sum is bit-identical to the cell walk.  A particle whose survivors do not fit the list
+// stride, or that was outside the recording pass's column filter, has cnt == NL_NONE and
+// walks the cells with the original loop.
+#pragma once
+#include "sphmw_internal.h"
+
+// the loop of k_binary, for particles without a list
+template <int DIM, class Op>
+__device__ __forceinline__ void nl_walk(Op &op, const Fields &f, const Params &prm, const Grid &g,
+                                        const CellCoord &home, int64_t p, double px, double py,
+                                        double pz, const uint32_t *__restrict__ cell_start,
+                                        unsigned &accepted) {
+    for (int d = 0; d < g.ndiff; ++d) {
+        unsigned nk;
+        if (!neighbour_pkey(g, home, d, nk)) continue;  // core.jl:98
+        uint32_t b = cell_start[nk], e = cell_start[nk + 1];
+        for (uint32_t q = b; q < e; ++q) {
+            double dx = px - f.s[S_X0][q];
+            double dy = py - f.s[S_X1][q];
+            double dz = 0.0;
+            double r2 = dx * dx + dy * dy;
+            if (DIM == 3) {
+                dz = pz - f.s[S_X2][q];
+                r2 = r2 + dz * dz;
+            }
+            if ((r2 > g.r2_max) || (q == p)) continue;
+            double r = sqrt(r2);
+            op.template pair<DIM>(f, prm, p, q, dx, dy, dz, r);
+            ++accepted;
+        }
+    }
+}
+
+// exact test + closure body for one recorded candidate (the particle itself is among them)
+template <int DIM, class Op>
+__device__ __forceinline__ void nl_entry(Op &op, const Fields &f, const Params &prm, const Grid &g,
+                                         int64_t p, uint32_t q, double px, double py, double pz,
+                                         unsigned &accepted) {
+    // dist(p,q) — core.jl:8-10, algebra.jl:49-60: left-to-right, no FMA
+    double dx = px - f.s[S_X0][q];
+    double dy = py - f.s[S_X1][q];
+    double dz = 0.0;
+    double r2 = dx * dx + dy * dy;
+    if (DIM == 3) {
+        dz = pz - f.s[S_X2][q];
+        r2 = r2 + dz * dz;
+    }
+    if ((r2 > g.r2_max) || (q == (uint32_t)p)) return;  // core.jl:105, decided on r2 (Grid::r2_max)
+    double r = sqrt(r2);
+    op.template pair<DIM>(f, prm, p, q, dx, dy, dz, r);
+    ++accepted;
+}
+
+// per-thread queue column in shared memory, addressed with 32-bit shared-window addresses so
+// that a push is one predicated st.shared and one predicated add (the queue is touched only
+// through these volatile statements, which keep their order).  Room for a whole cell run is
+// checked before the run starts (nl_room), not per candidate.
+__device__ __forceinline__ void nl_push(unsigned &top, uint32_t q, bool pass) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred ps;\n\t"
+        "setp.ne.u32 ps, %2, 0;\n\t"
+        "@ps st.shared.u32 [%0], %1;\n\t"
+        "@ps add.u32 %0, %0, %3;\n\t"
+        "}"
+        : "+r"(top)
+        : "r"(q), "r"((unsigned)pass), "n"(NL_BLOCK * 4));
+}
+__device__ __forceinline__ bool nl_room(unsigned top, unsigned end, uint32_t run) {
+    // run < 2^20 keeps the product inside 32 bits; longer runs never fit a stride <= 96 anyway
+    return run < (1u << 20) && top + run * (NL_BLOCK * 4u) <= end;
+}
+__device__ __forceinline__ uint32_t nl_peek(unsigned addr) {
+    uint32_t q;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"(addr));
+    return q;
+}
+
+__device__ __forceinline__ void nl_count_pairs(unsigned long long *pair_counter, unsigned accepted) {
+    if (pair_counter) {
+        unsigned m = __activemask();
+        unsigned tot = __reduce_add_sync(m, accepted);
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(pair_counter, (unsigned long long)tot);
+    }
+}
+
+template <int DIM, class Op, bool F32>
+__global__ void __launch_bounds__(NL_BLOCK)
+k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
+               const uint32_t *__restrict__ cellx, const uint32_t *__restrict__ cell_start, int64_t n,
+               int self, unsigned long long *pair_counter, ColFilter cf, PairList pl) {
+    extern __shared__ uint32_t nl_queue[];  // [stride][NL_BLOCK]: a private column per thread
+    const int64_t p = blockIdx.x * (int64_t)NL_BLOCK + threadIdx.x;
+    if (p >= n) return;
+    const CellCoord home = cell_of(g, key[p], cellx[p]);
+    if (cf.on && !col_selected(cf, home.i)) {
+        if (cf.copy) Op::template skip<DIM>(f, out, p);
+        pl.cnt[p] = NL_NONE;
+        return;
+    }
+    const uint32_t stride = (uint32_t)pl.stride;
+    const unsigned qbase = (unsigned)__cvta_generic_to_shared(nl_queue + threadIdx.x);
+    const unsigned qend = qbase + stride * (NL_BLOCK * 4u);
+    unsigned qtop = qbase;
+    const double px = f.s[S_X0][p], py = f.s[S_X1][p], pz = DIM == 3 ? f.s[S_X2][p] : 0.0;
+    bool fits = true;
+    // ---- phase 1: candidates -> queue -------------------------------------------------
+    if (F32) {
+        const float4 a = pl.xf[p];
+        for (int d = 0; d < g.ndiff; ++d) {
+            unsigned nk;
+            if (!neighbour_pkey(g, home, d, nk)) continue;
+            const uint32_t b = cell_start[nk], e = cell_start[nk + 1];
+            if (!nl_room(qtop, qend, e - b)) {
+                fits = false;
+                break;
+            }
+            // four candidates per trip, loads issued together; slots past the end of the run
+            // read the entries behind it (the mirror is padded) and are masked
+            const uint32_t last = e - 1;
+            for (uint32_t q = b; q < e; q += 4) {
+                const float4 *__restrict__ cp = pl.xf + q;
+                float4 c[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c[i] = cp[i];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float dx = a.x - c[i].x, dy = a.y - c[i].y;
+                    float r2 = fmaf(dy, dy, dx * dx);
+                    if (DIM == 3) {
+                        const float dz = a.z - c[i].z;
+                        r2 = fmaf(dz, dz, r2);
+                    }
+                    const uint32_t qi = q + i;
+                    nl_push(qtop, qi, !((r2 > pl.r2f_max) || (i > 0 && qi > last)));
+                }
+            }
+        }
+    } else {
+        for (int d = 0; d < g.ndiff; ++d) {
+            unsigned nk;
+            if (!neighbour_pkey(g, home, d, nk)) continue;
+            const uint32_t b = cell_start[nk], e = cell_start[nk + 1];
+            if (!nl_room(qtop, qend, e - b)) {
+                fits = false;
+                break;
+            }
+            for (uint32_t q = b; q < e; ++q) {
+                double dx = px - f.s[S_X0][q];
+                double dy = py - f.s[S_X1][q];
+                double r2 = dx * dx + dy * dy;
+                if (DIM == 3) {
+                    double dz = pz - f.s[S_X2][q];
+                    r2 = r2 + dz * dz;
+                }
+                nl_push(qtop, q, !(r2 > g.r2_max));
+            }
+        }
+    }
+    // ---- phase 2: exact test + closure over the queue; queue -> list --------------------
+    Op op;
+    op.template init<DIM>(f, prm, p);
+    unsigned accepted = 0;
+    if (fits) {
+        uint32_t *row = pl.list + ((size_t)(p >> 5) * stride) * 32 + (size_t)(p & 31);
+        for (unsigned a = qbase; a < qtop; a += NL_BLOCK * 4u, row += 32) {
+            const uint32_t q = nl_peek(a);
+            __stcs(row, q);
+            nl_entry<DIM>(op, f, prm, g, p, q, px, py, pz, accepted);
+        }
+        pl.cnt[p] = (qtop - qbase) / (NL_BLOCK * 4u);
+    } else {
+        pl.cnt[p] = NL_NONE;
+        atomicAdd(pl.overflow, 1ull);
+        nl_walk<DIM>(op, f, prm, g, home, p, px, py, pz, cell_start, accepted);
+    }
+    if (self) op.template pair<DIM>(f, prm, p, p, 0.0, 0.0, 0.0, 0.0);  // core.jl:155-157
+    op.template finish<DIM>(f, out, prm, p);
+    nl_count_pairs(pair_counter, accepted);
+}
+
+template <int DIM, class Op>
+__global__ void __launch_bounds__(NL_BLOCK)
+k_binary_list(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
+              const uint32_t *__restrict__ cellx, const uint32_t *__restrict__ cell_start, int64_t n,
+              int self, unsigned long long *pair_counter, ColFilter cf, PairList pl) {
+    const int64_t p = blockIdx.x * (int64_t)NL_BLOCK + threadIdx.x;
+    if (p >= n) return;
+    const CellCoord home = cell_of(g, key[p], cellx[p]);
+    if (cf.on && !col_selected(cf, home.i)) {
+        if (cf.copy) Op::template skip<DIM>(f, out, p);
+        return;
+    }
+    const uint32_t cnt = pl.cnt[p];
+    const double px = f.s[S_X0][p], py = f.s[S_X1][p], pz = DIM == 3 ? f.s[S_X2][p] : 0.0;
+    Op op;
+    op.template init<DIM>(f, prm, p);
+    unsigned accepted = 0;
+    if (cnt != NL_NONE) {
+        const uint32_t *row = pl.list + ((size_t)(p >> 5) * (uint32_t)pl.stride) * 32 + (size_t)(p & 31);
+        // (loading the next entry's position one iteration ahead as well was measured slower:
+        // profiles/r01_tuning.md)
+        uint32_t qn = cnt ? __ldcs(row) : 0u;
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const uint32_t q = qn;
+            if (k + 1 < cnt) qn = __ldcs(row + (size_t)(k + 1) * 32);  // one entry ahead
+            nl_entry<DIM>(op, f, prm, g, p, q, px, py, pz, accepted);
+        }
+    } else {
+        nl_walk<DIM>(op, f, prm, g, home, p, px, py, pz, cell_start, accepted);
+    }
+    if (self) op.template pair<DIM>(f, prm, p, p, 0.0, 0.0, 0.0, 0.0);
+    op.template finish<DIM>(f, out, prm, p);
+    nl_count_pairs(pair_counter, accepted);
+}

@@ -20,6 +20,7 @@
 
 #include "cell_pairs.cuh"
 #include "kernels_sph.cuh"
+#include "pair_list.cuh"
 #include "sphmw_internal.h"
 
 // Julia's max(a,b) propagates NaN (Base.max); fmax does not.
@@ -1111,13 +1112,13 @@ template <int DIM, class Op>
 __global__ void __launch_bounds__(128)
 k_binary(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
          const uint32_t *__restrict__ cellx, const uint32_t *__restrict__ cell_start, int64_t n,
-         int self, unsigned long long *pair_counter, int col_lo, int col_hi) {
+         int self, unsigned long long *pair_counter, ColFilter cf) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
     const CellCoord home = cell_of(g, key[p], cellx[p]);
-    if (col_lo > 0) {  // slab mode: only the columns [col_lo, col_hi] are evaluated
-        if (home.i < col_lo || home.i > col_hi) {
-            Op::template skip<DIM>(f, out, p);
+    if (cf.on) {  // slab mode: only the selected columns are evaluated
+        if (!col_selected(cf, home.i)) {
+            if (cf.copy) Op::template skip<DIM>(f, out, p);
             return;
         }
     }
@@ -1316,9 +1317,58 @@ static int run_unary(sphmw_ctx *c, const char *name) {
 
 // ghost_depth: how many ghost columns (from the owned range outwards) the pass must also
 // evaluate in slab mode; ignored for whole-domain contexts
+static ColFilter filter_for_depth(sphmw_ctx *c, int ghost_depth) {
+    ColFilter cf{0, 0, (int)c->grid.lim[0] - 1, 1, 0, 1};
+    if (c->slab_lo >= 0 && ghost_depth < GHOST_COLS) {
+        cf.on = 1;
+        cf.a0 = GHOST_COLS - ghost_depth;
+        cf.a1 = (int)c->grid.lim[0] - 1 - cf.a0;
+    }
+    return cf;
+}
+
+template <class Op>
+static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Fields &out, ColFilter cf);
+
 template <class Op>
 static int run_binary(sphmw_ctx *c, const char *name, int self, const Fields &out,
                       int ghost_depth = GHOST_COLS) {
+    return run_binary_cols<Op>(c, name, self, out, filter_for_depth(c, ghost_depth));
+}
+
+// device memory of the pair list, allocated on first use
+static int ensure_pair_list(sphmw_ctx *c) {
+    if (c->pl.list) return SPHMW_OK;
+    int stride = c->grid.dim == 3 ? 40 : 32;
+    if (const char *e = getenv("SPHMW_PAIR_LIST_STRIDE")) stride = atoi(e);
+    if (stride < 4) stride = 4;
+    if (stride > 96) stride = 96;  // 48 KB of queue per block
+    const size_t warps = (size_t)((c->cap + 31) / 32);
+    CUDA_TRY(cudaMalloc(&c->pl.list, sizeof(uint32_t) * warps * (size_t)stride * 32));
+    CUDA_TRY(cudaMalloc(&c->pl.cnt, sizeof(uint32_t) * (size_t)c->cap));
+    c->pl.stride = stride;
+    c->pl.overflow = c->d_counters + 2;
+    return SPHMW_OK;
+}
+
+int sphmw_pair_list_stats(sphmw_ctx *c, int64_t out[4]) {
+    out[0] = c->pl.stride;
+    out[1] = c->pl_builds;
+    CUDA_TRY(cudaMemcpyAsync(c->h_counters + 2, c->d_counters + 2, sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    out[2] = (int64_t)c->h_counters[2];
+    out[3] = c->pl.list ? (int64_t)(sizeof(uint32_t) * ((size_t)((c->cap + 31) / 32) * c->pl.stride * 32 + c->cap))
+                        : 0;
+    return SPHMW_OK;
+}
+
+// Three ways to run one binary pass (same results bit for bit):
+//   list valid for this cell list      -> k_binary_list   (replay)
+//   a list is wanted and none exists   -> k_binary_build  (walk once, record)
+//   otherwise                          -> k_binary        (walk)
+template <class Op>
+static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Fields &out, ColFilter cf) {
     if (!c->cell_list_valid) {
         sphmw_set_error("%s: create_cell_list must be called after positions change", name);
         return SPHMW_E_STATE;
@@ -1326,21 +1376,44 @@ static int run_binary(sphmw_ctx *c, const char *name, int self, const Fields &ou
     if (c->n == 0) return SPHMW_OK;
     unsigned long long *pc = c->count_pairs ? c->d_counters : nullptr;
     if (pc) CUDA_TRY(cudaMemsetAsync(pc, 0, sizeof(unsigned long long), c->stream));
-    int col_lo = 0, col_hi = (int)c->grid.lim[0] - 1;
-    if (c->slab_lo >= 0 && ghost_depth < GHOST_COLS) {
-        col_lo = GHOST_COLS - ghost_depth;
-        col_hi = (int)c->grid.lim[0] - 1 - col_lo;
+    const bool lists = !(c->flags & SPHMW_FLAG_NO_PAIR_LIST);
+    const bool replay = lists && c->pl.list && c->pl_gen == c->cell_gen;
+    const bool record = lists && !replay && (c->want_list || (c->flags & SPHMW_FLAG_PAIR_LIST_EAGER));
+    c->passes_this_gen += 1;
+    const unsigned blocks = grid_for(c->n, NL_BLOCK);
+#define NL_ARGS c->cur, out, c->prm, c->grid, c->key, c->cellx, c->cell_start, c->n, self, pc, cf
+    if (replay) {
+        TIMED(c, name);
+        if (c->grid.dim == 2)
+            k_binary_list<2, Op><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
+        else
+            k_binary_list<3, Op><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
+    } else if (record) {
+        TRY(ensure_pair_list(c));
+        c->pl.xf = c->xf;
+        const bool f32 = c->f32_filter_ok && !(c->flags & SPHMW_FLAG_NO_F32_FILTER);
+        const size_t smem = sizeof(uint32_t) * (size_t)c->pl.stride * NL_BLOCK;
+        TIMED(c, name);
+        if (c->grid.dim == 2) {
+            if (f32) k_binary_build<2, Op, true><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+            else k_binary_build<2, Op, false><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+        } else {
+            if (f32) k_binary_build<3, Op, true><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+            else k_binary_build<3, Op, false><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+        }
+        c->pl_gen = c->cell_gen;
+        c->pl_builds += 1;
+    } else {
+        // Measured on B200 (profiles/r01_tuning.md): forcing 6 or 8 resident blocks per SM
+        // (64 registers), 64-thread blocks and software prefetch of the next candidate were all
+        // neutral or slower than this plain configuration.
+        TIMED(c, name);
+        if (c->grid.dim == 2)
+            k_binary<2, Op><<<blocks, 128, 0, c->stream>>>(NL_ARGS);
+        else
+            k_binary<3, Op><<<blocks, 128, 0, c->stream>>>(NL_ARGS);
     }
-    // Measured on B200 (profiles/r01_tuning.md): forcing 6 or 8 resident blocks per SM
-    // (64 registers), 64-thread blocks and software prefetch of the next candidate were all
-    // neutral or slower than this plain configuration.
-    TIMED(c, name);
-    if (c->grid.dim == 2)
-        k_binary<2, Op><<<grid_for(c->n, 128), 128, 0, c->stream>>>(
-            c->cur, out, c->prm, c->grid, c->key, c->cellx, c->cell_start, c->n, self, pc, col_lo, col_hi);
-    else
-        k_binary<3, Op><<<grid_for(c->n, 128), 128, 0, c->stream>>>(
-            c->cur, out, c->prm, c->grid, c->key, c->cellx, c->cell_start, c->n, self, pc, col_lo, col_hi);
+#undef NL_ARGS
     CUDA_TRY(cudaGetLastError());
     return SPHMW_OK;
 }
@@ -1653,7 +1726,9 @@ static int step_wcsph_fused_post(sphmw_ctx *c) {
         TRY(sphmw_ensure_slot(c, s));
         c->stale[s] = false;
     }
-    // owned columns + the first ghost column (its sums are complete thanks to the second)
+    // owned columns + the first ghost column (its sums are complete thanks to the second).
+    // The density pass records the pair list, the force pass replays it.
+    c->want_list = true;
     if (c->flags & SPHMW_FLAG_CELL_PAIRS)
         TRY((run_cell_pairs<CP_Density>(c, "wcsph.density_fused", c->cur, 1)));
     else if (c->flags & SPHMW_FLAG_FAST_MATH)

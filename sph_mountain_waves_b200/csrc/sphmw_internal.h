@@ -119,6 +119,37 @@ __device__ __forceinline__ bool neighbour_pkey(const Grid &g, const CellCoord &c
 #define HALO_KIND_MIGRANT 0.0
 #define HALO_KIND_GHOST 1.0
 
+// which cell columns a pass evaluates (slab mode): [a0,a1] U [b0,b1]; `copy` = particles outside
+// the set carry double-buffered outputs over (B_*::skip)
+struct ColFilter {
+    int on, a0, a1, b0, b1, copy;
+};
+__host__ __device__ __forceinline__ bool col_selected(const ColFilter &cf, int i) {
+    return (i >= cf.a0 && i <= cf.a1) || (i >= cf.b0 && i <= cf.b1);
+}
+
+// ---------------------------------------------------------------------------
+// Neighbour ("pair") list of one cell-list generation.  The first binary pass after a
+// create_cell_list! walks the 9/27 neighbour cells once and records, per particle and in the
+// reference's traversal order (core.jl:94-112), the candidates that passed a CONSERVATIVE
+// cut-off test; every later pass on the same cell list (the force pass of verlet_step!,
+// wcsph_perturbed_witch.jl:330) reads that list instead of walking ~157 candidates again and
+// repeats only the exact FP64 test `r > sys.h` (core.jl:104-105).  Order and accepted set are
+// unchanged, so every sum keeps its bits.
+// Layout: entry k of particle p is list[((p >> 5) * stride + k) * 32 + (p & 31)] — the 32
+// particles of a warp interleaved, so a warp reads/writes one 128-byte line per k.
+// ---------------------------------------------------------------------------
+#define NL_NONE 0xFFFFFFFFu  // cnt value: no list for this particle (walk the cells)
+#define NL_BLOCK 128
+struct PairList {
+    uint32_t *list;
+    uint32_t *cnt;
+    const float4 *xf;  // FP32 mirror of the positions relative to the box origin (cell_list.cu)
+    int stride;
+    float r2f_max;     // FP32 threshold that no true pair (r <= h in FP64) can exceed
+    unsigned long long *overflow;  // counter: particles whose candidates did not fit `stride`
+};
+
 struct TimingEntry {
     int name_id;
     cudaEvent_t a, b;
@@ -164,6 +195,16 @@ struct sphmw_ctx {
     int64_t mv_cap = 0;
     unsigned long long *d_counters = nullptr;  // [0] pair counter, [1] scratch
     unsigned long long *h_counters = nullptr;  // pinned
+
+    // pair list (pair_list.cuh)
+    PairList pl{};
+    float4 *xf = nullptr;          // cap entries, rebuilt by every cell-list build
+    bool f32_filter_ok = false;    // the FP32 mirror resolves the cut-off (box extent / h small enough)
+    uint64_t cell_gen = 0;         // generation of the cell list
+    uint64_t pl_gen = ~0ull;       // generation the pair list was built for
+    bool want_list = false;        // build the list in the next binary pass
+    int passes_this_gen = 0;       // binary passes since the last cell-list build
+    int64_t pl_builds = 0;
 
     double *staging = nullptr;  // 3*cap doubles
     double *reduce_tmp = nullptr;
@@ -222,6 +263,7 @@ int sphmw_materialize(sphmw_ctx *c, int slot);
 int64_t sphmw_list_ops(char *buf, int64_t cap);
 int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n);
 int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added);
+int sphmw_pair_list_stats(sphmw_ctx *c, int64_t out[4]);
 // implemented in cell_list.cu
 int sphmw_exclusive_scan_u32(sphmw_ctx *c, uint32_t *data, int64_t n);
 // implemented in frame_io.cpp

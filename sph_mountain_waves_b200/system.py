@@ -281,6 +281,12 @@ class ParticleSystem:
         self._flags = int(flags)
         check(_capi.lib().sphmw_set_flags(self.ctx, int(flags)))
 
+    def pair_list_info(self) -> dict:
+        """stride, lists built, particles that overflowed the stride, device bytes"""
+        out = (C.c_int64 * 4)()
+        check(_capi.lib().sphmw_pair_list_info(self.ctx, out))
+        return {"stride": out[0], "builds": out[1], "overflow": out[2], "bytes": out[3]}
+
     def sync(self):
         if self._ctx is not None:
             check(_capi.lib().sphmw_sync(self._ctx))

@@ -1,0 +1,157 @@
+"""The pair list (include/sphmw.h SPHMW_FLAG_*PAIR_LIST*, csrc/pair_list.cuh): recording the
+candidates of _apply_binary! (src/core.jl:94-112) on the first binary pass of a cell list and
+replaying them on the later ones must not change a single bit — same accepted set (the exact
+FP64 test `r > sys.h` is repeated on every entry), same traversal order."""
+import os
+
+import numpy as np
+import pytest
+
+from sph_mountain_waves_b200 import cases
+from test_gpu_edge_cases import tiny_case
+from util import bits_equal, load_gpu, load_oracle, n_mismatch
+
+pytestmark = pytest.mark.gpu
+
+FAST_MATH, NO_LIST, EAGER, NO_F32 = 1, 4, 8, 16
+FIELDS = ["x", "v", "h", "rho", "rho_p", "rho_bg", "P", "P_p", "P_bg", "T", "theta", "type"]
+
+
+def small_2d():
+    return cases.mountain_wave_2d(n_y=24.0, dom_length=80e3, h_m=3000.0, a=10e3, U=20.0)
+
+
+def small_3d():
+    return cases.bell_hill_3d(24, 12, 10, h_m=3000.0, a=8e3, U=20.0)
+
+
+@pytest.mark.parametrize("make", [small_2d, small_3d])
+@pytest.mark.parametrize("arith", [0, FAST_MATH])
+def test_fused_step_same_bits_with_and_without_list(gpu, make, arith):
+    case = make()
+    runs = {}
+    for name, flags in (("walk", NO_LIST), ("list", 0), ("list_f64", NO_F32)):
+        s = load_gpu(case, flags=flags | arith)
+        s.create_cell_list()
+        s.count_pairs(True)
+        s.step(6)
+        runs[name] = ({f: s.field(f) for f in FIELDS}, s.pair_count(), s.pair_list_info())
+    assert runs["walk"][2]["builds"] == 0
+    for name in ("list", "list_f64"):
+        info = runs[name][2]
+        assert info["builds"] == 6 and info["overflow"] == 0, info
+        assert runs[name][1] == runs["walk"][1] > 0
+        for f in FIELDS:
+            assert bits_equal(runs[name][0][f], runs["walk"][0][f]), (name, f)
+
+
+@pytest.mark.parametrize("make", [small_2d, small_3d])
+def test_overflowing_particles_walk_the_cells(gpu, make, monkeypatch):
+    """a stride far too small for the lattice: every particle overflows and takes the
+    original loop inside the recording and the replaying kernels"""
+    case = make()
+    ref = load_gpu(case, flags=NO_LIST)
+    ref.create_cell_list()
+    ref.step(3)
+    for stride in ("4", "12"):
+        monkeypatch.setenv("SPHMW_PAIR_LIST_STRIDE", stride)
+        s = load_gpu(case)
+        s.create_cell_list()
+        s.step(3)
+        info = s.pair_list_info()
+        assert info["stride"] == int(stride) and (info["overflow"] > 0 or stride == "12")
+        for f in FIELDS:
+            assert bits_equal(s.field(f), ref.field(f)), (stride, f)
+
+
+@pytest.mark.parametrize("flags", [EAGER, EAGER | NO_F32])
+def test_operator_by_operator_with_eager_list(gpu, flags):
+    """op-by-op through apply!: the density pass records, the force pass replays; sums stay
+    bit-identical to the oracle where no transcendental is involved"""
+    case = small_3d()
+    o, s = load_oracle(case), load_gpu(case, flags=flags)
+    o.create_cell_list()
+    s.create_cell_list()
+    s.count_pairs(True)
+    for op in ("wcsph.reset_density", "wcsph.compute_density"):
+        o.apply(op)
+        s.apply(op)
+    assert o.pair_count() == s.pair_count()
+    assert n_mismatch(s.field("rho"), o.field("rho")) == 0
+    for op in ("wcsph.finalize_density", "wcsph.update_smoothing", "wcsph.compute_pressure"):
+        o.apply(op)
+    for f in ("rho_p", "rho_bg", "h", "P", "P_p", "P_bg"):
+        s.set_field(f, o.field(f))
+    o.apply("wcsph.balance_of_momentum")
+    s.apply("wcsph.balance_of_momentum")
+    assert o.pair_count() == s.pair_count()
+    assert n_mismatch(s.field("Dv"), o.field("Dv")) == 0
+    assert s.pair_list_info()["builds"] == 1
+
+
+@pytest.mark.parametrize("variant", ["hopkins", "hopkins_total"])
+def test_three_pass_schemes_pick_the_list_up_by_themselves(gpu, variant):
+    """schemes with three binary passes per cell list (hopkins_perturbed_witch.jl:325-349)
+    record a list from the second step on (the first cell list shows how many passes use it)"""
+    case = cases.hopkins_2d(variant)
+    a, b = load_gpu(case, flags=NO_LIST), load_gpu(case)
+    for s in (a, b):
+        s.create_cell_list()
+        s.step(5, variant)
+    assert a.pair_list_info()["builds"] == 0 and b.pair_list_info()["builds"] == 4
+    for f in ("x", "v", "rho", "P", "h"):
+        assert bits_equal(a.field(f), b.field(f)), f
+
+
+def test_crowded_cell_and_cutoff_boundary(gpu):
+    """700 particles in one cell (far beyond any stride) and pairs exactly at r == h"""
+    rng = np.random.default_rng(2)
+    n = 700
+    x = np.zeros((n, 3))
+    x[:, :2] = rng.uniform(0.05, 0.95, (n, 2))
+    x[::7, :2] += 1.0
+    case = tiny_case(x, m=rng.uniform(0.5, 1.5, n))
+    o, s = load_oracle(case), load_gpu(case, flags=EAGER)
+    o.create_cell_list()
+    s.create_cell_list()
+    for op in ("wcsph.reset_density", "wcsph.compute_density"):
+        o.apply(op)
+        s.apply(op)
+    assert n_mismatch(s.field("rho"), o.field("rho")) == 0
+    assert s.pair_list_info()["overflow"] > 0
+    # r == h accepted, one ulp beyond rejected — also through the FP32 pre-test, far from the origin
+    off = 2000.0
+    x = [[off, 0.0, 0.0], [off + 1.0, 0.0, 0.0], [off, np.nextafter(1.0, 2.0), 0.0],
+         [off - 0.6, 0.8, 0.0], [off + 0.3, -0.4, 0.0]]
+    case = tiny_case(x, box=((-3.0, -3.0, 0.0), (off + 3.0, 3.0, 0.0)), m=np.arange(1.0, 6.0))
+    o, s = load_oracle(case), load_gpu(case, capacity=16, flags=EAGER)
+    o.create_cell_list()
+    s.create_cell_list()
+    s.count_pairs(True)
+    for _ in range(2):  # second round replays the list
+        for op in ("wcsph.reset_density", "wcsph.compute_density"):
+            o.apply(op)
+            s.apply(op)
+        assert o.pair_count() == s.pair_count()
+        assert n_mismatch(s.field("rho"), o.field("rho")) == 0
+
+
+def test_random_cloud_matches_oracle_pairs_through_the_list(gpu):
+    """disordered particles (uneven cell occupancy): accepted pairs counted by the recording
+    and the replaying kernels equal the oracle's pair dump"""
+    rng = np.random.default_rng(11)
+    n = 4000
+    x = np.zeros((n, 3))
+    x[:, :2] = rng.uniform(-2.9, 2.9, (n, 2))
+    case = tiny_case(x, h=0.25, m=rng.uniform(0.5, 1.5, n))
+    o, s = load_oracle(case), load_gpu(case, flags=EAGER)
+    o.create_cell_list()
+    s.create_cell_list()
+    s.count_pairs(True)
+    pio, _ = o.pairs()
+    for _ in range(2):
+        for op in ("wcsph.reset_density", "wcsph.compute_density"):
+            o.apply(op)
+            s.apply(op)
+        assert s.pair_count() == len(pio)
+        assert n_mismatch(s.field("rho"), o.field("rho")) == 0
