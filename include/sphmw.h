@@ -235,7 +235,7 @@ int sphmw_launch_count(sphmw_ctx *ctx, int64_t *n);
  *     sphmw_step_phase(ctx, "wcsph", 0)        accelerate! + move!
  *     sphmw_halo_pack -> transport -> sphmw_halo_unpack
  *     sphmw_step_phase(ctx, "wcsph", 1)        cell list, density pass, force pass + kick
- * A record is sphmw_halo_record_doubles() doubles; buffers are DEVICE pointers owned by
+ * (phases 2 and 3: the overlapped variant below).  A record is sphmw_halo_record_doubles() doubles; buffers are DEVICE pointers owned by
  * the caller (NULL = no neighbour on that side). */
 int sphmw_step_phase(sphmw_ctx *ctx, const char *scheme, int32_t phase);
 int sphmw_halo_record_doubles(void);
@@ -244,6 +244,20 @@ int sphmw_halo_record_doubles(void);
 int sphmw_halo_pack(sphmw_ctx *ctx, double *dev_buf_left, double *dev_buf_right,
                     int64_t cap_records, int64_t counts[5]);
 int sphmw_halo_unpack(sphmw_ctx *ctx, const double *dev_buf, int64_t count, int64_t n_migrants);
+/* Overlapped variant for all but the last step of a run of steps: the records of the NEXT
+ * exchange travel while the interior columns are still in the force pass.
+ *     sphmw_step_phase(ctx, "wcsph", 2)   cell list, density pass; force pass + kick and the next
+ *                                         step's accelerate! + move! for the edge columns
+ *     sphmw_halo_pack_begin               pack the edge columns (enqueue only)
+ *     sphmw_step_phase(ctx, "wcsph", 3)   the same for the interior columns (enqueue only)
+ *     sphmw_halo_pack_finish              wait for the counts -> transport -> sphmw_halo_unpack
+ * leaves the state of "phase 1; phase 0; pack" bit for bit.  Requires |v| dt < h (a particle
+ * crosses at most one cell column per step); violations make pack_finish fail.
+ * sphmw_halo_pack_wait lets the transport's CUDA stream wait for the packed records. */
+int sphmw_halo_pack_begin(sphmw_ctx *ctx, double *dev_buf_left, double *dev_buf_right,
+                          int64_t cap_records);
+int sphmw_halo_pack_finish(sphmw_ctx *ctx, int64_t cap_records, int64_t counts[5]);
+int sphmw_halo_pack_wait(sphmw_ctx *ctx, void *cuda_stream);
 int sphmw_slab_counts(sphmw_ctx *ctx, int64_t *n_resident, int64_t *n_owned);
 /* global particle index of every resident particle (physical order) */
 int sphmw_set_index(sphmw_ctx *ctx, const int64_t *global_idx, int64_t n);

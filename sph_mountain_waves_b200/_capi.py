@@ -103,6 +103,9 @@ _SIGS = {
     "sphmw_step_phase": (C.c_int, [_P, C.c_char_p, C.c_int32]),
     "sphmw_halo_record_doubles": (C.c_int, []),
     "sphmw_halo_pack": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "sphmw_halo_pack_begin": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_int64]),
+    "sphmw_halo_pack_finish": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64)]),
+    "sphmw_halo_pack_wait": (C.c_int, [_P, C.c_void_p]),
     "sphmw_halo_unpack": (C.c_int, [_P, C.c_void_p, C.c_int64, C.c_int64]),
     "sphmw_slab_counts": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "sphmw_set_index": (C.c_int, [_P, C.c_void_p, C.c_int64]),

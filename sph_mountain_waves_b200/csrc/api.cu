@@ -274,6 +274,7 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
             sphmw_set_error("a slab must own at least %d cell columns", 2 * GHOST_COLS);
             return SPHMW_E_INVALID;
         }
+        c->global_cols = g.lim[0];
         long long width = (c->slab_hi - c->slab_lo) + 2 * GHOST_COLS;
         g.phase[0] += c->slab_lo - GHOST_COLS;
         g.key_max = g.key_max / g.lim[0] * width;
@@ -369,6 +370,8 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
         CUDA_TRY(cudaMalloc(&c->tag, sizeof(uint32_t) * c->cap));
         CUDA_TRY(cudaMalloc(&c->tag_alt, sizeof(uint32_t) * c->cap));
         CUDA_TRY(cudaMalloc(&c->halo_counters, sizeof(uint32_t) * 8));
+        CUDA_TRY(cudaMemsetAsync(c->halo_counters, 0, sizeof(uint32_t) * 8, c->stream));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->pack_event, cudaEventDisableTiming));
         CUDA_TRY(cudaMallocHost(&c->h_halo_counters, sizeof(uint32_t) * 8));
         CUDA_TRY(cudaMalloc(&c->key, sizeof(uint32_t) * c->cap));
         CUDA_TRY(cudaMalloc(&c->cellx, sizeof(uint32_t) * c->cap));
@@ -416,6 +419,7 @@ extern "C" int sphmw_destroy(sphmw_ctx *c) {
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto &t : c->timing_pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->pack_event) cudaEventDestroy(c->pack_event);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return SPHMW_OK;

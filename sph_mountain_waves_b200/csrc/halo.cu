@@ -16,12 +16,17 @@
 
 #include "sphmw_internal.h"
 
+// cf: only the particles that sat in the selected columns BEFORE the drift (cellx is the
+// column of the last cell list) are looked at — the overlapped step packs the edge columns
+// while the interior is still in the force pass; cf.on == 0 looks at everybody.
 template <int DIM>
 __global__ void k_halo_pack(Fields f, const uint32_t *__restrict__ idx, uint32_t *__restrict__ tag,
                             int64_t n, Grid g, int has_left, int has_right, double *buf_l,
-                            double *buf_r, uint32_t cap, uint32_t *counters) {
+                            double *buf_r, uint32_t cap, uint32_t *counters,
+                            const uint32_t *__restrict__ cellx, ColFilter cf) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
+    if (cf.on && !col_selected(cf, (int)cellx[p])) return;
     uint32_t t = tag[p];
     if (t != TAG_OWNED) {
         tag[p] = TAG_DEAD;
@@ -117,32 +122,49 @@ static int ensure_carried(sphmw_ctx *c) {
 
 extern "C" int sphmw_halo_record_doubles(void) { return HALO_RECORD; }
 
-// counts[0..4] = records to the left, to the right, migrants among them (left, right), lost.
-// Blocks (reads the counters back).
-extern "C" int sphmw_halo_pack(sphmw_ctx *c, double *dev_buf_left, double *dev_buf_right,
-                               int64_t cap_records, int64_t counts[5]) {
-    if (!c || !counts) { sphmw_set_error("null argument"); return SPHMW_E_INVALID; }
-    CUDA_TRY(cudaSetDevice(c->device));
-    if (c->slab_lo < 0) { sphmw_set_error("halo_pack: context has no slab"); return SPHMW_E_STATE; }
+// enqueue: classify + pack (all particles, or the edge columns of an overlapped step out of the
+// alt buffers), then read the counters back asynchronously and mark the point with an event
+static int pack_enqueue(sphmw_ctx *c, double *dev_buf_left, double *dev_buf_right, int64_t cap_records,
+                        bool edge_only) {
     TRY(ensure_carried(c));
     const int has_left = dev_buf_left != nullptr, has_right = dev_buf_right != nullptr;
-    CUDA_TRY(cudaMemsetAsync(c->halo_counters, 0, sizeof(uint32_t) * 8, c->stream));
+    // [0..4] belong to this pack; [5] (escapes counted by the previous interior advance) is read
+    // together with them and cleared afterwards
+    CUDA_TRY(cudaMemsetAsync(c->halo_counters, 0, sizeof(uint32_t) * 5, c->stream));
     if (c->n > 0) {
+        Fields view = c->cur;
+        ColFilter cf{0, 0, 0, 0, 0, 0};
+        if (edge_only) {
+            for (int s : {S_X0, S_X1, S_X2, S_V0, S_V1, S_V2}) view.s[s] = c->alt.s[s];
+            cf = sphmw_slab_cols(c).edge;
+        }
         TIMED(c, "halo_pack");
         if (c->grid.dim == 2)
             k_halo_pack<2><<<grid_for(c->n, 256), 256, 0, c->stream>>>(
-                c->cur, c->idx, c->tag, c->n, c->grid, has_left, has_right, dev_buf_left,
-                dev_buf_right, (uint32_t)cap_records, c->halo_counters);
+                view, c->idx, c->tag, c->n, c->grid, has_left, has_right, dev_buf_left,
+                dev_buf_right, (uint32_t)cap_records, c->halo_counters, c->cellx, cf);
         else
             k_halo_pack<3><<<grid_for(c->n, 256), 256, 0, c->stream>>>(
-                c->cur, c->idx, c->tag, c->n, c->grid, has_left, has_right, dev_buf_left,
-                dev_buf_right, (uint32_t)cap_records, c->halo_counters);
+                view, c->idx, c->tag, c->n, c->grid, has_left, has_right, dev_buf_left,
+                dev_buf_right, (uint32_t)cap_records, c->halo_counters, c->cellx, cf);
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaMemcpyAsync(c->h_halo_counters, c->halo_counters, sizeof(uint32_t) * 8,
                              cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->halo_counters + 5, 0, sizeof(uint32_t), c->stream));
+    CUDA_TRY(cudaEventRecord(c->pack_event, c->stream));
+    return SPHMW_OK;
+}
+
+static int pack_collect(sphmw_ctx *c, int64_t cap_records, int64_t counts[5]) {
+    CUDA_TRY(cudaEventSynchronize(c->pack_event));
     for (int k = 0; k < 5; ++k) counts[k] = c->h_halo_counters[k];
+    if (c->h_halo_counters[5] != 0) {
+        sphmw_set_error("overlapped halo exchange: %u particle(s) crossed more than one cell column in a "
+                        "step (it assumes |v| dt < h); use the plain step_phase 0/1 sequence",
+                        c->h_halo_counters[5]);
+        return SPHMW_E_STATE;
+    }
     if (counts[0] > cap_records || counts[1] > cap_records) {
         sphmw_set_error("halo buffer too small: %lld/%lld records for capacity %lld",
                         (long long)counts[0], (long long)counts[1], (long long)cap_records);
@@ -150,6 +172,46 @@ extern "C" int sphmw_halo_pack(sphmw_ctx *c, double *dev_buf_left, double *dev_b
     }
     c->n_owned -= counts[2] + counts[3] + counts[4];
     c->cell_list_valid = false;
+    return SPHMW_OK;
+}
+
+// counts[0..4] = records to the left, to the right, migrants among them (left, right), lost.
+// Blocks (reads the counters back).
+extern "C" int sphmw_halo_pack(sphmw_ctx *c, double *dev_buf_left, double *dev_buf_right,
+                               int64_t cap_records, int64_t counts[5]) {
+    if (!c || !counts) { sphmw_set_error("null argument"); return SPHMW_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->slab_lo < 0) { sphmw_set_error("halo_pack: context has no slab"); return SPHMW_E_STATE; }
+    if (c->overlap_stage != 0) { sphmw_set_error("halo_pack: an overlapped step is in flight"); return SPHMW_E_STATE; }
+    TRY(pack_enqueue(c, dev_buf_left, dev_buf_right, cap_records, false));
+    return pack_collect(c, cap_records, counts);
+}
+
+// The two halves of sphmw_halo_pack for the overlapped step (step_phase 2 -> pack_begin ->
+// step_phase 3 -> pack_finish): begin only enqueues, so the interior force pass can be queued
+// behind it before the host waits for the counts.
+extern "C" int sphmw_halo_pack_begin(sphmw_ctx *c, double *dev_buf_left, double *dev_buf_right,
+                                     int64_t cap_records) {
+    if (!c) { sphmw_set_error("null argument"); return SPHMW_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->slab_lo < 0) { sphmw_set_error("halo_pack_begin: context has no slab"); return SPHMW_E_STATE; }
+    if (c->overlap_stage != 1) { sphmw_set_error("halo_pack_begin: call step_phase 2 first"); return SPHMW_E_STATE; }
+    TRY(pack_enqueue(c, dev_buf_left, dev_buf_right, cap_records, true));
+    c->overlap_stage = 2;
+    return SPHMW_OK;
+}
+extern "C" int sphmw_halo_pack_finish(sphmw_ctx *c, int64_t cap_records, int64_t counts[5]) {
+    if (!c || !counts) { sphmw_set_error("null argument"); return SPHMW_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->overlap_stage != 3) { sphmw_set_error("halo_pack_finish: call step_phase 3 first"); return SPHMW_E_STATE; }
+    c->overlap_stage = 0;
+    return pack_collect(c, cap_records, counts);
+}
+// make another stream (the transport's) wait for the packed records
+extern "C" int sphmw_halo_pack_wait(sphmw_ctx *c, void *cuda_stream) {
+    if (!c) return SPHMW_E_INVALID;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)cuda_stream, c->pack_event, 0));
     return SPHMW_OK;
 }
 

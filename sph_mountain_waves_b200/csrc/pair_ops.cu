@@ -1755,12 +1755,159 @@ static int step_wcsph_fused(sphmw_ctx *c) {
     return step_wcsph_fused_post(c);
 }
 
+// ===========================================================================
+// Overlapped slab step (SURVEY.md §8e "overlap"): the halo exchange of step n+1 travels while
+// the interior columns of step n are still in the force pass.
+//
+//   phase 2   cell list, density pass, force + kick of the EDGE columns (the three outermost
+//             owned columns of each side that has a neighbour), then the next step's
+//             accelerate! + move! (wcsph_perturbed_witch.jl:311-312) for the edge columns,
+//             written to the alt buffers because the interior force pass still reads the
+//             old positions and velocities
+//   (halo.cu) sphmw_halo_pack_begin packs the edge columns' records from the alt buffers
+//   phase 3   force + kick of the interior columns, their accelerate! + move!, buffer swap
+//   (halo.cu) sphmw_halo_pack_finish, transport, sphmw_halo_unpack
+//
+// accelerate!/move! are per-particle, so doing them column set by column set changes no bit.
+// Records of the next exchange can only come from particles that sit in the edge columns
+// before the drift as long as nothing moves a whole cell column per step (|v| dt < h;
+// dt = 0.01 h/c in the drivers); the interior kernel counts violations and
+// sphmw_halo_pack_finish fails loudly on them.
+// ===========================================================================
+static ColFilter cols_range(int a0, int a1, int b0, int b1) {
+    ColFilter cf{1, a0, a1, b0, b1, 0};
+    return cf;
+}
+
+SlabCols sphmw_slab_cols(const sphmw_ctx *c) {
+    const int W = (int)c->grid.lim[0], G = GHOST_COLS;
+    const bool hl = c->slab_lo > 0, hr = c->slab_hi < c->global_cols;
+    const int il = hl ? G + 3 : 0;                     // first interior column
+    const int ir = hr ? W - G - 4 : W - 1;             // last interior column
+    const int er = hr ? (ir + 1 > il ? ir + 1 : il) : W;  // first column of the right edge set
+    SlabCols sc;
+    sc.edge = cols_range(hl ? 0 : 1, hl ? il - 1 : 0, hr ? er : 1, hr ? W - 1 : 0);
+    sc.interior = cols_range(il, ir, 1, 0);
+    sc.force_edge = cols_range(hl ? G : 1, hl ? il - 1 : 0, hr ? er : 1, hr ? W - G - 1 : 0);
+    sc.force_interior = cols_range(il > G ? il : G, ir < W - G - 1 ? ir : W - G - 1, 1, 0);
+    return sc;
+}
+
+// next step's accelerate! + move! for the particles of the selected columns, out of place:
+// `mix` has x and v in the alt buffers (v already holds the force pass's result) and every
+// other field in the current ones.  Ghosts just carry their state over (they are dropped by
+// the next pack).  check_escape: count particles that end up in a column whose records were
+// already packed.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_advance_cols(Fields cur, Fields mix, Params prm, Grid g, const uint32_t *__restrict__ cellx,
+               const uint32_t *__restrict__ tag, int64_t n, ColFilter cf, int check_escape, int has_left,
+               int has_right, uint32_t *__restrict__ counters) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    if (!col_selected(cf, (int)cellx[p])) return;
+    mix.s[S_X0][p] = cur.s[S_X0][p];
+    mix.s[S_X1][p] = cur.s[S_X1][p];
+    if (DIM == 3) mix.s[S_X2][p] = cur.s[S_X2][p];
+    if (tag[p] != TAG_OWNED) {
+        mix.s[S_V0][p] = cur.s[S_V0][p];
+        mix.s[S_V1][p] = cur.s[S_V1][p];
+        if (DIM == 3) mix.s[S_V2][p] = cur.s[S_V2][p];
+        return;
+    }
+    U_wcsph_accelerate<false>::apply<DIM>(mix, prm, p);
+    U_wcsph_move::apply<DIM>(mix, prm, p);
+    if (check_escape) {
+        const long long W = g.lim[0];
+        const long long i = (long long)floor(mix.s[S_X0][p] / g.h) - g.phase[0];
+        if ((has_left && i < 2 * GHOST_COLS) || (has_right && i >= W - 2 * GHOST_COLS))
+            atomicAdd(&counters[5], 1u);
+    }
+}
+
+static Fields mixed_view(sphmw_ctx *c) {
+    Fields m = c->cur;
+    for (int s : {S_X0, S_X1, S_X2, S_V0, S_V1, S_V2}) m.s[s] = c->alt.s[s];
+    return m;
+}
+
+static int run_advance_cols(sphmw_ctx *c, const char *name, const ColFilter &cf, int check_escape) {
+    if (c->n == 0) return SPHMW_OK;
+    const int hl = c->slab_lo > 0, hr = c->slab_hi < c->global_cols;
+    TIMED(c, name);
+    if (c->grid.dim == 2)
+        k_advance_cols<2><<<grid_for(c->n, 256), 256, 0, c->stream>>>(
+            c->cur, mixed_view(c), c->prm, c->grid, c->cellx, c->tag, c->n, cf, check_escape, hl, hr, c->halo_counters);
+    else
+        k_advance_cols<3><<<grid_for(c->n, 256), 256, 0, c->stream>>>(
+            c->cur, mixed_view(c), c->prm, c->grid, c->cellx, c->tag, c->n, cf, check_escape, hl, hr, c->halo_counters);
+    CUDA_TRY(cudaGetLastError());
+    return SPHMW_OK;
+}
+
+static int run_fused_force(sphmw_ctx *c, const char *name, const ColFilter &cf) {
+    if (c->flags & SPHMW_FLAG_FAST_MATH) return run_binary_cols<B_wcsph_momentum_fast>(c, name, 0, c->alt, cf);
+    return run_binary_cols<B_wcsph_momentum_fused>(c, name, 0, c->alt, cf);
+}
+
+static int step_wcsph_overlap_a(sphmw_ctx *c) {
+    if (c->slab_lo < 0 || (c->flags & SPHMW_FLAG_CELL_PAIRS)) {
+        sphmw_set_error("step_phase 2/3: the overlapped step runs on slab contexts without CELL_PAIRS");
+        return SPHMW_E_STATE;
+    }
+    if (c->overlap_stage != 0) { sphmw_set_error("step_phase 2: an overlapped step is already in flight"); return SPHMW_E_STATE; }
+    if (!c->dv_zero) { sphmw_set_error("step_phase 2: Dv must be zero (run step_phase 0 first)"); return SPHMW_E_STATE; }
+    TRY(sphmw_build_cell_list(c, nullptr));
+    for (int s : {S_RHO_BG, S_RHO_P, S_RHO, S_P_BG, S_P_P, S_P, S_PR2, S_CS}) {
+        TRY(sphmw_ensure_slot(c, s));
+        c->stale[s] = false;
+    }
+    c->want_list = true;
+    if (c->flags & SPHMW_FLAG_FAST_MATH)
+        TRY((run_binary<B_wcsph_density_fast>(c, "wcsph.density_fused", 0, c->cur, 1)));
+    else
+        TRY((run_binary<B_wcsph_density_fused>(c, "wcsph.density_fused", 0, c->cur, 1)));
+    TRY(sphmw_ensure_slot(c, S_V0));
+    const SlabCols sc = sphmw_slab_cols(c);
+    TRY(run_fused_force(c, "wcsph.momentum_fused_edge", sc.force_edge));
+    TRY(run_advance_cols(c, "wcsph.advance_edge", sc.edge, 0));
+    c->overlap_stage = 1;
+    return SPHMW_OK;
+}
+
+static int step_wcsph_overlap_b(sphmw_ctx *c) {
+    if (c->overlap_stage != 2) {
+        sphmw_set_error("step_phase 3: call step_phase 2 and halo_pack_begin first");
+        return SPHMW_E_STATE;
+    }
+    const SlabCols sc = sphmw_slab_cols(c);
+    TRY(run_fused_force(c, "wcsph.momentum_fused", sc.force_interior));
+    TRY(run_advance_cols(c, "wcsph.advance_interior", sc.interior, 1));
+    for (int s : {S_X0, S_X1, S_X2, S_V0, S_V1, S_V2})
+        if ((s != S_X2 && s != S_V2) || c->grid.dim == 3) std::swap(c->cur.s[s], c->alt.s[s]);
+    // as after step_wcsph_fused_pre: positions changed, per-step derived fields are stale
+    for (int s = S_DV0; s <= S_DV2; ++s)
+        if (c->allocated[s]) c->stale[s] = true;
+    c->cell_list_valid = false;
+    for (int s : {S_RHO_BG, S_P_BG, S_P_P, S_P, S_T_P, S_T, S_TH_BG, S_TH_P, S_TH, S_PR2, S_CS})
+        if (c->allocated[s]) c->stale[s] = true;
+    c->overlap_stage = 3;
+    return SPHMW_OK;
+}
+
 int sphmw_step_scheme_phase(sphmw_ctx *c, const char *scheme, int phase) {
     if (strcmp(scheme, "wcsph")) {
         sphmw_set_error("step_phase: only the fused 'wcsph' scheme runs on slabs");
         return SPHMW_E_UNSUPPORTED_OP;
     }
-    return phase == 0 ? step_wcsph_fused_pre(c) : step_wcsph_fused_post(c);
+    switch (phase) {
+        case 0: return step_wcsph_fused_pre(c);
+        case 1: return step_wcsph_fused_post(c);
+        case 2: return step_wcsph_overlap_a(c);
+        case 3: return step_wcsph_overlap_b(c);
+    }
+    sphmw_set_error("step_phase: phase must be 0..3");
+    return SPHMW_E_INVALID;
 }
 
 int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps) {

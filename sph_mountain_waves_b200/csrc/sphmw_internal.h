@@ -164,6 +164,11 @@ struct sphmw_ctx {
     int64_t n = 0;       // particles resident (incl. ghosts in slab mode)
     int64_t cap = 0;
     int64_t slab_lo = -1, slab_hi = -1;
+    int64_t global_cols = 0;  // cell columns of the whole domain (slab contexts)
+    // overlapped slab step (pair_ops.cu step_wcsph_overlap_*, halo.cu): 0 idle, 1 edge columns
+    // advanced into the alt buffers, 2 their records packed, 3 interior advanced and buffers swapped
+    int overlap_stage = 0;
+    cudaEvent_t pack_event = nullptr;
 
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
@@ -264,6 +269,13 @@ int64_t sphmw_list_ops(char *buf, int64_t cap);
 int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n);
 int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added);
 int sphmw_pair_list_stats(sphmw_ctx *c, int64_t out[4]);
+// column sets of the overlapped slab step (local column indices)
+struct SlabCols {
+    ColFilter edge;      // advanced and packed first: ghost columns + the three outermost owned ones
+    ColFilter interior;  // the rest
+    ColFilter force_edge, force_interior;  // their owned parts (the force pass covers owned columns only)
+};
+SlabCols sphmw_slab_cols(const sphmw_ctx *c);
 // implemented in cell_list.cu
 int sphmw_exclusive_scan_u32(sphmw_ctx *c, uint32_t *data, int64_t n);
 // implemented in frame_io.cpp

@@ -197,6 +197,32 @@ class LibSlabBackend:
             return
         check(_capi.lib().sphmw_halo_unpack(self.sys.ctx, C.c_void_p(recv.data_ptr()), len(recv), n_migrants))
 
+    # ---- overlapped step (include/sphmw.h: step_phase 2/3, halo_pack_begin/finish) ----------
+    @property
+    def can_overlap(self) -> bool:
+        return not (self.sys._flags & 2)   # CELL_PAIRS kernels take one column range only
+
+    def overlap_enqueue(self):
+        """finish the current step and start the next one: edge columns first (force, kick,
+        drift, pack), then the interior — everything is only enqueued"""
+        lib = _capi.lib()
+        check(lib.sphmw_step_phase(self.sys.ctx, b"wcsph", 2))
+        pl = C.c_void_p(self.buf_l.data_ptr()) if self.buf_l is not None else None
+        pr = C.c_void_p(self.buf_r.data_ptr()) if self.buf_r is not None else None
+        check(lib.sphmw_halo_pack_begin(self.sys.ctx, pl, pr, self.cap))
+        check(lib.sphmw_step_phase(self.sys.ctx, b"wcsph", 3))
+
+    def pack_finish(self):
+        counts = (C.c_int64 * 5)()
+        check(_capi.lib().sphmw_halo_pack_finish(self.sys.ctx, self.cap, counts))
+        self.lost += counts[4]
+        sl = self.buf_l[:counts[0]] if self.buf_l is not None else None
+        sr = self.buf_r[:counts[1]] if self.buf_r is not None else None
+        return sl, sr, int(counts[2]), int(counts[3])
+
+    def pack_wait(self, cuda_stream: int):
+        check(_capi.lib().sphmw_halo_pack_wait(self.sys.ctx, C.c_void_p(cuda_stream)))
+
     def counts(self):
         a, b = C.c_int64(), C.c_int64()
         check(_capi.lib().sphmw_slab_counts(self.sys.ctx, C.byref(a), C.byref(b)))
@@ -368,14 +394,38 @@ class SlabRun:
             self._halo()
             self.backend.build()
 
-    def step(self, nsteps: int):
-        if self.backend is None:
+    def step(self, nsteps: int, overlap: bool = True):
+        """nsteps of verlet_step!.  On slabs all but the last step run the overlapped schedule:
+        the halo records of step k+1 travel (on a second CUDA stream) while the interior columns
+        of step k are in the force pass.  Same bits either way."""
+        b = self.backend
+        if b is None:
             self.sys.step(nsteps)
             return
-        for _ in range(nsteps):
-            self.backend.pre()
-            self._halo()
-            self.backend.post()
+        if nsteps <= 0:
+            return
+        if not (overlap and nsteps > 1 and getattr(b, "can_overlap", False)):
+            for _ in range(nsteps):
+                b.pre()
+                self._halo()
+                b.post()
+            return
+        import torch
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream(b.dev)
+        comm = self._comm_stream
+        b.pre()
+        self._halo()
+        for _ in range(nsteps - 1):
+            b.overlap_enqueue()
+            sl, sr, ml, mr = b.pack_finish()       # the host waits for the edge columns only
+            with torch.cuda.stream(comm):          # transport beside the interior force pass
+                b.pack_wait(comm.cuda_stream)
+                (rl, nml), (rr, nmr) = exchange(self.plan, sl, sr, ml, mr, b.empty)
+            comm.synchronize()                     # records have arrived (and the sends have left)
+            b.unpack(rl, nml)
+            b.unpack(rr, nmr)
+        b.post()
 
     # ------------------------------------------------------------------ read-back (tests)
     def owned_fields(self, names=("x", "v", "rho", "h")):
@@ -478,7 +528,14 @@ class LocalCluster:
         self.runs = runs
 
     def _halo(self):
-        packs = [r.backend.pack() for r in self.runs]
+        self._handover([r.backend.pack() for r in self.runs])
+
+    def create_cell_list(self):
+        self._halo()
+        for r in self.runs:
+            r.backend.build()
+
+    def _handover(self, packs):
         for r, run in enumerate(self.runs):
             dev = run.backend.dev
             if r > 0:
@@ -488,18 +545,28 @@ class LocalCluster:
                 sl, sr, ml, mr = packs[r + 1]
                 run.backend.unpack(sl.to(dev), ml)      # my right neighbour's left-going records
 
-    def create_cell_list(self):
-        self._halo()
+    def step(self, nsteps: int, overlap: bool = True):
+        if nsteps <= 0:
+            return
+        if not (overlap and nsteps > 1 and all(r.backend.can_overlap for r in self.runs)):
+            for _ in range(nsteps):
+                for r in self.runs:
+                    r.backend.pre()
+                self._halo()
+                for r in self.runs:
+                    r.backend.post()
+            return
         for r in self.runs:
-            r.backend.build()
-
-    def step(self, nsteps: int):
-        for _ in range(nsteps):
+            r.backend.pre()
+        self._halo()
+        for _ in range(nsteps - 1):
             for r in self.runs:
-                r.backend.pre()
-            self._halo()
+                r.backend.overlap_enqueue()
+            self._handover([r.backend.pack_finish() for r in self.runs])
             for r in self.runs:
-                r.backend.post()
+                r.sys.sync()   # a sender's next pack must not overtake the receiver's unpack
+        for r in self.runs:
+            r.backend.post()
 
     def gather(self, names=("x", "v", "rho", "h")):
         """fields of all owned particles in reference index order"""
