@@ -148,6 +148,17 @@ function verlet_steps!(sys::ParticleSystem, scheme::String, n::Integer)
     check(ccall((:sphmw_step, libsphmw), Cint, (Ptr{Cvoid}, Cstring, Int32), sys.ctx, scheme, n))
 end
 
+# flags of `ParticleSystem(...; flags)` (include/sphmw.h): the pair list records each particle's
+# candidates on the first binary pass of a cell list and replays them on the later ones —
+# apply!(sys, compute_density!) then apply!(sys, balance_of_momentum!) walk the cells once
+const FLAG_FAST_MATH, FLAG_NO_PAIR_LIST, FLAG_PAIR_LIST_EAGER, FLAG_NO_F32_FILTER = 1, 4, 8, 16
+"(stride, lists built, particles that overflowed the stride, device bytes)"
+function pair_list_info(sys::ParticleSystem)
+    out = zeros(Int64, 4)
+    GC.@preserve out check(ccall((:sphmw_pair_list_info, libsphmw), Cint, (Ptr{Cvoid}, Ptr{Int64}), sys.ctx, out))
+    return Tuple(out)
+end
+
 # kernels.jl — evaluated on the device (scalar convenience wrappers)
 function kernel_eval(name::String, h::Float64, r::Float64)
     hh = [h]; rr = [r]; out = [0.0]
