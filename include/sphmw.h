@@ -74,12 +74,12 @@ typedef struct sphmw_config {
  * when the previous cell list saw two or more binary passes (always inside the fused "wcsph"
  * step), and later passes on the same cell list read that list instead of walking the 9/27
  * neighbour cells again.  NO_PAIR_LIST: always walk the cells.  PAIR_LIST_EAGER: record on the
- * first pass of every cell list.  NO_F32_FILTER: the recording pass tests candidates in FP64
- * only (default: conservative FP32 pre-test on a mirror of the positions, exact FP64 test for
- * the survivors). */
+ * first pass of every cell list.  NO_PRETEST: the recording pass tests candidates in FP64 only
+ * (default: conservative integer pre-test on a 10-bit-per-axis mirror of each particle's position
+ * inside its cell, exact FP64 test for the survivors). */
 #define SPHMW_FLAG_NO_PAIR_LIST 4
 #define SPHMW_FLAG_PAIR_LIST_EAGER 8
-#define SPHMW_FLAG_NO_F32_FILTER 16
+#define SPHMW_FLAG_NO_PRETEST 16
 
 int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out);
 int sphmw_destroy(sphmw_ctx *ctx);

@@ -293,6 +293,8 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
             for (int dj = -1; dj <= 1; ++dj) {
                 g.nb_di[g.ndiff] = di;
                 g.nb_drest[g.ndiff] = dj;
+                g.nb_dj[g.ndiff] = dj;
+                g.nb_dk[g.ndiff] = 0;
                 g.key_diff[g.ndiff++] = (int)(di + g.lim[0] * dj);
             }
     } else {
@@ -301,6 +303,8 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
             for (int dj = -1; dj <= 1; ++dj)
                 for (int dk = -1; dk <= 1; ++dk) {
                     g.nb_di[g.ndiff] = di;
+                    g.nb_dj[g.ndiff] = dj;
+                    g.nb_dk[g.ndiff] = dk;
                     g.nb_drest[g.ndiff] = (int)(dj + g.lim[1] * dk);
                     g.key_diff[g.ndiff++] = (int)(di + g.lim[0] * (dj + g.lim[1] * dk));
                 }
@@ -341,24 +345,6 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
         while (sqrt(nextafter(t, INFINITY)) <= g.h) t = nextafter(t, INFINITY);
         g.r2_max = t;
     }
-    {
-        // FP32 pre-test of the pair-list recording pass (pair_list.cuh).  The mirror stores
-        // float(x - box_min): |error| <= ext * 2^-24 per coordinate.  For a true pair
-        // (|dx| <= h) the FP32 difference is off by at most eps, hence r2_f <= T below
-        // (the (1 + 8u) factor covers the roundings of the three products and two sums).
-        double ext = 0.0;
-        for (int a = 0; a < 3; ++a) ext = std::max(ext, cfg->box_max[a] - cfg->box_min[a]);
-        const double u = ldexp(1.0, -24);
-        const double delta = ext * u * 1.001;
-        const double eps = 2.0 * delta + u * (g.h + 2.0 * delta) * 1.001;
-        const double T = (g.h * g.h + 3.0 * (2.0 * g.h * eps + eps * eps)) * (1.0 + 8.0 * u);
-        float tf = (float)T;
-        while ((double)tf < T) tf = nextafterf(tf, INFINITY);
-        tf = nextafterf(tf, INFINITY);
-        c->pl.r2f_max = tf;
-        // worth it only while the margin stays thin (else too many false candidates)
-        c->f32_filter_ok = std::isfinite(T) && T < 1.02 * g.h * g.h && (double)tf < 3.0e38 && T > 1e-30;
-    }
     memset(&c->prm, 0, sizeof(Params));
 
     int rc = [&]() -> int {
@@ -385,8 +371,8 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
         CUDA_TRY(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 8));
         CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 8, c->stream));
         CUDA_TRY(cudaMallocHost(&c->h_counters, sizeof(unsigned long long) * 8));
-        CUDA_TRY(cudaMalloc(&c->xf, sizeof(float4) * (c->cap + 4)));  // +4: pair_list.cuh reads past a run
-        CUDA_TRY(cudaMemsetAsync(c->xf, 0, sizeof(float4) * (c->cap + 4), c->stream));
+        CUDA_TRY(cudaMalloc(&c->xq, sizeof(uint32_t) * (c->cap + 4)));  // +4: pair_list.cuh reads past a run
+        CUDA_TRY(cudaMemsetAsync(c->xq, 0, sizeof(uint32_t) * (c->cap + 4), c->stream));
         CUDA_TRY(cudaMalloc(&c->staging, sizeof(double) * 3 * c->cap));
         CUDA_TRY(cudaMalloc(&c->reduce_tmp, sizeof(double) * 4096));
         return SPHMW_OK;
@@ -414,7 +400,7 @@ extern "C" int sphmw_destroy(sphmw_ctx *c) {
     cudaFree(c->cell_start); cudaFree(c->scan_tmp); cudaFree(c->removed);
     cudaFree(c->mv_old); cudaFree(c->mv_new);
     cudaFree(c->d_counters); cudaFree(c->staging); cudaFree(c->reduce_tmp);
-    cudaFree(c->xf); cudaFree(c->pl.list); cudaFree(c->pl.cnt);
+    cudaFree(c->xq); cudaFree(c->pl.list); cudaFree(c->pl.cnt);
     if (c->h_removed) cudaFreeHost(c->h_removed);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto &t : c->timing_pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }

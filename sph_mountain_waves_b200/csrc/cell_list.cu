@@ -231,10 +231,11 @@ struct GatherList {
     const double *from[NSLOT];
     double *to[NSLOT];
     int count;
-    // FP32 mirror of the sorted positions relative to the box origin (pair_list.cuh)
+    // quantised mirror of the sorted positions (pair_list.cuh): where the particle sits inside
+    // its own cell, 10 bits per axis (h/1024)
     int xpos[3];  // entry of x0/x1/x2 in the lists above (-1: no such component)
-    double org[3];
-    float4 *xf;
+    double h;
+    uint32_t *xq;
 };
 
 __global__ void k_gather(GatherList gl, const uint32_t *__restrict__ src,
@@ -252,15 +253,22 @@ __global__ void k_gather(GatherList gl, const uint32_t *__restrict__ src,
     key_out[slot] = key[s];
     tag_out[slot] = tag[s];
     cellx_out[slot] = cellx[s];
-    float m[3] = {0.f, 0.f, 0.f};
+    uint32_t qm = 0;
     for (int f = 0; f < gl.count; ++f) {
         const double v = gl.from[f][s];
         gl.to[f][slot] = v;
 #pragma unroll
         for (int a = 0; a < 3; ++a)
-            if (f == gl.xpos[a]) m[a] = (float)(v - gl.org[a]);
+            if (f == gl.xpos[a]) {
+                // the cell index is floor(x / h) (structs.jl:99, k_keys); what is left of x / h
+                const double t = v / gl.h;
+                const double fr = t - floor(t);  // exact, in [0, 1)
+                int q = (int)(fr * (double)NL_Q10_ONE);
+                q = q < 0 ? 0 : (q > NL_Q10_ONE - 1 ? NL_Q10_ONE - 1 : q);
+                qm |= (uint32_t)q << (10 * a);
+            }
     }
-    gl.xf[slot] = make_float4(m[0], m[1], m[2], 0.f);
+    gl.xq[slot] = qm;
 }
 
 __global__ void k_renumber(uint32_t *__restrict__ idx, const uint32_t *__restrict__ pos_of_idx,
@@ -390,11 +398,9 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     GatherList gl;
     gl.count = 0;
     int gathered[NSLOT];
-    gl.xf = c->xf;
-    for (int a = 0; a < 3; ++a) {
-        gl.xpos[a] = -1;
-        gl.org[a] = g.box[a];
-    }
+    gl.xq = c->xq;
+    gl.h = g.h;
+    for (int a = 0; a < 3; ++a) gl.xpos[a] = -1;
     for (int s = 0; s < NSLOT; ++s)
         if (c->allocated[s] && !c->stale[s]) {
             gl.from[gl.count] = c->cur.s[s];

@@ -2,7 +2,7 @@
 // replaying passes.  See PairList in sphmw_internal.h for the layout and the invariants.
 //
 //   k_binary_build  walks the 9/27 neighbour cells in key_diff order (structs.jl:73-81) with a
-//                   cheap cut-off test (FP32 on the position mirror, or the exact FP64 one), queues
+//                   cheap cut-off test (integers on a 10-bit mirror, or the exact FP64 one), queues
 //                   the survivors per thread in shared memory, then — with the lanes of a warp
 //                   compacted onto ~26 survivors instead of ~157 candidates — runs the exact test
 //                   `r > sys.h` (core.jl:104-105) and the closure body, and streams the queue
@@ -96,7 +96,13 @@ __device__ __forceinline__ void nl_count_pairs(unsigned long long *pair_counter,
     }
 }
 
-template <int DIM, class Op, bool F32>
+// FILTER: how phase 1 tests a candidate — the exact FP64 test (three 8-byte loads), or integers
+// on the 10-bit cell-relative mirror (one 4-byte load; survivors get the exact test in phase 2).
+// An FP32 mirror of the absolute positions (float4, 16-byte loads) was measured slower:
+// profiles/r01b_pair_list.md.
+#define NL_FILTER_F64 0
+#define NL_FILTER_Q10 2
+template <int DIM, class Op, int FILTER>
 __global__ void __launch_bounds__(NL_BLOCK)
 k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
                const uint32_t *__restrict__ cellx, const uint32_t *__restrict__ cell_start, int64_t n,
@@ -117,8 +123,15 @@ k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restr
     const double px = f.s[S_X0][p], py = f.s[S_X1][p], pz = DIM == 3 ? f.s[S_X2][p] : 0.0;
     bool fits = true;
     // ---- phase 1: candidates -> queue -------------------------------------------------
-    if (F32) {
-        const float4 a = pl.xf[p];
+    if (FILTER == NL_FILTER_Q10) {
+        // own position in h/1024 inside the home cell, and the home cell's row coordinates: a
+        // neighbour cell reached without any wrap of the linear key arithmetic (core.jl:98 has no
+        // per-axis check) lies exactly (di, dj, dk) cells away; the few wrapped ones (cells on
+        // the faces of the grid) take the exact FP64 test instead
+        const uint32_t ow = pl.xq[p];
+        const int qx = (int)(ow & 1023u), qy = (int)((ow >> 10) & 1023u), qz = (int)(ow >> 20);
+        const int ly = (int)g.lim[1];
+        const int hj = home.rest % ly, hk = home.rest / ly;
         for (int d = 0; d < g.ndiff; ++d) {
             unsigned nk;
             if (!neighbour_pkey(g, home, d, nk)) continue;
@@ -127,24 +140,41 @@ k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restr
                 fits = false;
                 break;
             }
-            // four candidates per trip, loads issued together; slots past the end of the run
-            // read the entries behind it (the mirror is padded) and are masked
-            const uint32_t last = e - 1;
-            for (uint32_t q = b; q < e; q += 4) {
-                const float4 *__restrict__ cp = pl.xf + q;
-                float4 c[4];
+            const int di = g.nb_di[d], dj = g.nb_dj[d], dk = g.nb_dk[d];
+            const bool regular = (unsigned)(home.i + di) < (unsigned)g.lim[0] && (unsigned)(hj + dj) < (unsigned)ly &&
+                                 (unsigned)(hk + dk) < (unsigned)g.lim[2];
+            if (regular) {
+                int ox = qx - NL_Q10_ONE * di, oy = qy - NL_Q10_ONE * dj, oz = qz - NL_Q10_ONE * dk;
+                asm volatile("" : "+r"(ox), "+r"(oy), "+r"(oz));  // keep them out of the inner loop
+                const uint32_t last = e - 1;
+                for (uint32_t q = b; q < e; q += 4) {
+                    const uint32_t *__restrict__ cp = pl.xq + q;  // padded: slots past the run are masked
+                    uint32_t w[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) c[i] = cp[i];
+                    for (int i = 0; i < 4; ++i) w[i] = cp[i];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float dx = a.x - c[i].x, dy = a.y - c[i].y;
-                    float r2 = fmaf(dy, dy, dx * dx);
-                    if (DIM == 3) {
-                        const float dz = a.z - c[i].z;
-                        r2 = fmaf(dz, dz, r2);
+                    for (int i = 0; i < 4; ++i) {
+                        const int dx = ox - (int)(w[i] & 1023u);
+                        const int dy = oy - (int)((w[i] >> 10) & 1023u);
+                        int s2 = dx * dx + dy * dy;
+                        if (DIM == 3) {
+                            const int dz = oz - (int)(w[i] >> 20);
+                            s2 += dz * dz;
+                        }
+                        const uint32_t qi = q + i;
+                        nl_push(qtop, qi, !((s2 > NL_Q10_R2MAX) || (i > 0 && qi > last)));
                     }
-                    const uint32_t qi = q + i;
-                    nl_push(qtop, qi, !((r2 > pl.r2f_max) || (i > 0 && qi > last)));
+                }
+            } else {
+                for (uint32_t q = b; q < e; ++q) {
+                    double dx = px - f.s[S_X0][q];
+                    double dy = py - f.s[S_X1][q];
+                    double r2 = dx * dx + dy * dy;
+                    if (DIM == 3) {
+                        double dz = pz - f.s[S_X2][q];
+                        r2 = r2 + dz * dz;
+                    }
+                    nl_push(qtop, q, !(r2 > g.r2_max));
                 }
             }
         }

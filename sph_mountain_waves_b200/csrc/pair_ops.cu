@@ -1390,16 +1390,18 @@ static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Field
             k_binary_list<3, Op><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
     } else if (record) {
         TRY(ensure_pair_list(c));
-        c->pl.xf = c->xf;
-        const bool f32 = c->f32_filter_ok && !(c->flags & SPHMW_FLAG_NO_F32_FILTER);
+        c->pl.xq = c->xq;
+        // pre-test of the recording pass: integers on the 10-bit cell-relative mirror, or
+        // (SPHMW_FLAG_NO_PRETEST) the exact FP64 test only
+        const bool q10 = !(c->flags & SPHMW_FLAG_NO_PRETEST);
         const size_t smem = sizeof(uint32_t) * (size_t)c->pl.stride * NL_BLOCK;
         TIMED(c, name);
         if (c->grid.dim == 2) {
-            if (f32) k_binary_build<2, Op, true><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
-            else k_binary_build<2, Op, false><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+            if (q10) k_binary_build<2, Op, NL_FILTER_Q10><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+            else k_binary_build<2, Op, NL_FILTER_F64><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
         } else {
-            if (f32) k_binary_build<3, Op, true><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
-            else k_binary_build<3, Op, false><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+            if (q10) k_binary_build<3, Op, NL_FILTER_Q10><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+            else k_binary_build<3, Op, NL_FILTER_F64><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
         }
         c->pl_gen = c->cell_gen;
         c->pl_builds += 1;

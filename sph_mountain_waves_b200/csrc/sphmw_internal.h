@@ -73,6 +73,8 @@ struct Grid {
     long long pkey_max;
     int nb_di[27];
     int nb_drest[27];
+    int nb_dj[27];  // the row part split into its y and z offsets (nb_drest = dj + Ly*dk)
+    int nb_dk[27];
 };
 
 #ifdef __CUDACC__
@@ -141,12 +143,19 @@ __host__ __device__ __forceinline__ bool col_selected(const ColFilter &cf, int i
 // ---------------------------------------------------------------------------
 #define NL_NONE 0xFFFFFFFFu  // cnt value: no list for this particle (walk the cells)
 #define NL_BLOCK 128
+// Pre-test of the recording pass on the quantised mirror.  A position is cell + (q + e)/1024 with
+// e in [0,1) per axis, so for a pair with r <= h the integer differences d_a (in h/1024, cell
+// offsets included) satisfy |d_a| < |t_a| + 1 with sum t_a^2 <= 1024^2, hence
+// sum d_a^2 < (1024 + sqrt(3))^2.  1.74 > sqrt(3) leaves room for the rounding of x/h (1e-13).
+#define NL_Q10_ONE 1024
+#define NL_Q10_R2MAX 1052142  // floor((1024 + 1.74)^2)
 struct PairList {
     uint32_t *list;
     uint32_t *cnt;
-    const float4 *xf;  // FP32 mirror of the positions relative to the box origin (cell_list.cu)
+    // 10-bit-per-axis mirror: the position inside its own cell in units of h/1024, x | y<<10 | z<<20
+    // (rebuilt by every cell-list build, cell_list.cu)
+    const uint32_t *xq;
     int stride;
-    float r2f_max;     // FP32 threshold that no true pair (r <= h in FP64) can exceed
     unsigned long long *overflow;  // counter: particles whose candidates did not fit `stride`
 };
 
@@ -203,8 +212,7 @@ struct sphmw_ctx {
 
     // pair list (pair_list.cuh)
     PairList pl{};
-    float4 *xf = nullptr;          // cap entries, rebuilt by every cell-list build
-    bool f32_filter_ok = false;    // the FP32 mirror resolves the cut-off (box extent / h small enough)
+    uint32_t *xq = nullptr;        // cap (+4) entries, rebuilt by every cell-list build
     uint64_t cell_gen = 0;         // generation of the cell list
     uint64_t pl_gen = ~0ull;       // generation the pair list was built for
     bool want_list = false;        // build the list in the next binary pass

@@ -13,7 +13,7 @@ from util import bits_equal, load_gpu, load_oracle, n_mismatch
 
 pytestmark = pytest.mark.gpu
 
-FAST_MATH, NO_LIST, EAGER, NO_F32 = 1, 4, 8, 16
+FAST_MATH, NO_LIST, EAGER, NO_PRETEST = 1, 4, 8, 16
 FIELDS = ["x", "v", "h", "rho", "rho_p", "rho_bg", "P", "P_p", "P_bg", "T", "theta", "type"]
 
 
@@ -28,9 +28,11 @@ def small_3d():
 @pytest.mark.parametrize("make", [small_2d, small_3d])
 @pytest.mark.parametrize("arith", [0, FAST_MATH])
 def test_fused_step_same_bits_with_and_without_list(gpu, make, arith):
+    """list: the recording pass pre-tests candidates with integers on the 10-bit cell-relative
+    mirror; list_f64 (NO_PRETEST): with the exact FP64 test only"""
     case = make()
     runs = {}
-    for name, flags in (("walk", NO_LIST), ("list", 0), ("list_f64", NO_F32)):
+    for name, flags in (("walk", NO_LIST), ("list", 0), ("list_f64", NO_PRETEST)):
         s = load_gpu(case, flags=flags | arith)
         s.create_cell_list()
         s.count_pairs(True)
@@ -64,7 +66,7 @@ def test_overflowing_particles_walk_the_cells(gpu, make, monkeypatch):
             assert bits_equal(s.field(f), ref.field(f)), (stride, f)
 
 
-@pytest.mark.parametrize("flags", [EAGER, EAGER | NO_F32])
+@pytest.mark.parametrize("flags", [EAGER, EAGER | NO_PRETEST])
 def test_operator_by_operator_with_eager_list(gpu, flags):
     """op-by-op through apply!: the density pass records, the force pass replays; sums stay
     bit-identical to the oracle where no transcendental is involved"""
@@ -119,7 +121,7 @@ def test_crowded_cell_and_cutoff_boundary(gpu):
         s.apply(op)
     assert n_mismatch(s.field("rho"), o.field("rho")) == 0
     assert s.pair_list_info()["overflow"] > 0
-    # r == h accepted, one ulp beyond rejected — also through the FP32 pre-test, far from the origin
+    # r == h accepted, one ulp beyond rejected — also through the integer pre-test, far from the origin
     off = 2000.0
     x = [[off, 0.0, 0.0], [off + 1.0, 0.0, 0.0], [off, np.nextafter(1.0, 2.0), 0.0],
          [off - 0.6, 0.8, 0.0], [off + 0.3, -0.4, 0.0]]
@@ -149,6 +151,58 @@ def test_random_cloud_matches_oracle_pairs_through_the_list(gpu):
     s.create_cell_list()
     s.count_pairs(True)
     pio, _ = o.pairs()
+    for _ in range(2):
+        for op in ("wcsph.reset_density", "wcsph.compute_density"):
+            o.apply(op)
+            s.apply(op)
+        assert s.pair_count() == len(pio)
+        assert n_mismatch(s.field("rho"), o.field("rho")) == 0
+
+
+@pytest.mark.parametrize("flags", [EAGER, EAGER | NO_PRETEST])
+def test_wrapped_cells_of_a_narrow_grid(gpu, flags):
+    """quirk 5 (no per-axis bounds check, core.jl:98): on a grid two cells wide the linear key
+    arithmetic reaches wrapped cells whose particles CAN be within h; the recording pass must
+    find them too (they take the exact test instead of the cell-relative integer one)"""
+    rng = np.random.default_rng(9)
+    n = 60
+    x = np.zeros((n, 3))
+    x[:, 0] = rng.uniform(0.0, 1.9, n)
+    x[:, 1] = rng.uniform(0.0, 4.9, n)
+    case = tiny_case(x, box=((0.0, 0.0, 0.0), (1.95, 4.95, 0.0)), m=rng.uniform(0.5, 1.5, n))
+    o, s = load_oracle(case), load_gpu(case, capacity=128, flags=flags)
+    o.create_cell_list()
+    s.create_cell_list()
+    s.count_pairs(True)
+    pio, _ = o.pairs()
+    for _ in range(2):
+        for op in ("wcsph.reset_density", "wcsph.compute_density"):
+            o.apply(op)
+            s.apply(op)
+        assert s.pair_count() == len(pio)
+        assert n_mismatch(s.field("rho"), o.field("rho")) == 0
+
+
+def test_cutoff_boundary_in_3d_across_cell_faces(gpu):
+    """pairs exactly at r == h (accepted) and one ulp beyond (rejected) whose partners sit in
+    different cells along every axis, far from the origin and at negative coordinates"""
+    base = np.array([-37.25, 11.5, -3.75])
+    dirs = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [0.6, 0.8, 0.0], [0.0, -0.6, 0.8], [-0.8, 0.0, 0.6],
+                     [1 / 3, 2 / 3, 2 / 3], [-2 / 3, 1 / 3, -2 / 3]])
+    pts = [base]
+    for dvec in dirs:
+        pts.append(base + dvec)                                   # r == h up to rounding
+        pts.append(base + dvec * np.nextafter(1.0, 2.0) * (1 + 1e-12))  # just outside
+        pts.append(base + dvec * (1 - 1e-12))                     # just inside
+    x = np.array(pts)
+    n = len(x)
+    case = tiny_case(x, box=((-40.0, -3.0, -8.0), (3.0, 15.0, 3.0)), m=np.arange(1.0, n + 1.0))
+    assert case.dim == 3
+    o, s = load_oracle(case), load_gpu(case, capacity=64, flags=EAGER)
+    assert o.create_cell_list() == s.create_cell_list() == n
+    s.count_pairs(True)
+    pio, pjo = o.pairs()
+    assert len(pio) > 2 * len(dirs)
     for _ in range(2):
         for op in ("wcsph.reset_density", "wcsph.compute_density"):
             o.apply(op)
