@@ -750,6 +750,39 @@ extern "C" int sphmw_pair_list_info(sphmw_ctx *c, int64_t out[4]) {
     CUDA_TRY(cudaSetDevice(c->device));
     return sphmw_pair_list_stats(c, out);
 }
+// ---- host-only test hooks (no device, no context) --------------------------------------
+extern "C" int sphmw_pretest_pairs(const double *xp, const double *xq, int64_t n, double h, int32_t dim,
+                                   uint8_t *pass) {
+    if (!xp || !xq || !pass || !(h > 0.0) || (dim != 2 && dim != 3)) return SPHMW_E_INVALID;
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t wp = 0, wq = 0;
+        int dc[3] = {0, 0, 0};
+        bool neighbour = true;
+        for (int a = 0; a < dim; ++a) {
+            const double p = xp[3 * i + a], q = xq[3 * i + a];
+            wp |= nl_q10_axis(p, h) << (10 * a);
+            wq |= nl_q10_axis(q, h) << (10 * a);
+            const double d = floor(q / h) - floor(p / h);
+            if (!(fabs(d) <= 1.0)) neighbour = false;
+            dc[a] = (int)d;
+        }
+        pass[i] = !neighbour ? 2 : (nl_q10_pass(wp, wq, dc[0], dc[1], dc[2], dim) ? 1 : 0);
+    }
+    return SPHMW_OK;
+}
+extern "C" int sphmw_slab_column_sets(int32_t width, int32_t has_left, int32_t has_right, int32_t out[16]) {
+    if (!out || width < 2 * GHOST_COLS + 2 * GHOST_COLS) return SPHMW_E_INVALID;
+    const SlabCols sc = sphmw_slab_cols_of(width, has_left != 0, has_right != 0);
+    const ColFilter *f[4] = {&sc.edge, &sc.interior, &sc.force_edge, &sc.force_interior};
+    for (int k = 0; k < 4; ++k) {
+        out[4 * k + 0] = f[k]->a0;
+        out[4 * k + 1] = f[k]->a1;
+        out[4 * k + 2] = f[k]->b0;
+        out[4 * k + 3] = f[k]->b1;
+    }
+    return SPHMW_OK;
+}
+
 extern "C" int sphmw_count_pairs(sphmw_ctx *c, int32_t enable) {
     if (!c) return SPHMW_E_INVALID;
     c->count_pairs = enable != 0;

@@ -57,7 +57,12 @@ __global__ void k_keys(const double *__restrict__ x0, const double *__restrict__
             cellx[pos] = ci;
         }
         unsigned m = __ballot_sync(0xffffffffu, dead);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&removed[0], (uint32_t)__popc(m));
+        // removed[1]: the owned particles that stay — the rank's share of the global count
+        unsigned mo = __ballot_sync(0xffffffffu, live && !dead && tag[pos] == TAG_OWNED);
+        if ((threadIdx.x & 31) == 0) {
+            if (m) atomicAdd(&removed[0], (uint32_t)__popc(m));
+            if (mo) atomicAdd(&removed[1], (uint32_t)__popc(mo));
+        }
         return;
     }
     if (pos >= n) return;
@@ -260,12 +265,7 @@ __global__ void k_gather(GatherList gl, const uint32_t *__restrict__ src,
 #pragma unroll
         for (int a = 0; a < 3; ++a)
             if (f == gl.xpos[a]) {
-                // the cell index is floor(x / h) (structs.jl:99, k_keys); what is left of x / h
-                const double t = v / gl.h;
-                const double fr = t - floor(t);  // exact, in [0, 1)
-                int q = (int)(fr * (double)NL_Q10_ONE);
-                q = q < 0 ? 0 : (q > NL_Q10_ONE - 1 ? NL_Q10_ONE - 1 : q);
-                qm |= (uint32_t)q << (10 * a);
+                qm |= nl_q10_axis(v, gl.h) << (10 * a);
             }
     }
     gl.xq[slot] = qm;
@@ -316,6 +316,7 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     if (n == 0) {
         CUDA_TRY(cudaMemsetAsync(c->cell_start, 0, sizeof(uint32_t) * (ncells + 2), c->stream));
         c->cell_list_valid = true;
+        c->n_owned = 0;
         if (n_alive) *n_alive = 0;
         return SPHMW_OK;
     }
@@ -330,7 +331,7 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
         CUDA_TRY(cudaMalloc(&c->scan_tmp, sizeof(uint32_t) * c->scan_tmp_len));
     }
 
-    CUDA_TRY(cudaMemsetAsync(c->removed, 0, sizeof(uint32_t), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->removed, 0, sizeof(uint32_t) * 2, c->stream));
     {
         TIMED(c, "cell_keys");
         const bool slab = c->slab_lo >= 0;
@@ -343,7 +344,7 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
         else k_keys<3, true><<<gr, 256, 0, c->stream>>>(KEYS_ARGS);
 #undef KEYS_ARGS
     }
-    CUDA_TRY(cudaMemcpyAsync(c->h_removed, c->removed, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+    CUDA_TRY(cudaMemcpyAsync(c->h_removed, c->removed, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost,
                              c->stream));
     // overlap the host round trip with the histogram
     CUDA_TRY(cudaMemsetAsync(c->cell_start, 0, sizeof(uint32_t) * (ncells + 2), c->stream));
@@ -358,6 +359,7 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     const int64_t k = c->h_removed[0];
+    const uint32_t owned_live = c->h_removed[1];  // slab mode only (else the first removed index)
     if (k > 0 && c->slab_lo < 0) {
         if (k > c->removed_cap) {
             sphmw_set_error("more than %lld particles left the domain in one step",
@@ -422,7 +424,7 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     std::swap(c->tag, c->tag_alt);
     std::swap(c->cellx, c->cellx_alt);
     c->n = n_new;
-    if (c->slab_lo < 0) c->n_owned = n_new;
+    c->n_owned = c->slab_lo < 0 ? n_new : (int64_t)owned_live;
     c->cell_list_valid = true;
     if (n_alive) *n_alive = n_new;
     return SPHMW_OK;

@@ -1782,8 +1782,12 @@ static ColFilter cols_range(int a0, int a1, int b0, int b1) {
 }
 
 SlabCols sphmw_slab_cols(const sphmw_ctx *c) {
-    const int W = (int)c->grid.lim[0], G = GHOST_COLS;
-    const bool hl = c->slab_lo > 0, hr = c->slab_hi < c->global_cols;
+    return sphmw_slab_cols_of((int)c->grid.lim[0], c->slab_lo > 0, c->slab_hi < c->global_cols);
+}
+
+// W: local columns including the GHOST_COLS ghost columns per side; hl/hr: a neighbour exists
+SlabCols sphmw_slab_cols_of(int W, bool hl, bool hr) {
+    const int G = GHOST_COLS;
     const int il = hl ? G + 3 : 0;                     // first interior column
     const int ir = hr ? W - G - 4 : W - 1;             // last interior column
     const int er = hr ? (ir + 1 > il ? ir + 1 : il) : W;  // first column of the right edge set

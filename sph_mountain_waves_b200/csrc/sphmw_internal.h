@@ -1,6 +1,7 @@
 // Internal declarations of libsphmw (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include <string>
@@ -149,6 +150,30 @@ __host__ __device__ __forceinline__ bool col_selected(const ColFilter &cf, int i
 // sum d_a^2 < (1024 + sqrt(3))^2.  1.74 > sqrt(3) leaves room for the rounding of x/h (1e-13).
 #define NL_Q10_ONE 1024
 #define NL_Q10_R2MAX 1052142  // floor((1024 + 1.74)^2)
+#ifdef __CUDACC__
+#define NL_HD __host__ __device__ __forceinline__
+#else
+#define NL_HD static inline
+#endif
+// one axis: where x sits inside its cell floor(x / h) (structs.jl:99, k_keys), in h/1024
+NL_HD uint32_t nl_q10_axis(double x, double h) {
+    const double t = x / h;
+    const double fr = t - floor(t);  // exact, in [0, 1)
+    int q = (int)(fr * (double)NL_Q10_ONE);
+    q = q < 0 ? 0 : (q > NL_Q10_ONE - 1 ? NL_Q10_ONE - 1 : q);
+    return (uint32_t)q;
+}
+// the pre-test itself: own = mirror word of p, (di, dj, dk) = cell of q minus cell of p
+NL_HD bool nl_q10_pass(uint32_t own, uint32_t other, int di, int dj, int dk, int dim) {
+    const int dx = (int)(own & 1023u) - NL_Q10_ONE * di - (int)(other & 1023u);
+    const int dy = (int)((own >> 10) & 1023u) - NL_Q10_ONE * dj - (int)((other >> 10) & 1023u);
+    int s2 = dx * dx + dy * dy;
+    if (dim == 3) {
+        const int dz = (int)(own >> 20) - NL_Q10_ONE * dk - (int)(other >> 20);
+        s2 += dz * dz;
+    }
+    return !(s2 > NL_Q10_R2MAX);
+}
 struct PairList {
     uint32_t *list;
     uint32_t *cnt;
@@ -284,6 +309,7 @@ struct SlabCols {
     ColFilter force_edge, force_interior;  // their owned parts (the force pass covers owned columns only)
 };
 SlabCols sphmw_slab_cols(const sphmw_ctx *c);
+SlabCols sphmw_slab_cols_of(int W, bool has_left, bool has_right);
 // implemented in cell_list.cu
 int sphmw_exclusive_scan_u32(sphmw_ctx *c, uint32_t *data, int64_t n);
 // implemented in frame_io.cpp
