@@ -13,7 +13,11 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sphmw_internal.h"
@@ -22,27 +26,68 @@ namespace {
 
 const size_t BLOCK = 1u << 15;  // vtkZLibDataCompressor default block size (32 KiB)
 
-// one appended array: UInt64 header + compressed blocks
-void append_compressed(std::string &out, const void *data, size_t nbytes) {
+// one appended array: UInt64 header + compressed blocks.  The blocks are independent zlib
+// streams, so they are compressed by a few host threads (a 64 M-particle frame is ~6 GB of
+// doubles; one thread at zlib level 1 would take a minute).  SPHMW_IO_THREADS overrides.
+struct AppendedArray {
+    std::vector<uint64_t> header;      // [nblocks, blocksize, lastblocksize, csize...]
+    std::vector<std::string> parts;    // compressed blocks, one string per thread, in order
+    size_t bytes() const {
+        size_t b = header.size() * sizeof(uint64_t);
+        for (const std::string &p : parts) b += p.size();
+        return b;
+    }
+};
+
+unsigned io_threads(size_t nblocks) {
+    unsigned t = std::thread::hardware_concurrency();
+    if (const char *e = getenv("SPHMW_IO_THREADS")) t = (unsigned)atoi(e);
+    if (t < 1) t = 1;
+    if (t > 64) t = 64;
+    const size_t by_work = nblocks / 64 + 1;  // at least ~2 MB of input per thread
+    return (unsigned)std::min<size_t>(t, by_work);
+}
+
+AppendedArray compress_array(const void *data, size_t nbytes) {
     const unsigned char *src = (const unsigned char *)data;
-    size_t nblocks = nbytes == 0 ? 0 : (nbytes + BLOCK - 1) / BLOCK;
+    const size_t nblocks = nbytes == 0 ? 0 : (nbytes + BLOCK - 1) / BLOCK;
     size_t last = nbytes == 0 ? 0 : nbytes - (nblocks - 1) * BLOCK;
     if (last == BLOCK) last = 0;  // VTK convention: 0 means "last block is full"
-    std::vector<uint64_t> header(3 + nblocks);
-    header[0] = nblocks;
-    header[1] = BLOCK;
-    header[2] = last;
-    std::string body;
-    std::vector<unsigned char> buf(compressBound(BLOCK));
-    for (size_t b = 0; b < nblocks; ++b) {
-        size_t len = std::min(BLOCK, nbytes - b * BLOCK);
-        uLongf clen = buf.size();
-        compress2(buf.data(), &clen, src + b * BLOCK, len, 1);
-        header[3 + b] = clen;
-        body.append((const char *)buf.data(), clen);
+    AppendedArray a;
+    a.header.resize(3 + nblocks);
+    a.header[0] = nblocks;
+    a.header[1] = BLOCK;
+    a.header[2] = last;
+    const unsigned nt = io_threads(nblocks);
+    a.parts.resize(nt);
+    auto work = [&](unsigned t) {
+        const size_t b0 = nblocks * t / nt, b1 = nblocks * (t + 1) / nt;
+        std::vector<unsigned char> buf(compressBound(BLOCK));
+        std::string &out = a.parts[t];
+        out.reserve((b1 - b0) * BLOCK / 2);
+        for (size_t b = b0; b < b1; ++b) {
+            const size_t len = std::min(BLOCK, nbytes - b * BLOCK);
+            uLongf clen = buf.size();
+            compress2(buf.data(), &clen, src + b * BLOCK, len, 1);
+            a.header[3 + b] = clen;
+            out.append((const char *)buf.data(), clen);
+        }
+    };
+    if (nt <= 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; ++t) pool.emplace_back(work, t);
+        for (std::thread &th : pool) th.join();
     }
-    out.append((const char *)header.data(), header.size() * sizeof(uint64_t));
-    out.append(body);
+    return a;
+}
+
+bool write_array(FILE *fp, const AppendedArray &a) {
+    if (fwrite(a.header.data(), sizeof(uint64_t), a.header.size(), fp) != a.header.size()) return false;
+    for (const std::string &p : a.parts)
+        if (!p.empty() && fwrite(p.data(), 1, p.size(), fp) != p.size()) return false;
+    return true;
 }
 
 int mkpath(const std::string &path) {
@@ -62,22 +107,24 @@ int mkpath(const std::string &path) {
 // data[f]: ncomps[f] x N column-major, i.e. interleaved per point (IO.jl:62-68)
 int sphmw_write_vtp(const char *path, int64_t n, const double *points3n, int nfields,
                     const char *const *names, const int *ncomps, const double *const *data) {
-    std::string appended;
-    std::vector<size_t> offsets;
-    offsets.push_back(appended.size());
-    append_compressed(appended, points3n, sizeof(double) * 3 * (size_t)n);
-    std::vector<int64_t> conn((size_t)n), offs((size_t)n);
-    for (int64_t i = 0; i < n; ++i) {
-        conn[i] = i;
-        offs[i] = i + 1;
+    std::vector<AppendedArray> arrays;
+    arrays.push_back(compress_array(points3n, sizeof(double) * 3 * (size_t)n));
+    {
+        std::vector<int64_t> conn((size_t)n), offs((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            conn[i] = i;
+            offs[i] = i + 1;
+        }
+        arrays.push_back(compress_array(conn.data(), sizeof(int64_t) * (size_t)n));
+        arrays.push_back(compress_array(offs.data(), sizeof(int64_t) * (size_t)n));
     }
-    offsets.push_back(appended.size());
-    append_compressed(appended, conn.data(), sizeof(int64_t) * (size_t)n);
-    offsets.push_back(appended.size());
-    append_compressed(appended, offs.data(), sizeof(int64_t) * (size_t)n);
-    for (int f = 0; f < nfields; ++f) {
-        offsets.push_back(appended.size());
-        append_compressed(appended, data[f], sizeof(double) * (size_t)ncomps[f] * (size_t)n);
+    for (int f = 0; f < nfields; ++f)
+        arrays.push_back(compress_array(data[f], sizeof(double) * (size_t)ncomps[f] * (size_t)n));
+    std::vector<size_t> offsets;
+    size_t running = 0;
+    for (const AppendedArray &a : arrays) {
+        offsets.push_back(running);
+        running += a.bytes();
     }
 
     FILE *fp = fopen(path, "wb");
@@ -118,9 +165,10 @@ int sphmw_write_vtp(const char *path, int64_t n, const double *points3n, int nfi
     fprintf(fp, "    </Piece>\n");
     fprintf(fp, "  </PolyData>\n");
     fprintf(fp, "  <AppendedData encoding=\"raw\">\n_");
-    fwrite(appended.data(), 1, appended.size(), fp);
+    bool ok = true;
+    for (const AppendedArray &a : arrays) ok = ok && write_array(fp, a);
     fprintf(fp, "\n  </AppendedData>\n</VTKFile>\n");
-    if (fclose(fp) != 0) {
+    if (fclose(fp) != 0 || !ok) {
         sphmw_set_error("write to %s failed", path);
         return SPHMW_E_IO;
     }

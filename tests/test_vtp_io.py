@@ -53,3 +53,21 @@ def test_reader_errors(tmp_path):
     bad.write_text("<VTKFile type=\"PolyData\"><Piece NumberOfPoints=\"1\"></Piece></VTKFile>")
     with pytest.raises(SphmwError):
         read_vtp(str(bad))
+
+
+def test_threaded_compression_writes_the_same_bytes(tmp_path, monkeypatch):
+    """the zlib blocks of a large frame are compressed by several host threads; the file must
+    not depend on how many (blocks are independent streams, written in order)"""
+    rng = np.random.default_rng(7)
+    n = 300_000
+    pts = rng.normal(size=(n, 3)).round(3)
+    fields = {"ρ": rng.normal(size=n).round(2), "v": rng.normal(size=(n, 3))}
+    blobs = []
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("SPHMW_IO_THREADS", threads)
+        path = tmp_path / f"frame_t{threads}.vtp"
+        write_vtp(str(path), pts, fields)
+        blobs.append(path.read_bytes())
+    assert blobs[0] == blobs[1] == blobs[2]
+    d = read_vtp(str(tmp_path / "frame_t8.vtp"))
+    assert np.array_equal(d["Points"], pts) and np.array_equal(d["v"], fields["v"])
