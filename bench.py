@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--cpu-sample", default="bell_hill_3d_1M")
     ap.add_argument("--flags", type=int, default=1,
                     help="SPHMW_FLAG_*: 0 strict (bit-identical sums), 1 FAST_MATH (default), 2 CELL_PAIRS, "
-                         "+4 NO_PAIR_LIST (walk the cells in every pass), +16 NO_PRETEST")
+                         "+4 NO_PAIR_LIST (walk the cells in every pass), +16 NO_PRETEST, +32 PACKED_RECORDS (experimental)")
     return ap.parse_args()
 
 

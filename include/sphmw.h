@@ -80,6 +80,10 @@ typedef struct sphmw_config {
 #define SPHMW_FLAG_NO_PAIR_LIST 4
 #define SPHMW_FLAG_PAIR_LIST_EAGER 8
 #define SPHMW_FLAG_NO_PRETEST 16
+/* Fused "wcsph" step only, experimental (default off): the replaying passes read their
+ * neighbours from three packed 32-byte records with 256-bit loads instead of eleven 8-byte
+ * gathers (+96 B per particle; same bits).  Ignored together with NO_PAIR_LIST / CELL_PAIRS. */
+#define SPHMW_FLAG_PACKED_RECORDS 32
 
 int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out);
 int sphmw_destroy(sphmw_ctx *ctx);

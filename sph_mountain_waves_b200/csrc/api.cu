@@ -401,6 +401,7 @@ extern "C" int sphmw_destroy(sphmw_ctx *c) {
     cudaFree(c->mv_old); cudaFree(c->mv_new);
     cudaFree(c->d_counters); cudaFree(c->staging); cudaFree(c->reduce_tmp);
     cudaFree(c->xq); cudaFree(c->pl.list); cudaFree(c->pl.cnt);
+    for (int k = 0; k < 3; ++k) cudaFree(c->rec[k]);
     if (c->h_removed) cudaFreeHost(c->h_removed);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto &t : c->timing_pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -452,6 +453,15 @@ __global__ void k_iota(uint32_t *a, uint32_t *b, uint32_t *tag, int64_t first, i
         if (b) b[i] = (uint32_t)i;
         tag[i] = TAG_OWNED;
     }
+}
+
+int sphmw_ensure_records(sphmw_ctx *c) {
+    for (int k = 0; k < 3; ++k)
+        if (!c->rec[k]) {
+            CUDA_TRY(cudaMalloc(&c->rec[k], sizeof(NbRec) * (size_t)c->cap));
+            CUDA_TRY(cudaMemsetAsync(c->rec[k], 0, sizeof(NbRec) * (size_t)c->cap, c->stream));
+        }
+    return SPHMW_OK;
 }
 
 int sphmw_ensure_slot(sphmw_ctx *c, int slot) {

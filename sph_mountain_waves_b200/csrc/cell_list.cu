@@ -241,6 +241,9 @@ struct GatherList {
     int xpos[3];  // entry of x0/x1/x2 in the lists above (-1: no such component)
     double h;
     uint32_t *xq;
+    // packed neighbour record A {x, y, z, m} (SPHMW_FLAG_PACKED_RECORDS; null otherwise)
+    int mpos;
+    NbRec *recA;
 };
 
 __global__ void k_gather(GatherList gl, const uint32_t *__restrict__ src,
@@ -259,16 +262,20 @@ __global__ void k_gather(GatherList gl, const uint32_t *__restrict__ src,
     tag_out[slot] = tag[s];
     cellx_out[slot] = cellx[s];
     uint32_t qm = 0;
+    double ra[4] = {0.0, 0.0, 0.0, 0.0};
     for (int f = 0; f < gl.count; ++f) {
         const double v = gl.from[f][s];
         gl.to[f][slot] = v;
+        if (f == gl.mpos) ra[3] = v;
 #pragma unroll
         for (int a = 0; a < 3; ++a)
             if (f == gl.xpos[a]) {
+                ra[a] = v;
                 qm |= nl_q10_axis(v, gl.h) << (10 * a);
             }
     }
     gl.xq[slot] = qm;
+    if (gl.recA) nb_store(gl.recA + slot, ra[0], ra[1], ra[2], ra[3]);
 }
 
 __global__ void k_renumber(uint32_t *__restrict__ idx, const uint32_t *__restrict__ pos_of_idx,
@@ -403,12 +410,20 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     gl.xq = c->xq;
     gl.h = g.h;
     for (int a = 0; a < 3; ++a) gl.xpos[a] = -1;
+    gl.mpos = -1;
+    gl.recA = nullptr;
+    if ((c->flags & SPHMW_FLAG_PACKED_RECORDS) && c->allocated[S_M] && !c->stale[S_M]) {
+        TRY(sphmw_ensure_records(c));
+        gl.recA = c->rec[0];
+        c->rec_gen = c->cell_gen;
+    }
     for (int s = 0; s < NSLOT; ++s)
         if (c->allocated[s] && !c->stale[s]) {
             gl.from[gl.count] = c->cur.s[s];
             gl.to[gl.count] = c->alt.s[s];
             gathered[gl.count] = s;
             if (s >= S_X0 && s <= S_X2) gl.xpos[s - S_X0] = gl.count;
+            if (s == S_M) gl.mpos = gl.count;
             ++gl.count;
         }
     if (n_new > 0) {

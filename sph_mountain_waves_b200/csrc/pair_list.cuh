@@ -63,6 +63,48 @@ __device__ __forceinline__ void nl_entry(Op &op, const Fields &f, const Params &
     ++accepted;
 }
 
+// ---- packed-record variants (SPHMW_FLAG_PACKED_RECORDS; NbRec in sphmw_internal.h) ----------
+// density closure: position and mass of q from record A
+template <int DIM, class Op>
+__device__ __forceinline__ void nl_entry_rec_density(Op &op, const Params &prm, const Grid &g, int64_t p,
+                                                     uint32_t q, double px, double py, double pz,
+                                                     const NbRec *__restrict__ recA, unsigned &accepted) {
+    const NbRec A = nb_load(recA + q);
+    double dx = px - A.a;
+    double dy = py - A.b;
+    double dz = 0.0;
+    double r2 = dx * dx + dy * dy;
+    if (DIM == 3) {
+        dz = pz - A.c;
+        r2 = r2 + dz * dz;
+    }
+    if ((r2 > g.r2_max) || (q == (uint32_t)p)) return;
+    double r = sqrt(r2);
+    op.template pair_m<DIM>(prm, A.d, dx, dy, dz, r);
+    ++accepted;
+}
+// force closure: all three records are requested up front (the exact test rejects few entries)
+template <int DIM, class Op>
+__device__ __forceinline__ void nl_entry_rec_force(Op &op, const Params &prm, const Grid &g, int64_t p,
+                                                   uint32_t q, double px, double py, double pz,
+                                                   const PairList &pl, unsigned &accepted) {
+    const NbRec A = nb_load(pl.recA + q);
+    const NbRec B = nb_load(pl.recB + q);
+    const NbRec C = nb_load(pl.recC + q);
+    double dx = px - A.a;
+    double dy = py - A.b;
+    double dz = 0.0;
+    double r2 = dx * dx + dy * dy;
+    if (DIM == 3) {
+        dz = pz - A.c;
+        r2 = r2 + dz * dz;
+    }
+    if ((r2 > g.r2_max) || (q == (uint32_t)p)) return;
+    double r = sqrt(r2);
+    op.template pair_rec<DIM>(prm, A.d, B, C, dx, dy, dz, r);
+    ++accepted;
+}
+
 // per-thread queue column in shared memory, addressed with 32-bit shared-window addresses so
 // that a push is one predicated st.shared and one predicated add (the queue is touched only
 // through these volatile statements, which keep their order).  Room for a whole cell run is
@@ -102,7 +144,9 @@ __device__ __forceinline__ void nl_count_pairs(unsigned long long *pair_counter,
 // profiles/r01b_pair_list.md.
 #define NL_FILTER_F64 0
 #define NL_FILTER_Q10 2
-template <int DIM, class Op, int FILTER>
+// REC (fused density pass only): phase 2 reads q from record A, and the particle's own records B
+// and C are written once its density, smoothing length and pressure are final
+template <int DIM, class Op, int FILTER, bool REC = false>
 __global__ void __launch_bounds__(NL_BLOCK)
 k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
                const uint32_t *__restrict__ cellx, const uint32_t *__restrict__ cell_start, int64_t n,
@@ -208,7 +252,9 @@ k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restr
         for (unsigned a = qbase; a < qtop; a += NL_BLOCK * 4u, row += 32) {
             const uint32_t q = nl_peek(a);
             __stcs(row, q);
-            nl_entry<DIM>(op, f, prm, g, p, q, px, py, pz, accepted);
+            if constexpr (REC && Op::REC_KIND == 1)
+                nl_entry_rec_density<DIM>(op, prm, g, p, q, px, py, pz, pl.recA, accepted);
+            else nl_entry<DIM>(op, f, prm, g, p, q, px, py, pz, accepted);
         }
         pl.cnt[p] = (qtop - qbase) / (NL_BLOCK * 4u);
     } else {
@@ -218,10 +264,18 @@ k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restr
     }
     if (self) op.template pair<DIM>(f, prm, p, p, 0.0, 0.0, 0.0, 0.0);  // core.jl:155-157
     op.template finish<DIM>(f, out, prm, p);
+    if constexpr (REC && Op::REC_KIND == 1) {
+        // what finish() just stored for p (same thread: reads see its own writes), as records
+        nb_store(pl.recB + p, f.s[S_V0][p], f.s[S_V1][p], DIM == 3 ? f.s[S_V2][p] : 0.0, f.s[S_H][p]);
+        const double rho = f.s[S_RHO][p];
+        const double rfl = (rho != rho) ? rho : (rho < prm.rho_floor ? prm.rho_floor : rho);  // jl_max
+        nb_store(pl.recC + p, f.s[S_PR2][p], rfl, f.s[S_CS][p], 0.0);
+    }
     nl_count_pairs(pair_counter, accepted);
 }
 
-template <int DIM, class Op>
+// REC (fused force pass only): entries are evaluated from the packed records
+template <int DIM, class Op, bool REC = false>
 __global__ void __launch_bounds__(NL_BLOCK)
 k_binary_list(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
               const uint32_t *__restrict__ cellx, const uint32_t *__restrict__ cell_start, int64_t n,
@@ -246,7 +300,9 @@ k_binary_list(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restri
         for (uint32_t k = 0; k < cnt; ++k) {
             const uint32_t q = qn;
             if (k + 1 < cnt) qn = __ldcs(row + (size_t)(k + 1) * 32);  // one entry ahead
-            nl_entry<DIM>(op, f, prm, g, p, q, px, py, pz, accepted);
+            if constexpr (REC && Op::REC_KIND == 2)
+                nl_entry_rec_force<DIM>(op, prm, g, p, q, px, py, pz, pl, accepted);
+            else nl_entry<DIM>(op, f, prm, g, p, q, px, py, pz, accepted);
         }
     } else {
         nl_walk<DIM>(op, f, prm, g, home, p, px, py, pz, cell_start, accepted);

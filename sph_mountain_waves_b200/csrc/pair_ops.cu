@@ -406,6 +406,9 @@ __global__ void __launch_bounds__(256) k_unary(Fields f, Params c, int64_t n) {
 struct PairOpBase {
     template <int DIM>
     static __device__ void skip(const Fields &, const Fields &, int64_t) {}
+    // packed neighbour records (pair_list.cuh): 0 the operator does not use them, 1 it has
+    // pair_m (needs record A), 2 it has pair_rec (needs A, B, C)
+    static constexpr int REC_KIND = 0;
 };
 
 // compute_density!  wcsph_perturbed_witch.jl:226-228
@@ -862,6 +865,7 @@ struct B_pack_momentum : PairOpBase {
 // compute_pressure!  (wcsph_perturbed_witch.jl:316-323) in one pass, plus the
 // per-particle invariants of the pair force.
 struct B_wcsph_density_fused : PairOpBase {
+    static constexpr int REC_KIND = 1;
     double rho, hp;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &, int64_t p) {
@@ -872,6 +876,11 @@ struct B_wcsph_density_fused : PairOpBase {
     __device__ void pair(const Fields &f, const Params &, int64_t, int64_t q, double, double,
                          double, double r) {
         rho += QF(S_M) * sph_W<DIM>(hp, r);
+    }
+    // the same with the neighbour's mass out of its packed record (SPHMW_FLAG_PACKED_RECORDS)
+    template <int DIM>
+    __device__ void pair_m(const Params &, double qm, double, double, double, double r) {
+        rho += qm * sph_W<DIM>(hp, r);
     }
     template <int DIM>
     __device__ void finish(const Fields &f, const Fields &, const Params &c, int64_t p) {
@@ -900,6 +909,7 @@ struct B_wcsph_density_fused : PairOpBase {
 // Dv starts at 0 (accelerate! zeroed it) and is never stored; the new velocity
 // goes to the `out` field set because other threads still read the old one.
 struct B_wcsph_momentum_fused : PairOpBase {
+    static constexpr int REC_KIND = 2;
     double dv0, dv1, dv2, v0, v1, v2, hp, prho, pr2, cs;
     // the velocity is double-buffered: a skipped (ghost) particle carries its value over
     template <int DIM>
@@ -947,6 +957,35 @@ struct B_wcsph_momentum_fused : PairOpBase {
             if (DIM == 3) dv2 += fv * dz;
         }
     }
+    // the same with the neighbour's fields out of its packed records: qm = A.d,
+    // B = {vx, vy, vz, h}, C = {P'/rho^2, max(rho, rho_floor), c_s}
+    template <int DIM>
+    __device__ void pair_rec(const Params &c, double qm, const NbRec &B, const NbRec &C, double dx, double dy,
+                             double dz, double r) {
+        double vx = v0 - B.a, vy = v1 - B.b;
+        double dot_product = dx * vx + dy * vy;
+        if (DIM == 3) {
+            double vz = v2 - B.c;
+            dot_product = dot_product + dz * vz;
+        }
+        double h_ij = 0.5 * (hp + B.d);
+        double ker = sph_rDW<DIM>(h_ij, r);
+        double fc = -qm * (pr2 + C.a) * ker;
+        dv0 += fc * dx;
+        dv1 += fc * dy;
+        if (DIM == 3) dv2 += fc * dz;
+        if (dot_product < 0.0) {
+            double qrho = C.b;
+            double c_ij = 0.5 * (cs + C.c);
+            double rho_ij = 0.5 * (prho + qrho);
+            double mu_ij = (h_ij * dot_product) / (r * r + c.eps * h_ij * h_ij);
+            double pi_ij = (-c.alpha * c_ij * mu_ij + c.beta * mu_ij * mu_ij) / rho_ij;
+            double fv = -qm * pi_ij * ker;
+            dv0 += fv * dx;
+            dv1 += fv * dy;
+            if (DIM == 3) dv2 += fv * dz;
+        }
+    }
     template <int DIM>
     __device__ void finish(const Fields &f, const Fields &out, const Params &c, int64_t p) {
         double n0 = v0, n1 = v1, n2 = v2;
@@ -981,6 +1020,7 @@ __device__ __forceinline__ double fast_sqrt_pos(double a) {
 }
 
 struct B_wcsph_density_fast : PairOpBase {
+    static constexpr int REC_KIND = 1;
     double rho, hp, inv_h, cw;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &, int64_t p) {
@@ -1001,6 +1041,17 @@ struct B_wcsph_density_fast : PairOpBase {
         double t2 = t * t;
         double w = cw * (t2 * t2) * fma(4.0, x, 1.0);
         rho = fma(QF(S_M), w, rho);
+    }
+    template <int DIM>
+    __device__ void pair_m(const Params &, double qm, double dx, double dy, double dz, double) {
+        double r2 = fma(dx, dx, dy * dy);
+        if (DIM == 3) r2 = fma(dz, dz, r2);
+        double x = fast_sqrt_pos(r2) * inv_h;
+        if (x > 1.0) return;
+        double t = 1.0 - x;
+        double t2 = t * t;
+        double w = cw * (t2 * t2) * fma(4.0, x, 1.0);
+        rho = fma(qm, w, rho);
     }
     template <int DIM>
     __device__ void finish(const Fields &f, const Fields &, const Params &c, int64_t p) {
@@ -1026,6 +1077,7 @@ struct B_wcsph_density_fast : PairOpBase {
 };
 
 struct B_wcsph_momentum_fast : PairOpBase {
+    static constexpr int REC_KIND = 2;
     double dv0, dv1, dv2, v0, v1, v2, hp, prho, pr2, cs;
     template <int DIM>
     static __device__ void skip(const Fields &f, const Fields &out, int64_t p) {
@@ -1070,6 +1122,40 @@ struct B_wcsph_momentum_fast : PairOpBase {
             double c_ij = 0.5 * (cs + QF(S_CS));
             double rho_ij = 0.5 * (prho + qrho);
             // mu = h dot / D,  pi = (-alpha c mu + beta mu^2) / rho_ij, with one reciprocal
+            double D = fma(c.eps * h_ij, h_ij, r2);
+            double R = 1.0 / (D * rho_ij);
+            double hd = h_ij * dot_product;
+            double mu = hd * rho_ij * R;
+            double pi_ij = hd * R * fma(c.beta, mu, -c.alpha * c_ij);
+            fc = fma(-qm * pi_ij, ker, fc);
+        }
+        dv0 = fma(fc, dx, dv0);
+        dv1 = fma(fc, dy, dv1);
+        if (DIM == 3) dv2 = fma(fc, dz, dv2);
+    }
+    template <int DIM>
+    __device__ void pair_rec(const Params &c, double qm, const NbRec &B, const NbRec &C, double dx, double dy,
+                             double dz, double) {
+        double r2 = fma(dx, dx, dy * dy);
+        double dot_product = fma(dy, v1 - B.b, dx * (v0 - B.a));
+        if (DIM == 3) {
+            r2 = fma(dz, dz, r2);
+            dot_product = fma(dz, v2 - B.c, dot_product);
+        }
+        double h_ij = 0.5 * (hp + B.d);
+        double inv_h = 1.0 / h_ij;
+        double x = fast_sqrt_pos(r2) * inv_h;
+        if (x > 1.0) return;
+        double t = 1.0 - x;
+        double ih2 = inv_h * inv_h;
+        double ih4 = ih2 * ih2;
+        double ker = DIM == 2 ? -44.563384065730695 * (t * t * t) * ih4
+                              : -66.84507609859604 * (t * t * t) * (ih4 * inv_h);
+        double fc = -qm * (pr2 + C.a) * ker;
+        if (dot_product < 0.0) {
+            double qrho = C.b;
+            double c_ij = 0.5 * (cs + C.c);
+            double rho_ij = 0.5 * (prho + qrho);
             double D = fma(c.eps * h_ij, h_ij, r2);
             double R = 1.0 / (D * rho_ij);
             double hd = h_ij * dot_product;
@@ -1327,13 +1413,13 @@ static ColFilter filter_for_depth(sphmw_ctx *c, int ghost_depth) {
     return cf;
 }
 
-template <class Op>
+template <class Op, bool REC = false>
 static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Fields &out, ColFilter cf);
 
-template <class Op>
+template <class Op, bool REC = false>
 static int run_binary(sphmw_ctx *c, const char *name, int self, const Fields &out,
                       int ghost_depth = GHOST_COLS) {
-    return run_binary_cols<Op>(c, name, self, out, filter_for_depth(c, ghost_depth));
+    return run_binary_cols<Op, REC>(c, name, self, out, filter_for_depth(c, ghost_depth));
 }
 
 // device memory of the pair list, allocated on first use
@@ -1367,7 +1453,9 @@ int sphmw_pair_list_stats(sphmw_ctx *c, int64_t out[4]) {
 //   list valid for this cell list      -> k_binary_list   (replay)
 //   a list is wanted and none exists   -> k_binary_build  (walk once, record)
 //   otherwise                          -> k_binary        (walk)
-template <class Op>
+// REC (the two fused WCSPH passes with SPHMW_FLAG_PACKED_RECORDS): the list kernels read their
+// neighbours from the packed records; needs record A of this cell-list generation.
+template <class Op, bool REC>
 static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Fields &out, ColFilter cf) {
     if (!c->cell_list_valid) {
         sphmw_set_error("%s: create_cell_list must be called after positions change", name);
@@ -1381,9 +1469,21 @@ static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Field
     const bool record = lists && !replay && (c->want_list || (c->flags & SPHMW_FLAG_PAIR_LIST_EAGER));
     c->passes_this_gen += 1;
     const unsigned blocks = grid_for(c->n, NL_BLOCK);
+    const bool rec = REC && c->rec[0] && c->rec[1] && c->rec[2] && c->rec_gen == c->cell_gen;
+    c->pl.recA = c->rec[0];
+    c->pl.recB = c->rec[1];
+    c->pl.recC = c->rec[2];
 #define NL_ARGS c->cur, out, c->prm, c->grid, c->key, c->cellx, c->cell_start, c->n, self, pc, cf
     if (replay) {
         TIMED(c, name);
+        if constexpr (REC) {
+            if (rec && c->rec_bc_gen == c->cell_gen) {
+                if (c->grid.dim == 2) k_binary_list<2, Op, true><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
+                else k_binary_list<3, Op, true><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
+                CUDA_TRY(cudaGetLastError());
+                return SPHMW_OK;
+            }
+        }
         if (c->grid.dim == 2)
             k_binary_list<2, Op><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
         else
@@ -1396,6 +1496,19 @@ static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Field
         const bool q10 = !(c->flags & SPHMW_FLAG_NO_PRETEST);
         const size_t smem = sizeof(uint32_t) * (size_t)c->pl.stride * NL_BLOCK;
         TIMED(c, name);
+        c->pl_gen = c->cell_gen;
+        c->pl_builds += 1;
+        if constexpr (REC) {
+            if (rec) {
+                if (c->grid.dim == 2)
+                    k_binary_build<2, Op, NL_FILTER_Q10, true><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+                else
+                    k_binary_build<3, Op, NL_FILTER_Q10, true><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+                if (Op::REC_KIND == 1) c->rec_bc_gen = c->cell_gen;
+                CUDA_TRY(cudaGetLastError());
+                return SPHMW_OK;
+            }
+        }
         if (c->grid.dim == 2) {
             if (q10) k_binary_build<2, Op, NL_FILTER_Q10><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
             else k_binary_build<2, Op, NL_FILTER_F64><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
@@ -1403,8 +1516,6 @@ static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Field
             if (q10) k_binary_build<3, Op, NL_FILTER_Q10><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
             else k_binary_build<3, Op, NL_FILTER_F64><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
         }
-        c->pl_gen = c->cell_gen;
-        c->pl_builds += 1;
     } else {
         // Measured on B200 (profiles/r01_tuning.md): forcing 6 or 8 resident blocks per SM
         // (64 registers), 64-thread blocks and software prefetch of the next candidate were all
@@ -1720,6 +1831,27 @@ static int step_wcsph_fused_pre(sphmw_ctx *c) {
     return SPHMW_OK;
 }
 
+// the two fused pair passes of the "wcsph" step (strict / FAST_MATH closures, optionally with
+// the packed neighbour records)
+static int run_fused_density(sphmw_ctx *c) {
+    // owned columns + the first ghost column (its sums are complete thanks to the second)
+    const bool rec = (c->flags & SPHMW_FLAG_PACKED_RECORDS) != 0;
+    const char *name = "wcsph.density_fused";
+    if (c->flags & SPHMW_FLAG_FAST_MATH)
+        return rec ? run_binary<B_wcsph_density_fast, true>(c, name, 0, c->cur, 1)
+                   : run_binary<B_wcsph_density_fast>(c, name, 0, c->cur, 1);
+    return rec ? run_binary<B_wcsph_density_fused, true>(c, name, 0, c->cur, 1)
+               : run_binary<B_wcsph_density_fused>(c, name, 0, c->cur, 1);
+}
+static int run_fused_force(sphmw_ctx *c, const char *name, const ColFilter &cf) {
+    const bool rec = (c->flags & SPHMW_FLAG_PACKED_RECORDS) != 0;
+    if (c->flags & SPHMW_FLAG_FAST_MATH)
+        return rec ? run_binary_cols<B_wcsph_momentum_fast, true>(c, name, 0, c->alt, cf)
+                   : run_binary_cols<B_wcsph_momentum_fast>(c, name, 0, c->alt, cf);
+    return rec ? run_binary_cols<B_wcsph_momentum_fused, true>(c, name, 0, c->alt, cf)
+               : run_binary_cols<B_wcsph_momentum_fused>(c, name, 0, c->alt, cf);
+}
+
 // slab mode: the halo exchange sits between the two halves (after the drift, before the sort)
 static int step_wcsph_fused_post(sphmw_ctx *c) {
     TRY(sphmw_build_cell_list(c, nullptr));  // :313
@@ -1733,19 +1865,15 @@ static int step_wcsph_fused_post(sphmw_ctx *c) {
     c->want_list = true;
     if (c->flags & SPHMW_FLAG_CELL_PAIRS)
         TRY((run_cell_pairs<CP_Density>(c, "wcsph.density_fused", c->cur, 1)));
-    else if (c->flags & SPHMW_FLAG_FAST_MATH)
-        TRY((run_binary<B_wcsph_density_fast>(c, "wcsph.density_fused", 0, c->cur, 1)));
     else
-        TRY((run_binary<B_wcsph_density_fused>(c, "wcsph.density_fused", 0, c->cur, 1)));
+        TRY(run_fused_density(c));
     // :326-327 find_temperature!/find_pot_temp! are diagnostics: left stale, rebuilt on demand
     // :330-331 — owned columns only
     TRY(sphmw_ensure_slot(c, S_V0));
     if (c->flags & SPHMW_FLAG_CELL_PAIRS)
         TRY((run_cell_pairs<CP_Momentum>(c, "wcsph.momentum_fused", c->alt, 0)));
-    else if (c->flags & SPHMW_FLAG_FAST_MATH)
-        TRY((run_binary<B_wcsph_momentum_fast>(c, "wcsph.momentum_fused", 0, c->alt, 0)));
     else
-        TRY((run_binary<B_wcsph_momentum_fused>(c, "wcsph.momentum_fused", 0, c->alt, 0)));
+        TRY(run_fused_force(c, "wcsph.momentum_fused", filter_for_depth(c, 0)));
     std::swap(c->cur.s[S_V0], c->alt.s[S_V0]);
     std::swap(c->cur.s[S_V1], c->alt.s[S_V1]);
     if (c->grid.dim == 3) std::swap(c->cur.s[S_V2], c->alt.s[S_V2]);
@@ -1851,11 +1979,6 @@ static int run_advance_cols(sphmw_ctx *c, const char *name, const ColFilter &cf,
     return SPHMW_OK;
 }
 
-static int run_fused_force(sphmw_ctx *c, const char *name, const ColFilter &cf) {
-    if (c->flags & SPHMW_FLAG_FAST_MATH) return run_binary_cols<B_wcsph_momentum_fast>(c, name, 0, c->alt, cf);
-    return run_binary_cols<B_wcsph_momentum_fused>(c, name, 0, c->alt, cf);
-}
-
 static int step_wcsph_overlap_a(sphmw_ctx *c) {
     if (c->slab_lo < 0 || (c->flags & SPHMW_FLAG_CELL_PAIRS)) {
         sphmw_set_error("step_phase 2/3: the overlapped step runs on slab contexts without CELL_PAIRS");
@@ -1869,10 +1992,7 @@ static int step_wcsph_overlap_a(sphmw_ctx *c) {
         c->stale[s] = false;
     }
     c->want_list = true;
-    if (c->flags & SPHMW_FLAG_FAST_MATH)
-        TRY((run_binary<B_wcsph_density_fast>(c, "wcsph.density_fused", 0, c->cur, 1)));
-    else
-        TRY((run_binary<B_wcsph_density_fused>(c, "wcsph.density_fused", 0, c->cur, 1)));
+    TRY(run_fused_density(c));
     TRY(sphmw_ensure_slot(c, S_V0));
     const SlabCols sc = sphmw_slab_cols(c);
     TRY(run_fused_force(c, "wcsph.momentum_fused_edge", sc.force_edge));

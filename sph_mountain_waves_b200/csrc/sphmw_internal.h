@@ -174,9 +174,31 @@ NL_HD bool nl_q10_pass(uint32_t own, uint32_t other, int di, int dj, int dk, int
     }
     return !(s2 > NL_Q10_R2MAX);
 }
+// Packed neighbour records (SPHMW_FLAG_PACKED_RECORDS): what a replayed list entry needs from its
+// neighbour, as three 32-byte records read with one 256-bit load each instead of eleven 8-byte
+// gathers (profiles/microbench/gather_width.cu: 1.31x on the replay's access pattern).
+//   A {x, y, z, m}          written by the cell-list gather
+//   B {vx, vy, vz, h}       written by the density pass (h after update_smoothing!)
+//   C {P'/rho^2, rho^, c}   written by the density pass (rho^ = max(rho, rho_floor))
+// They are bit copies of the SoA fields, so results do not change.
+struct __align__(32) NbRec {
+    double a, b, c, d;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ NbRec nb_load(const NbRec *p) {
+    NbRec r;
+    asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void nb_store(NbRec *p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+#endif
+
 struct PairList {
     uint32_t *list;
     uint32_t *cnt;
+    NbRec *recA, *recB, *recC;  // null unless SPHMW_FLAG_PACKED_RECORDS
     // 10-bit-per-axis mirror: the position inside its own cell in units of h/1024, x | y<<10 | z<<20
     // (rebuilt by every cell-list build, cell_list.cu)
     const uint32_t *xq;
@@ -238,6 +260,9 @@ struct sphmw_ctx {
     // pair list (pair_list.cuh)
     PairList pl{};
     uint32_t *xq = nullptr;        // cap (+4) entries, rebuilt by every cell-list build
+    NbRec *rec[3] = {nullptr, nullptr, nullptr};  // packed neighbour records A, B, C (cap entries each)
+    uint64_t rec_gen = ~0ull;      // cell-list generation record A was written for
+    uint64_t rec_bc_gen = ~0ull;   // ... and records B, C (by the fused density pass)
     uint64_t cell_gen = 0;         // generation of the cell list
     uint64_t pl_gen = ~0ull;       // generation the pair list was built for
     bool want_list = false;        // build the list in the next binary pass
@@ -302,6 +327,7 @@ int64_t sphmw_list_ops(char *buf, int64_t cap);
 int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n);
 int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added);
 int sphmw_pair_list_stats(sphmw_ctx *c, int64_t out[4]);
+int sphmw_ensure_records(sphmw_ctx *c);  // api.cu: allocate the packed neighbour records
 // column sets of the overlapped slab step (local column indices)
 struct SlabCols {
     ColFilter edge;      // advanced and packed first: ghost columns + the three outermost owned ones

@@ -151,7 +151,7 @@ end
 # flags of `ParticleSystem(...; flags)` (include/sphmw.h): the pair list records each particle's
 # candidates on the first binary pass of a cell list and replays them on the later ones —
 # apply!(sys, compute_density!) then apply!(sys, balance_of_momentum!) walk the cells once
-const FLAG_FAST_MATH, FLAG_NO_PAIR_LIST, FLAG_PAIR_LIST_EAGER, FLAG_NO_PRETEST = 1, 4, 8, 16
+const FLAG_FAST_MATH, FLAG_NO_PAIR_LIST, FLAG_PAIR_LIST_EAGER, FLAG_NO_PRETEST, FLAG_PACKED_RECORDS = 1, 4, 8, 16, 32
 "(stride, lists built, particles that overflowed the stride, device bytes)"
 function pair_list_info(sys::ParticleSystem)
     out = zeros(Int64, 4)

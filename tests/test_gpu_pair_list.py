@@ -209,3 +209,57 @@ def test_cutoff_boundary_in_3d_across_cell_faces(gpu):
             s.apply(op)
         assert s.pair_count() == len(pio)
         assert n_mismatch(s.field("rho"), o.field("rho")) == 0
+
+
+# ---------------------------------------------------------------------------------------
+# SPHMW_FLAG_PACKED_RECORDS (experimental, default off): written after the round's GPU budget was
+# spent, so it has only ever been compiled.  Opt in with SPHMW_TEST_EXPERIMENTAL=1.
+# ---------------------------------------------------------------------------------------
+PACKED = 32
+experimental = pytest.mark.skipif(os.environ.get("SPHMW_TEST_EXPERIMENTAL") != "1",
+                                  reason="experimental path, never run on a GPU yet: set SPHMW_TEST_EXPERIMENTAL=1")
+
+
+@experimental
+@pytest.mark.parametrize("make", [small_2d, small_3d])
+@pytest.mark.parametrize("arith", [0, FAST_MATH])
+def test_packed_records_same_bits(gpu, make, arith):
+    """neighbours read from three 32-byte records with 256-bit loads: bit copies of the SoA
+    fields, so nothing may change"""
+    case = make()
+    a, b = load_gpu(case, flags=arith), load_gpu(case, flags=arith | PACKED)
+    for s in (a, b):
+        s.create_cell_list()
+        s.count_pairs(True)
+        s.step(6)
+    assert a.pair_count() == b.pair_count() > 0
+    for f in FIELDS:
+        assert bits_equal(a.field(f), b.field(f)), f
+
+
+@experimental
+def test_packed_records_on_slabs_with_the_overlapped_schedule(gpu):
+    from sph_mountain_waves_b200.slabs import LocalCluster, SlabRun
+    case = cases.bell_hill_3d(48, 10, 8, h_m=3000.0, a=8e3, U=20.0)
+    whole = load_gpu(case, flags=FAST_MATH)
+    whole.create_cell_list()
+    whole.step(12)
+    cluster = LocalCluster([SlabRun.from_global_case(case, r, 3, flags=FAST_MATH | PACKED) for r in range(3)])
+    cluster.create_cell_list()
+    cluster.step(12)
+    _, got = cluster.gather(("x", "v", "rho", "h"))
+    for f, arr in got.items():
+        assert np.array_equal(arr, whole.field(f)), f
+
+
+@experimental
+def test_packed_records_with_overflowing_lists(gpu, monkeypatch):
+    monkeypatch.setenv("SPHMW_PAIR_LIST_STRIDE", "12")
+    case = small_3d()
+    a, b = load_gpu(case, flags=NO_LIST), load_gpu(case, flags=PACKED)
+    for s in (a, b):
+        s.create_cell_list()
+        s.step(3)
+    assert b.pair_list_info()["overflow"] > 0
+    for f in FIELDS:
+        assert bits_equal(a.field(f), b.field(f)), f
