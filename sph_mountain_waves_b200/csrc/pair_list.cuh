@@ -295,7 +295,7 @@ k_binary_list(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restri
     if (cnt != NL_NONE) {
         const uint32_t *row = pl.list + ((size_t)(p >> 5) * (uint32_t)pl.stride) * 32 + (size_t)(p & 31);
         // (loading the next entry's position one iteration ahead as well was measured slower:
-        // profiles/r01_tuning.md)
+        // profiles/r01b_pair_list.md)
         uint32_t qn = cnt ? __ldcs(row) : 0u;
         for (uint32_t k = 0; k < cnt; ++k) {
             const uint32_t q = qn;
