@@ -1,0 +1,371 @@
+// The closures of the fused "wcsph" step as device functors — balance of
+// wcsph_perturbed_witch.jl:195-303 folded into two pair passes — and the
+// helpers they share with the operator menu in pair_ops.cu.  Kept in a header so that the
+// pair-list kernels and these closures can also be compiled for the host by the emulation
+// harness of the CPU test suite (tests/emu/), which checks them against the oracle.
+//
+// Arithmetic: compiled with -fmad=false; every product/sum is written in the reference's
+// evaluation order (Julia's n-ary * and + fold left).
+#pragma once
+#include <math.h>
+
+#include "kernels_sph.cuh"
+#include "sphmw_internal.h"
+
+// Julia's max(a,b) propagates NaN (Base.max); fmax does not.
+__device__ __forceinline__ double jl_max(double a, double b) {
+    if (a != a || b != b) return a + b;
+    return a < b ? b : a;
+}
+
+// wcsph_perturbed_witch.jl:177-189
+__device__ __forceinline__ double background_density(const Params &c, double y) {
+    return c.rho0 * exp(-y * c.g / (c.R_mass * c.T_bg));
+}
+__device__ __forceinline__ double background_pressure(const Params &c, double y) {
+    double rho_bg = background_density(c, y);
+    return c.R_mass * c.T_bg * rho_bg;
+}
+__device__ __forceinline__ double background_pot_temperature(const Params &c, double y) {
+    double P_bg = background_pressure(c, y);
+    return c.T_bg * pow((c.T_bg * c.R_gas * c.rho0) / P_bg, 2.0 / 7.0);
+}
+
+#define PF(slot) f.s[slot][p]
+#define QF(slot) f.s[slot][q]
+
+// particles outside the column range a pass covers (slab mode: ghost columns) are skipped
+struct PairOpBase {
+    template <int DIM>
+    static __device__ void skip(const Fields &, const Fields &, int64_t) {}
+    // packed neighbour records (pair_list.cuh): 0 the operator does not use them, 1 it has
+    // pair_m (needs record A), 2 it has pair_rec (needs A, B, C)
+    static constexpr int REC_KIND = 0;
+};
+
+// ---- fused operators of the fast path (sphmw_step, scheme "wcsph") --------
+// reset_density! + compute_density! + finalize_density! + update_smoothing! +
+// compute_pressure!  (wcsph_perturbed_witch.jl:316-323) in one pass, plus the
+// per-particle invariants of the pair force.
+struct B_wcsph_density_fused : PairOpBase {
+    static constexpr int REC_KIND = 1;
+    double rho, hp;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &, int64_t p) {
+        rho = 0.0;  // reset_density!
+        hp = PF(S_H);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &, int64_t, int64_t q, double, double,
+                         double, double r) {
+        rho += QF(S_M) * sph_W<DIM>(hp, r);
+    }
+    // the same with the neighbour's mass out of its packed record (SPHMW_FLAG_PACKED_RECORDS)
+    template <int DIM>
+    __device__ void pair_m(const Params &, double qm, double, double, double, double r) {
+        rho += qm * sph_W<DIM>(hp, r);
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &c, int64_t p) {
+        double y = PF(S_X1);
+        double rbg = background_density(c, y);  // finalize_density!
+        double rho_p = rho - rbg;
+        double rfl = jl_max(rho, c.rho_floor);  // update_smoothing!
+        double m = PF(S_M);
+        double hn = DIM == 2 ? c.eta * sqrt(m / rfl) : c.eta * cbrt(m / rfl);
+        double pbg = c.R_mass * c.T_bg * rbg;  // compute_pressure! (same rho_bg(y) value)
+        double pp = sph_pow2(c.c) * rho_p;
+        double P = pbg + pp;
+        PF(S_RHO) = rho;
+        PF(S_RHO_BG) = rbg;
+        PF(S_RHO_P) = rho_p;
+        PF(S_H) = hn;
+        PF(S_P_BG) = pbg;
+        PF(S_P_P) = pp;
+        PF(S_P) = P;
+        PF(S_PR2) = pp / sph_pow2(rfl);
+        PF(S_CS) = sqrt(c.gamma * P / rfl);
+    }
+};
+
+// balance_of_momentum! + accelerate!  (wcsph_perturbed_witch.jl:330-331).
+// Dv starts at 0 (accelerate! zeroed it) and is never stored; the new velocity
+// goes to the `out` field set because other threads still read the old one.
+struct B_wcsph_momentum_fused : PairOpBase {
+    static constexpr int REC_KIND = 2;
+    double dv0, dv1, dv2, v0, v1, v2, hp, prho, pr2, cs;
+    // the velocity is double-buffered: a skipped (ghost) particle carries its value over
+    template <int DIM>
+    static __device__ void skip(const Fields &f, const Fields &out, int64_t p) {
+        out.s[S_V0][p] = f.s[S_V0][p];
+        out.s[S_V1][p] = f.s[S_V1][p];
+        if (DIM == 3) out.s[S_V2][p] = f.s[S_V2][p];
+    }
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &c, int64_t p) {
+        dv0 = dv1 = dv2 = 0.0;
+        v0 = PF(S_V0);
+        v1 = PF(S_V1);
+        v2 = DIM == 3 ? PF(S_V2) : 0.0;
+        hp = PF(S_H);
+        prho = jl_max(PF(S_RHO), c.rho_floor);
+        pr2 = PF(S_PR2);
+        cs = PF(S_CS);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        double vx = v0 - QF(S_V0), vy = v1 - QF(S_V1);
+        double dot_product = dx * vx + dy * vy;
+        if (DIM == 3) {
+            double vz = v2 - QF(S_V2);
+            dot_product = dot_product + dz * vz;
+        }
+        double h_ij = 0.5 * (hp + QF(S_H));
+        double ker = sph_rDW<DIM>(h_ij, r);
+        double qm = QF(S_M);
+        double fc = -qm * (pr2 + QF(S_PR2)) * ker;
+        dv0 += fc * dx;
+        dv1 += fc * dy;
+        if (DIM == 3) dv2 += fc * dz;
+        if (dot_product < 0.0) {
+            double qrho = jl_max(QF(S_RHO), c.rho_floor);
+            double c_ij = 0.5 * (cs + QF(S_CS));
+            double rho_ij = 0.5 * (prho + qrho);
+            double mu_ij = (h_ij * dot_product) / (r * r + c.eps * h_ij * h_ij);
+            double pi_ij = (-c.alpha * c_ij * mu_ij + c.beta * mu_ij * mu_ij) / rho_ij;
+            double fv = -qm * pi_ij * ker;
+            dv0 += fv * dx;
+            dv1 += fv * dy;
+            if (DIM == 3) dv2 += fv * dz;
+        }
+    }
+    // the same with the neighbour's fields out of its packed records: qm = A.d,
+    // B = {vx, vy, vz, h}, C = {P'/rho^2, max(rho, rho_floor), c_s}
+    template <int DIM>
+    __device__ void pair_rec(const Params &c, double qm, const NbRec &B, const NbRec &C, double dx, double dy,
+                             double dz, double r) {
+        double vx = v0 - B.a, vy = v1 - B.b;
+        double dot_product = dx * vx + dy * vy;
+        if (DIM == 3) {
+            double vz = v2 - B.c;
+            dot_product = dot_product + dz * vz;
+        }
+        double h_ij = 0.5 * (hp + B.d);
+        double ker = sph_rDW<DIM>(h_ij, r);
+        double fc = -qm * (pr2 + C.a) * ker;
+        dv0 += fc * dx;
+        dv1 += fc * dy;
+        if (DIM == 3) dv2 += fc * dz;
+        if (dot_product < 0.0) {
+            double qrho = C.b;
+            double c_ij = 0.5 * (cs + C.c);
+            double rho_ij = 0.5 * (prho + qrho);
+            double mu_ij = (h_ij * dot_product) / (r * r + c.eps * h_ij * h_ij);
+            double pi_ij = (-c.alpha * c_ij * mu_ij + c.beta * mu_ij * mu_ij) / rho_ij;
+            double fv = -qm * pi_ij * ker;
+            dv0 += fv * dx;
+            dv1 += fv * dy;
+            if (DIM == 3) dv2 += fv * dz;
+        }
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &out, const Params &c, int64_t p) {
+        double n0 = v0, n1 = v1, n2 = v2;
+        if (PF(S_TYPE) == c.fluid) {  // accelerate!
+            const double rho_p = PF(S_RHO_P), rho = PF(S_RHO);
+            const bool sponge = PF(S_X1) >= c.sponge_z0;
+            const double hdt = 0.5 * c.dt;
+            n0 = v0 + hdt * (dv0 + -c.g * 0.0 * rho_p / rho + (sponge ? c.sponge_y * 0.0 : 0.0));
+            n1 = v1 + hdt * (dv1 + -c.g * 1.0 * rho_p / rho + (sponge ? c.sponge_y * 1.0 : 0.0));
+            if (DIM == 3)
+                n2 = v2 + hdt * (dv2 + -c.g * 0.0 * rho_p / rho + (sponge ? c.sponge_y * 0.0 : 0.0));
+        }
+        out.s[S_V0][p] = n0;
+        out.s[S_V1][p] = n1;
+        if (DIM == 3) out.s[S_V2][p] = n2;
+    }
+};
+// ---- fast-arithmetic variants of the two fused passes (SPHMW_FLAG_FAST_MATH) ----------
+// Same neighbour set (the cut-off test stays exact) and the same summation ORDER, but the
+// closure bodies use fused multiply-adds, reciprocals instead of divisions and one rsqrt,
+// like the reference's own @fastmath kernels (kernels.jl:108-195).  Every operation is
+// accurate to ~1 ulp, so rho and v stay within a few 1e-16 relative of the strict path per
+// pair — far inside the north star's 1e-10 per step — while the FP64 instruction count of
+// the accepted-pair path drops ~2.5x.  Results remain deterministic and independent of the
+// number of ranks (the code path is the same everywhere).
+__device__ __forceinline__ double fast_sqrt_pos(double a) {
+    // a > 0 finite in the accepted-pair path (a == 0 only for coincident particles)
+    if (a <= 0.0) return a == 0.0 ? 0.0 : sqrt(a);
+    double y = rsqrt(a);
+    double r = a * y;
+    return fma(fma(-r, r, a), 0.5 * y, r);  // one Newton step: ~0.5 ulp
+}
+
+struct B_wcsph_density_fast : PairOpBase {
+    static constexpr int REC_KIND = 1;
+    double rho, hp, inv_h, cw;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &, int64_t p) {
+        rho = 0.0;
+        hp = PF(S_H);
+        inv_h = 1.0 / hp;
+        // 7/pi / h^2  or  21/(2 pi) / h^3
+        cw = DIM == 2 ? 2.228169203286535 * (inv_h * inv_h) : 3.3422538049298023 * (inv_h * inv_h * inv_h);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &, int64_t, int64_t q, double dx, double dy,
+                         double dz, double) {
+        double r2 = fma(dx, dx, dy * dy);
+        if (DIM == 3) r2 = fma(dz, dz, r2);
+        double x = fast_sqrt_pos(r2) * inv_h;
+        if (x > 1.0) return;  // kernels.jl:110-112
+        double t = 1.0 - x;
+        double t2 = t * t;
+        double w = cw * (t2 * t2) * fma(4.0, x, 1.0);
+        rho = fma(QF(S_M), w, rho);
+    }
+    template <int DIM>
+    __device__ void pair_m(const Params &, double qm, double dx, double dy, double dz, double) {
+        double r2 = fma(dx, dx, dy * dy);
+        if (DIM == 3) r2 = fma(dz, dz, r2);
+        double x = fast_sqrt_pos(r2) * inv_h;
+        if (x > 1.0) return;
+        double t = 1.0 - x;
+        double t2 = t * t;
+        double w = cw * (t2 * t2) * fma(4.0, x, 1.0);
+        rho = fma(qm, w, rho);
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &c, int64_t p) {
+        double y = PF(S_X1);
+        double rbg = background_density(c, y);
+        double rho_p = rho - rbg;
+        double rfl = jl_max(rho, c.rho_floor);
+        double m = PF(S_M);
+        double hn = DIM == 2 ? c.eta * sqrt(m / rfl) : c.eta * cbrt(m / rfl);
+        double pbg = c.R_mass * c.T_bg * rbg;
+        double pp = sph_pow2(c.c) * rho_p;
+        double P = pbg + pp;
+        PF(S_RHO) = rho;
+        PF(S_RHO_BG) = rbg;
+        PF(S_RHO_P) = rho_p;
+        PF(S_H) = hn;
+        PF(S_P_BG) = pbg;
+        PF(S_P_P) = pp;
+        PF(S_P) = P;
+        PF(S_PR2) = pp / sph_pow2(rfl);
+        PF(S_CS) = sqrt(c.gamma * P / rfl);
+    }
+};
+
+struct B_wcsph_momentum_fast : PairOpBase {
+    static constexpr int REC_KIND = 2;
+    double dv0, dv1, dv2, v0, v1, v2, hp, prho, pr2, cs;
+    template <int DIM>
+    static __device__ void skip(const Fields &f, const Fields &out, int64_t p) {
+        out.s[S_V0][p] = f.s[S_V0][p];
+        out.s[S_V1][p] = f.s[S_V1][p];
+        if (DIM == 3) out.s[S_V2][p] = f.s[S_V2][p];
+    }
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &c, int64_t p) {
+        dv0 = dv1 = dv2 = 0.0;
+        v0 = PF(S_V0);
+        v1 = PF(S_V1);
+        v2 = DIM == 3 ? PF(S_V2) : 0.0;
+        hp = PF(S_H);
+        prho = jl_max(PF(S_RHO), c.rho_floor);
+        pr2 = PF(S_PR2);
+        cs = PF(S_CS);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double) {
+        double r2 = fma(dx, dx, dy * dy);
+        double dot_product = fma(dy, v1 - QF(S_V1), dx * (v0 - QF(S_V0)));
+        if (DIM == 3) {
+            r2 = fma(dz, dz, r2);
+            dot_product = fma(dz, v2 - QF(S_V2), dot_product);
+        }
+        double h_ij = 0.5 * (hp + QF(S_H));
+        double inv_h = 1.0 / h_ij;
+        double x = fast_sqrt_pos(r2) * inv_h;
+        if (x > 1.0) return;  // rDwendland: 0 outside its own support (kernels.jl:142-144)
+        double t = 1.0 - x;
+        double ih2 = inv_h * inv_h;
+        double ih4 = ih2 * ih2;
+        // -140/pi (1-x)^3 / h^4   or   -210/pi (1-x)^3 / h^5
+        double ker = DIM == 2 ? -44.563384065730695 * (t * t * t) * ih4
+                              : -66.84507609859604 * (t * t * t) * (ih4 * inv_h);
+        double qm = QF(S_M);
+        double fc = -qm * (pr2 + QF(S_PR2)) * ker;
+        if (dot_product < 0.0) {
+            double qrho = jl_max(QF(S_RHO), c.rho_floor);
+            double c_ij = 0.5 * (cs + QF(S_CS));
+            double rho_ij = 0.5 * (prho + qrho);
+            // mu = h dot / D,  pi = (-alpha c mu + beta mu^2) / rho_ij, with one reciprocal
+            double D = fma(c.eps * h_ij, h_ij, r2);
+            double R = 1.0 / (D * rho_ij);
+            double hd = h_ij * dot_product;
+            double mu = hd * rho_ij * R;
+            double pi_ij = hd * R * fma(c.beta, mu, -c.alpha * c_ij);
+            fc = fma(-qm * pi_ij, ker, fc);
+        }
+        dv0 = fma(fc, dx, dv0);
+        dv1 = fma(fc, dy, dv1);
+        if (DIM == 3) dv2 = fma(fc, dz, dv2);
+    }
+    template <int DIM>
+    __device__ void pair_rec(const Params &c, double qm, const NbRec &B, const NbRec &C, double dx, double dy,
+                             double dz, double) {
+        double r2 = fma(dx, dx, dy * dy);
+        double dot_product = fma(dy, v1 - B.b, dx * (v0 - B.a));
+        if (DIM == 3) {
+            r2 = fma(dz, dz, r2);
+            dot_product = fma(dz, v2 - B.c, dot_product);
+        }
+        double h_ij = 0.5 * (hp + B.d);
+        double inv_h = 1.0 / h_ij;
+        double x = fast_sqrt_pos(r2) * inv_h;
+        if (x > 1.0) return;
+        double t = 1.0 - x;
+        double ih2 = inv_h * inv_h;
+        double ih4 = ih2 * ih2;
+        double ker = DIM == 2 ? -44.563384065730695 * (t * t * t) * ih4
+                              : -66.84507609859604 * (t * t * t) * (ih4 * inv_h);
+        double fc = -qm * (pr2 + C.a) * ker;
+        if (dot_product < 0.0) {
+            double qrho = C.b;
+            double c_ij = 0.5 * (cs + C.c);
+            double rho_ij = 0.5 * (prho + qrho);
+            double D = fma(c.eps * h_ij, h_ij, r2);
+            double R = 1.0 / (D * rho_ij);
+            double hd = h_ij * dot_product;
+            double mu = hd * rho_ij * R;
+            double pi_ij = hd * R * fma(c.beta, mu, -c.alpha * c_ij);
+            fc = fma(-qm * pi_ij, ker, fc);
+        }
+        dv0 = fma(fc, dx, dv0);
+        dv1 = fma(fc, dy, dv1);
+        if (DIM == 3) dv2 = fma(fc, dz, dv2);
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &out, const Params &c, int64_t p) {
+        double n0 = v0, n1 = v1, n2 = v2;
+        if (PF(S_TYPE) == c.fluid) {
+            const double rho_p = PF(S_RHO_P), rho = PF(S_RHO);
+            const bool sponge = PF(S_X1) >= c.sponge_z0;
+            const double hdt = 0.5 * c.dt;
+            n0 = v0 + hdt * (dv0 + -c.g * 0.0 * rho_p / rho + (sponge ? c.sponge_y * 0.0 : 0.0));
+            n1 = v1 + hdt * (dv1 + -c.g * 1.0 * rho_p / rho + (sponge ? c.sponge_y * 1.0 : 0.0));
+            if (DIM == 3)
+                n2 = v2 + hdt * (dv2 + -c.g * 0.0 * rho_p / rho + (sponge ? c.sponge_y * 0.0 : 0.0));
+        }
+        out.s[S_V0][p] = n0;
+        out.s[S_V1][p] = n1;
+        if (DIM == 3) out.s[S_V2][p] = n2;
+    }
+};
+#undef PF
+#undef QF

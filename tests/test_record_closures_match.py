@@ -1,4 +1,4 @@
-"""The packed-record variants of the fused closures (pair_m / pair_rec, csrc/pair_ops.cu) restate
+"""The packed-record variants of the fused closures (pair_m / pair_rec, csrc/wcsph_ops.cuh) restate
 pair() with the neighbour's fields taken from its records instead of the SoA arrays.  The two
 bodies must stay the same arithmetic, token for token, or the record path would no longer be
 bit-identical (wcsph_perturbed_witch.jl:226-228, :261-286).  This test compares the source text
@@ -8,7 +8,7 @@ from pathlib import Path
 
 import pytest
 
-SRC = (Path(__file__).resolve().parent.parent / "sph_mountain_waves_b200" / "csrc" / "pair_ops.cu").read_text()
+SRC = (Path(__file__).resolve().parent.parent / "sph_mountain_waves_b200" / "csrc" / "wcsph_ops.cuh").read_text()
 
 # field of q in the SoA closure -> the same value in the record closure
 SUBST = [
