@@ -83,24 +83,12 @@ static const ParamDesc PARAM_TABLE[] = {
     {"cp", POFF(cp)},           {"bc_width", POFF(bc_width)},   {"x_inflow", POFF(x_inflow)},
     {"dr", POFF(dr)},           {"inflow", POFF(inflow)},       {nullptr, 0}};
 
-static void derive_params(Params &p) {
-    // damping_structure, wcsph_perturbed_witch.jl:245-251: a constant vector.
-    // Evaluated once on the host in the written order.
-    p.sponge_z0 = p.z_t - p.z_b;
-    if (p.z_b != 0.0) {
-        double sn = sin(M_PI / 2 * (1 - (p.z_t - p.z_b) / p.z_b));
-        p.sponge_y = -p.gamma_r * (sn * sn);
-    } else {
-        p.sponge_y = 0.0;
-    }
-}
-
 extern "C" int sphmw_set_param(sphmw_ctx *c, const char *name, double v) {
     if (!c || !name) { sphmw_set_error("null argument"); return SPHMW_E_INVALID; }
     for (const ParamDesc *d = PARAM_TABLE; d->name; ++d)
         if (!strcmp(d->name, name)) {
             *(double *)((char *)&c->prm + d->off) = v;
-            derive_params(c->prm);
+            sphmw_derive_params(c->prm);
             return SPHMW_OK;
         }
     sphmw_set_error("unknown parameter '%s'", name);
@@ -242,108 +230,16 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
     c->cap = cfg->capacity;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     Grid &g = c->grid;
-    g.h = cfg->h;
-    for (int a = 0; a < 3; ++a) {
-        g.box[a] = cfg->box_min[a];
-        g.box[3 + a] = cfg->box_max[a];
-    }
-    // structs.jl:66-68
-    g.key_max = 1;
-    for (int a = 0; a < 3; ++a) {
-        g.phase[a] = (long long)floor(g.box[a] / g.h);
-        g.lim[a] = (long long)floor(g.box[3 + a] / g.h) - g.phase[a] + 1;
-        if (g.lim[a] <= 0) {
-            delete c;
-            sphmw_set_error("empty bounding box along axis %d", a);
-            return SPHMW_E_INVALID;
-        }
-        g.key_max *= g.lim[a];
-    }
     c->slab_lo = cfg->slab_lo;
     c->slab_hi = cfg->slab_hi;
-    if (c->slab_lo >= 0) {
-        // local grid = owned columns + GHOST_COLS ghost columns each side; keys are local
-        if (!(c->slab_hi > c->slab_lo) || c->slab_hi > g.lim[0]) {
+    {
+        // key tables, neighbour offsets, physical cell order, exact cut-off (grid_setup.cpp)
+        const int rc = sphmw_grid_setup(g, cfg->box_min, cfg->box_max, cfg->h, cfg->slab_lo, cfg->slab_hi,
+                                        &c->global_cols);
+        if (rc != SPHMW_OK) {
             delete c;
-            sphmw_set_error("invalid slab [%lld,%lld) for %lld columns", (long long)c->slab_lo,
-                            (long long)c->slab_hi, g.lim[0]);
-            return SPHMW_E_INVALID;
+            return rc;
         }
-        if (c->slab_hi - c->slab_lo < 2 * GHOST_COLS) {
-            delete c;
-            sphmw_set_error("a slab must own at least %d cell columns", 2 * GHOST_COLS);
-            return SPHMW_E_INVALID;
-        }
-        c->global_cols = g.lim[0];
-        long long width = (c->slab_hi - c->slab_lo) + 2 * GHOST_COLS;
-        g.phase[0] += c->slab_lo - GHOST_COLS;
-        g.key_max = g.key_max / g.lim[0] * width;
-        g.lim[0] = width;
-    }
-    if (g.key_max >= (long long)0xFFFFFFF0u) {
-        delete c;
-        sphmw_set_error("too many cells (%lld)", g.key_max);
-        return SPHMW_E_INVALID;
-    }
-    // structs.jl:70-82 — di outermost
-    g.ndiff = 0;
-    if (g.lim[2] == 1) {
-        g.dim = 2;
-        for (int di = -1; di <= 1; ++di)
-            for (int dj = -1; dj <= 1; ++dj) {
-                g.nb_di[g.ndiff] = di;
-                g.nb_drest[g.ndiff] = dj;
-                g.nb_dj[g.ndiff] = dj;
-                g.nb_dk[g.ndiff] = 0;
-                g.key_diff[g.ndiff++] = (int)(di + g.lim[0] * dj);
-            }
-    } else {
-        g.dim = 3;
-        for (int di = -1; di <= 1; ++di)
-            for (int dj = -1; dj <= 1; ++dj)
-                for (int dk = -1; dk <= 1; ++dk) {
-                    g.nb_di[g.ndiff] = di;
-                    g.nb_dj[g.ndiff] = dj;
-                    g.nb_dk[g.ndiff] = dk;
-                    g.nb_drest[g.ndiff] = (int)(dj + g.lim[1] * dk);
-                    g.key_diff[g.ndiff++] = (int)(di + g.lim[0] * (dj + g.lim[1] * dk));
-                }
-    }
-    // physical x-chunking.  A pass needs three x-y planes of cells at a time; chunks are sized
-    // so that three chunk-planes (~6 particles x ~100 B per cell) stay near 40 MB, well inside
-    // the 126 MB L2: about 22000 / Ly columns (measured on the 64 M case, profiles/r01_tuning.md:
-    // 256 columns best of 32..2048).  Grids up to 1.5x that wide, and 2D grids, stay one chunk
-    // (plain x-fastest rows); wider ones are cut into equal-looking power-of-two chunks.
-    {
-        const long long lx = g.lim[0];
-        const long long want = g.dim == 3 ? std::max<long long>(32, 22000 / std::max<long long>(1, g.lim[1])) : lx;
-        long long cols = lx;
-        if (2 * lx > 3 * want) {
-            const long long nchunks = (lx + want - 1) / want;
-            cols = (lx + nchunks - 1) / nchunks;
-        }
-        g.cx_shift = 0;
-        while ((1LL << g.cx_shift) < cols) ++g.cx_shift;
-    }
-    if (getenv("SPHMW_CX_SHIFT")) g.cx_shift = atoi(getenv("SPHMW_CX_SHIFT"));
-    g.rows = g.lim[1] * g.lim[2];
-    {
-        long long cx = 1LL << g.cx_shift;
-        long long nchunks = (g.lim[0] + cx - 1) / cx;
-        g.pkey_max = nchunks * cx * g.rows;
-    }
-    if (g.pkey_max >= (long long)0x7FFFFFF0) {
-        delete c;
-        sphmw_set_error("too many cells (%lld)", g.pkey_max);
-        return SPHMW_E_INVALID;
-    }
-    {
-        // exact threshold for the cut-off test (sqrt is monotone and correctly rounded on
-        // host and device alike)
-        double t = g.h * g.h;
-        while (sqrt(t) > g.h) t = nextafter(t, 0.0);
-        while (sqrt(nextafter(t, INFINITY)) <= g.h) t = nextafter(t, INFINITY);
-        g.r2_max = t;
     }
     memset(&c->prm, 0, sizeof(Params));
 

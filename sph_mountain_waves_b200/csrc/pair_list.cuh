@@ -109,6 +109,19 @@ __device__ __forceinline__ void nl_entry_rec_force(Op &op, const Params &prm, co
 // that a push is one predicated st.shared and one predicated add (the queue is touched only
 // through these volatile statements, which keep their order).  Room for a whole cell run is
 // checked before the run starts (nl_room), not per candidate.
+__device__ __forceinline__ bool nl_room(unsigned top, unsigned end, uint32_t run) {
+    // run < 2^20 keeps the product inside 32 bits; longer runs never fit a stride <= 96 anyway
+    return run < (1u << 20) && top + run * (NL_BLOCK * 4u) <= end;
+}
+#ifdef SPHMW_EMU  // host build for the CPU tests: the "shared window" is the array itself
+inline void nl_push(unsigned &top, uint32_t q, bool pass) {
+    if (pass) {
+        *(uint32_t *)((char *)nl_queue_emu() + top) = q;
+        top += NL_BLOCK * 4u;
+    }
+}
+inline uint32_t nl_peek(unsigned addr) { return *(const uint32_t *)((const char *)nl_queue_emu() + addr); }
+#else
 __device__ __forceinline__ void nl_push(unsigned &top, uint32_t q, bool pass) {
     asm volatile(
         "{\n\t"
@@ -120,15 +133,12 @@ __device__ __forceinline__ void nl_push(unsigned &top, uint32_t q, bool pass) {
         : "+r"(top)
         : "r"(q), "r"((unsigned)pass), "n"(NL_BLOCK * 4));
 }
-__device__ __forceinline__ bool nl_room(unsigned top, unsigned end, uint32_t run) {
-    // run < 2^20 keeps the product inside 32 bits; longer runs never fit a stride <= 96 anyway
-    return run < (1u << 20) && top + run * (NL_BLOCK * 4u) <= end;
-}
 __device__ __forceinline__ uint32_t nl_peek(unsigned addr) {
     uint32_t q;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"(addr));
     return q;
 }
+#endif
 
 __device__ __forceinline__ void nl_count_pairs(unsigned long long *pair_counter, unsigned accepted) {
     if (pair_counter) {

@@ -78,7 +78,7 @@ struct Grid {
     int nb_dk[27];
 };
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(SPHMW_EMU)
 // 32-bit cell arithmetic (all quantities < 2^31: sphmw_create checks pkey_max)
 struct CellCoord {
     int i, rest;
@@ -150,7 +150,7 @@ __host__ __device__ __forceinline__ bool col_selected(const ColFilter &cf, int i
 // sum d_a^2 < (1024 + sqrt(3))^2.  1.74 > sqrt(3) leaves room for the rounding of x/h (1e-13).
 #define NL_Q10_ONE 1024
 #define NL_Q10_R2MAX 1052142  // floor((1024 + 1.74)^2)
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(SPHMW_EMU)
 #define NL_HD __host__ __device__ __forceinline__
 #else
 #define NL_HD static inline
@@ -184,7 +184,10 @@ NL_HD bool nl_q10_pass(uint32_t own, uint32_t other, int di, int dj, int dk, int
 struct __align__(32) NbRec {
     double a, b, c, d;
 };
-#ifdef __CUDACC__
+#if defined(SPHMW_EMU)  // host build of the device headers for the CPU tests (tests/emu/)
+inline NbRec nb_load(const NbRec *p) { return *p; }
+inline void nb_store(NbRec *p, double a, double b, double c, double d) { *p = NbRec{a, b, c, d}; }
+#elif defined(__CUDACC__)
 __device__ __forceinline__ NbRec nb_load(const NbRec *p) {
     NbRec r;
     asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
@@ -315,6 +318,10 @@ struct FieldDesc {
 };
 const FieldDesc *sphmw_find_field(const char *name);
 
+// implemented in grid_setup.cpp (host only, no CUDA calls)
+void sphmw_derive_params(Params &p);
+int sphmw_grid_setup(Grid &g, const double box_min[3], const double box_max[3], double h, int64_t slab_lo,
+                     int64_t slab_hi, int64_t *global_cols);
 // implemented in cell_list.cu
 int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive);
 int sphmw_ensure_slot(sphmw_ctx *c, int slot);

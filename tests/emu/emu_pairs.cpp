@@ -1,0 +1,286 @@
+// CPU emulation harness of the pair kernels of libsphmw — TEST INFRASTRUCTURE, never shipped.
+//
+// Compiles the device headers (csrc/pair_list.cuh, wcsph_ops.cuh, kernels_sph.cuh) with g++
+// against tests/emu/cuda_runtime.h and runs the kernels one "thread" at a time:
+//   walk        the cell walk of _apply_binary! (src/core.jl:94-112), as k_binary does it
+//   list        k_binary_build (integer pre-test) + k_binary_list
+//   list_f64    the same with the exact FP64 test in the recording pass
+//   records     k_binary_build / k_binary_list with the packed neighbour records
+// for the two fused passes of verlet_step! (wcsph_perturbed_witch.jl:316-331) on the particle
+// state it is given (positions already advanced).  All variants must agree bit for bit; the
+// result of the first one is written out so that the Python test can compare it with the oracle
+// (-ffp-contract=off and the same libm: strict arithmetic is expected to match exactly).
+//
+// usage: emu_pairs <input.bin> <output.bin>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "cuda_runtime.h"
+#include "pair_list.cuh"
+#include "sphmw_internal.h"
+#include "wcsph_ops.cuh"
+
+uint3 threadIdx, blockIdx, blockDim;
+uint32_t nl_queue[96 * NL_BLOCK];
+
+void sphmw_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    fputc('\n', stderr);
+}
+
+template <class F>
+static void launch(int64_t n, F &&thread_body) {
+    blockDim = uint3{NL_BLOCK, 1, 1};
+    for (int64_t b = 0; b * NL_BLOCK < n; ++b) {
+        blockIdx = uint3{(unsigned)b, 0, 0};
+        for (unsigned t = 0; t < NL_BLOCK; ++t) {
+            threadIdx = uint3{t, 0, 0};
+            thread_body();
+        }
+    }
+}
+
+// what k_binary (pair_ops.cu) does for one particle
+template <int DIM, class Op>
+static void walk_thread(Fields f, Fields out, Params prm, Grid g, const uint32_t *key, const uint32_t *cellx,
+                        const uint32_t *cell_start, int64_t n, unsigned long long *pc) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const CellCoord home = cell_of(g, key[p], cellx[p]);
+    Op op;
+    op.template init<DIM>(f, prm, p);
+    const double px = f.s[S_X0][p], py = f.s[S_X1][p], pz = DIM == 3 ? f.s[S_X2][p] : 0.0;
+    unsigned acc = 0;
+    nl_walk<DIM>(op, f, prm, g, home, p, px, py, pz, cell_start, acc);
+    op.template finish<DIM>(f, out, prm, p);
+    *pc += acc;
+}
+
+struct State {
+    int64_t n = 0;
+    std::vector<double> cur[NSLOT], alt[NSLOT];
+    std::vector<uint32_t> key, cellx, cell_start, idx, xq, list, cnt;
+    std::vector<NbRec> rec[3];
+    Fields fcur{}, falt{};
+    void bind() {
+        for (int s = 0; s < NSLOT; ++s) {
+            fcur.s[s] = cur[s].empty() ? nullptr : cur[s].data();
+            falt.s[s] = alt[s].empty() ? nullptr : alt[s].data();
+        }
+    }
+};
+
+static const int WRITTEN[] = {S_RHO, S_RHO_BG, S_RHO_P, S_H, S_P_BG, S_P_P, S_P, S_PR2, S_CS};
+
+struct Result {
+    std::vector<double> fields[9], vnew[3];
+    unsigned long long pairs_density = 0, pairs_force = 0, overflow = 0;
+    bool same_as(const Result &o) const {
+        for (int k = 0; k < 9; ++k)
+            if (memcmp(fields[k].data(), o.fields[k].data(), sizeof(double) * fields[k].size())) return false;
+        for (int k = 0; k < 3; ++k)
+            if (memcmp(vnew[k].data(), o.vnew[k].data(), sizeof(double) * vnew[k].size())) return false;
+        return pairs_density == o.pairs_density && pairs_force == o.pairs_force;
+    }
+};
+
+enum Variant { WALK, LIST_Q10, LIST_F64, RECORDS };
+
+template <int DIM, class DensityOp, class ForceOp>
+static Result run_variant(State st, const Grid &g, const Params &prm, Variant v, int stride) {
+    st.bind();
+    const int64_t n = st.n;
+    Result r;
+    unsigned long long counters[4] = {0, 0, 0, 0};
+    ColFilter cf{0, 0, (int)g.lim[0] - 1, 1, 0, 1};
+    PairList pl{};
+    pl.list = st.list.data();
+    pl.cnt = st.cnt.data();
+    pl.xq = st.xq.data();
+    pl.stride = stride;
+    pl.overflow = &counters[2];
+    pl.recA = st.rec[0].data();
+    pl.recB = st.rec[1].data();
+    pl.recC = st.rec[2].data();
+    const uint32_t *key = st.key.data(), *cellx = st.cellx.data(), *cs = st.cell_start.data();
+    // density pass (in place), then force pass (new velocity into alt)
+    if (v == WALK) {
+        launch(n, [&] { walk_thread<DIM, DensityOp>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, &counters[0]); });
+        launch(n, [&] { walk_thread<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, &counters[1]); });
+    } else if (v == LIST_Q10) {
+        launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q10>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cf, pl); });
+        launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cf, pl); });
+    } else if (v == LIST_F64) {
+        launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_F64>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cf, pl); });
+        launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cf, pl); });
+    } else {
+        launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q10, true>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cf, pl); });
+        launch(n, [&] { k_binary_list<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cf, pl); });
+    }
+    r.pairs_density = counters[0];
+    r.pairs_force = counters[1];
+    r.overflow = counters[2];
+    // back to reference index order
+    for (int k = 0; k < 9; ++k) {
+        r.fields[k].resize(n);
+        for (int64_t p = 0; p < n; ++p) r.fields[k][st.idx[p]] = st.cur[WRITTEN[k]][p];
+    }
+    for (int k = 0; k < 3; ++k) {
+        r.vnew[k].assign(n, 0.0);
+        if (k < DIM)
+            for (int64_t p = 0; p < n; ++p) r.vnew[k][st.idx[p]] = st.alt[S_V0 + k][p];
+    }
+    return r;
+}
+
+static void read_exact(FILE *fp, void *dst, size_t bytes) {
+    if (bytes && fread(dst, 1, bytes, fp) != bytes) {
+        fprintf(stderr, "emu_pairs: truncated input\n");
+        exit(2);
+    }
+}
+
+int main(int argc, char **argv) {
+    if (argc != 3) {
+        fprintf(stderr, "usage: emu_pairs <input.bin> <output.bin>\n");
+        return 2;
+    }
+    FILE *fp = fopen(argv[1], "rb");
+    if (!fp) {
+        perror(argv[1]);
+        return 2;
+    }
+    int32_t head[4];  // fast, stride, cx_shift (-1: library default), nparams
+    int64_t n;
+    double box[7];  // min[3], max[3], h
+    read_exact(fp, head, sizeof(head));
+    read_exact(fp, &n, sizeof(n));
+    read_exact(fp, box, sizeof(box));
+    const int fast = head[0], stride = head[1], nparams = head[3];
+    if (head[2] >= 0) setenv("SPHMW_CX_SHIFT", std::to_string(head[2]).c_str(), 1);
+    Params prm;
+    memset(&prm, 0, sizeof(prm));
+    struct Named {
+        const char *name;
+        double Params::*field;
+    };
+    static const Named TABLE[] = {{"dt", &Params::dt}, {"g", &Params::g}, {"c", &Params::c}, {"gamma", &Params::gamma},
+                                  {"alpha", &Params::alpha}, {"beta", &Params::beta}, {"eps", &Params::eps},
+                                  {"eta", &Params::eta}, {"rho0", &Params::rho0}, {"R_mass", &Params::R_mass},
+                                  {"R_gas", &Params::R_gas}, {"T_bg", &Params::T_bg}, {"rho_floor", &Params::rho_floor},
+                                  {"P_floor", &Params::P_floor}, {"z_t", &Params::z_t}, {"z_b", &Params::z_b},
+                                  {"gamma_r", &Params::gamma_r}, {"fluid", &Params::fluid}};
+    for (int k = 0; k < nparams; ++k) {
+        char name[16];
+        double value;
+        read_exact(fp, name, 16);
+        read_exact(fp, &value, sizeof(value));
+        name[15] = 0;
+        for (const Named &t : TABLE)
+            if (!strcmp(t.name, name)) prm.*(t.field) = value;
+    }
+    sphmw_derive_params(prm);
+    Grid g;
+    memset(&g, 0, sizeof(g));
+    int64_t global_cols = 0;
+    if (sphmw_grid_setup(g, box, box + 3, box[6], -1, -1, &global_cols) != SPHMW_OK) return 3;
+    const int dim = g.dim;
+
+    // fields in reference index order, component-major
+    const int IN_SLOTS[] = {S_X0, S_X1, S_X2, S_V0, S_V1, S_V2, S_M, S_H, S_RHO, S_RHO_P, S_TYPE};
+    std::vector<double> in[11];
+    for (int k = 0; k < 11; ++k) {
+        in[k].resize(n);
+        read_exact(fp, in[k].data(), sizeof(double) * n);
+    }
+    fclose(fp);
+
+    // ---- cell list: keys (structs.jl:97-106), order (cell ascending, index descending) --------
+    std::vector<uint32_t> pkey(n), col(n), order(n);
+    for (int64_t i = 0; i < n; ++i) {
+        const long long ci = (long long)floor(in[0][i] / g.h) - g.phase[0];
+        const long long cj = (long long)floor(in[1][i] / g.h) - g.phase[1];
+        const long long ck = dim == 3 ? (long long)floor(in[2][i] / g.h) - g.phase[2] : 0;
+        if (ci < 0 || ci >= g.lim[0] || cj < 0 || cj >= g.lim[1] || ck < 0 || ck >= g.lim[2]) {
+            fprintf(stderr, "emu_pairs: particle %lld is outside the box (not supported here)\n", (long long)i);
+            return 3;
+        }
+        pkey[i] = pkey_of(g, (int)ci, (int)(cj + g.lim[1] * ck));
+        col[i] = (uint32_t)ci;
+    }
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(),
+              [&](uint32_t a, uint32_t b) { return pkey[a] != pkey[b] ? pkey[a] < pkey[b] : a > b; });
+    State st;
+    st.n = n;
+    st.key.resize(n);
+    st.cellx.resize(n);
+    st.idx.resize(n);
+    st.xq.assign(n + 4, 0u);
+    st.cell_start.assign(g.pkey_max + 2, 0u);
+    for (int s = 0; s < NSLOT; ++s) {
+        st.cur[s].assign(n, 0.0);
+        st.alt[s].assign(n, 0.0);
+    }
+    for (int k = 0; k < 3; ++k) st.rec[k].assign(n, NbRec{0, 0, 0, 0});
+    for (int64_t p = 0; p < n; ++p) {
+        const uint32_t i = order[p];
+        st.idx[p] = i;
+        st.key[p] = pkey[i];
+        st.cellx[p] = col[i];
+        st.cell_start[pkey[i] + 1] += 1;
+        for (int k = 0; k < 11; ++k) st.cur[IN_SLOTS[k]][p] = in[k][i];
+        uint32_t w = 0;
+        for (int a = 0; a < dim; ++a) w |= nl_q10_axis(in[a][i], g.h) << (10 * a);
+        st.xq[p] = w;
+        st.rec[0][p] = NbRec{in[0][i], in[1][i], dim == 3 ? in[2][i] : 0.0, in[6][i]};
+    }
+    for (long long c = 0; c <= g.pkey_max; ++c) st.cell_start[c + 1] += st.cell_start[c];
+    const size_t warps = (size_t)((n + 31) / 32);
+    st.list.assign(warps * (size_t)stride * 32, 0u);
+    st.cnt.assign(n, 0u);
+
+    // ---- the variants --------------------------------------------------------------------------
+    auto run = [&](Variant v) -> Result {
+        if (dim == 2)
+            return fast ? run_variant<2, B_wcsph_density_fast, B_wcsph_momentum_fast>(st, g, prm, v, stride)
+                        : run_variant<2, B_wcsph_density_fused, B_wcsph_momentum_fused>(st, g, prm, v, stride);
+        return fast ? run_variant<3, B_wcsph_density_fast, B_wcsph_momentum_fast>(st, g, prm, v, stride)
+                    : run_variant<3, B_wcsph_density_fused, B_wcsph_momentum_fused>(st, g, prm, v, stride);
+    };
+    const Result base = run(WALK);
+    static const char *NAMES[] = {"walk", "list", "list_f64", "records"};
+    unsigned long long overflow = 0;
+    for (Variant v : {LIST_Q10, LIST_F64, RECORDS}) {
+        const Result r = run(v);
+        if (!r.same_as(base)) {
+            fprintf(stderr, "emu_pairs: variant '%s' differs from the cell walk (pairs %llu/%llu vs %llu/%llu)\n",
+                    NAMES[v], r.pairs_density, r.pairs_force, base.pairs_density, base.pairs_force);
+            return 1;
+        }
+        overflow = std::max(overflow, r.overflow);
+    }
+    FILE *out = fopen(argv[2], "wb");
+    if (!out) {
+        perror(argv[2]);
+        return 2;
+    }
+    const int64_t meta[6] = {n, dim, (int64_t)base.pairs_density, (int64_t)base.pairs_force, (int64_t)overflow,
+                             g.cx_shift};
+    fwrite(meta, sizeof(meta), 1, out);
+    for (int k = 0; k < 7; ++k) fwrite(base.fields[k].data(), sizeof(double), n, out);  // rho .. P
+    for (int k = 0; k < 3; ++k) fwrite(base.vnew[k].data(), sizeof(double), n, out);
+    fclose(out);
+    printf("emu_pairs: n=%lld dim=%d pairs=%llu overflow=%llu cx_shift=%d: walk == list == list_f64 == records\n",
+           (long long)n, dim, base.pairs_force, overflow, g.cx_shift);
+    return 0;
+}
