@@ -73,15 +73,44 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md).  The timed region
+    of the default run is about half a second, so the samples come from NVML in-process every
+    20 ms when pynvml is importable (the same counters nvidia-smi prints); nvidia-smi every 200 ms
+    otherwise."""
 
     def __init__(self, index: int):
         self.index = index
         self.samples = []
+        self.source = "nvidia-smi"
         self._stop = threading.Event()
         self._t = None
 
+    def _run_nvml(self) -> bool:
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        except Exception:
+            return False
+        self.source = "nvml"
+        bits = (N.nvmlClocksThrottleReasonHwSlowdown, N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                N.nvmlClocksThrottleReasonSwThermalSlowdown, N.nvmlClocksThrottleReasonSwPowerCap)
+        while not self._stop.is_set():
+            try:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+        return True
+
     def _run(self):
+        if self._run_nvml():
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -114,7 +143,7 @@ class ClockSampler:
         reasons = sorted({names[i] for s in self.samples for i in range(4)
                           if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
 # --------------------------------------------------------------------------- CPU arm
