@@ -29,54 +29,6 @@
 // ===========================================================================
 #define FLD(slot) f.s[slot][p]
 
-// accelerate!  wcsph_perturbed_witch.jl:298-303 (+ buyoancy_force :253-256,
-// damping_structure :245-251).  Vector arithmetic per component, as StaticArrays
-// does: ((-g*e_a)*rho')/rho, e = VECY.
-template <bool HAS_DV>
-struct U_wcsph_accelerate {
-    template <int DIM>
-    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
-        if (FLD(S_TYPE) == c.fluid) {
-            const double rho_p = FLD(S_RHO_P), rho = FLD(S_RHO);
-            const bool sponge = FLD(S_X1) >= c.sponge_z0;
-            const double hdt = 0.5 * c.dt;
-            {
-                double dv = HAS_DV ? FLD(S_DV0) : 0.0;
-                double buoy = -c.g * 0.0 * rho_p / rho;
-                double damp = sponge ? c.sponge_y * 0.0 : 0.0;
-                FLD(S_V0) += hdt * (dv + buoy + damp);
-            }
-            {
-                double dv = HAS_DV ? FLD(S_DV1) : 0.0;
-                double buoy = -c.g * 1.0 * rho_p / rho;
-                double damp = sponge ? c.sponge_y * 1.0 : 0.0;
-                FLD(S_V1) += hdt * (dv + buoy + damp);
-            }
-            if (DIM == 3) {
-                double dv = HAS_DV ? FLD(S_DV2) : 0.0;
-                double buoy = -c.g * 0.0 * rho_p / rho;
-                double damp = sponge ? c.sponge_y * 0.0 : 0.0;
-                FLD(S_V2) += hdt * (dv + buoy + damp);
-            }
-        }
-        if (HAS_DV) {
-            FLD(S_DV0) = 0.0;
-            FLD(S_DV1) = 0.0;
-            if (DIM == 3) FLD(S_DV2) = 0.0;
-        }
-    }
-};
-// move!  :292-296
-struct U_wcsph_move {
-    template <int DIM>
-    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
-        if (FLD(S_TYPE) == c.fluid) {
-            FLD(S_X0) += c.dt * FLD(S_V0);
-            FLD(S_X1) += c.dt * FLD(S_V1);
-            if (DIM == 3) FLD(S_X2) += c.dt * FLD(S_V2);
-        }
-    }
-};
 // reset_density!  :220-223
 struct U_wcsph_reset_density {
     template <int DIM>

@@ -11,6 +11,10 @@
 // result of the first one is written out so that the Python test can compare it with the oracle
 // (-ffp-contract=off and the same libm: strict arithmetic is expected to match exactly).
 //
+// With nsteps > 0 in the input header it instead runs whole verlet_step!s (:309-332) — accelerate!,
+// move!, cell list, density pass, force pass + kick — cycling through the four variants, and
+// writes x, v, rho, h after the last step.
+//
 // usage: emu_pairs <input.bin> <output.bin>
 #include <stdarg.h>
 #include <stdio.h>
@@ -159,13 +163,13 @@ int main(int argc, char **argv) {
         perror(argv[1]);
         return 2;
     }
-    int32_t head[4];  // fast, stride, cx_shift (-1: library default), nparams
+    int32_t head[6];  // fast, stride, cx_shift (-1: library default), nparams, nsteps, reserved
     int64_t n;
     double box[7];  // min[3], max[3], h
     read_exact(fp, head, sizeof(head));
     read_exact(fp, &n, sizeof(n));
     read_exact(fp, box, sizeof(box));
-    const int fast = head[0], stride = head[1], nparams = head[3];
+    const int fast = head[0], stride = head[1], nparams = head[3], nsteps = head[4];
     if (head[2] >= 0) setenv("SPHMW_CX_SHIFT", std::to_string(head[2]).c_str(), 1);
     Params prm;
     memset(&prm, 0, sizeof(prm));
@@ -205,6 +209,7 @@ int main(int argc, char **argv) {
     fclose(fp);
 
     // ---- cell list: keys (structs.jl:97-106), order (cell ascending, index descending) --------
+    auto build_state = [&](State &st) -> int {
     std::vector<uint32_t> pkey(n), col(n), order(n);
     for (int64_t i = 0; i < n; ++i) {
         const long long ci = (long long)floor(in[0][i] / g.h) - g.phase[0];
@@ -220,7 +225,6 @@ int main(int argc, char **argv) {
     std::iota(order.begin(), order.end(), 0u);
     std::sort(order.begin(), order.end(),
               [&](uint32_t a, uint32_t b) { return pkey[a] != pkey[b] ? pkey[a] < pkey[b] : a > b; });
-    State st;
     st.n = n;
     st.key.resize(n);
     st.cellx.resize(n);
@@ -248,6 +252,10 @@ int main(int argc, char **argv) {
     const size_t warps = (size_t)((n + 31) / 32);
     st.list.assign(warps * (size_t)stride * 32, 0u);
     st.cnt.assign(n, 0u);
+    return 0;
+    };
+    State st;
+    if (build_state(st)) return 3;
 
     // ---- the variants --------------------------------------------------------------------------
     auto run = [&](Variant v) -> Result {
@@ -257,6 +265,48 @@ int main(int argc, char **argv) {
         return fast ? run_variant<3, B_wcsph_density_fast, B_wcsph_momentum_fast>(st, g, prm, v, stride)
                     : run_variant<3, B_wcsph_density_fused, B_wcsph_momentum_fused>(st, g, prm, v, stride);
     };
+    if (nsteps > 0) {
+        // master copy stays in reference index order; kick and drift are per-particle
+        Fields master{};
+        for (int k = 0; k < 11; ++k) master.s[IN_SLOTS[k]] = in[k].data();
+        unsigned long long pairs = 0;
+        for (int step = 0; step < nsteps; ++step) {
+            launch(n, [&] {
+                const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+                if (p >= n) return;
+                if (dim == 2) {
+                    U_wcsph_accelerate<false>::apply<2>(master, prm, p);
+                    U_wcsph_move::apply<2>(master, prm, p);
+                } else {
+                    U_wcsph_accelerate<false>::apply<3>(master, prm, p);
+                    U_wcsph_move::apply<3>(master, prm, p);
+                }
+            });
+            st = State();
+            if (build_state(st)) return 3;
+            const Result r = run((Variant)(step % 4));
+            pairs = r.pairs_force;
+            for (int64_t i = 0; i < n; ++i) {
+                in[8][i] = r.fields[0][i];   // rho
+                in[9][i] = r.fields[2][i];   // rho'
+                in[7][i] = r.fields[3][i];   // h
+                for (int a = 0; a < 3; ++a) in[3 + a][i] = r.vnew[a][i];
+            }
+        }
+        FILE *out = fopen(argv[2], "wb");
+        if (!out) {
+            perror(argv[2]);
+            return 2;
+        }
+        const int64_t meta[6] = {n, dim, (int64_t)pairs, (int64_t)pairs, 0, g.cx_shift};
+        fwrite(meta, sizeof(meta), 1, out);
+        for (int k : {8, 9, 9, 7, 9, 9, 9}) fwrite(in[k].data(), sizeof(double), n, out);  // rho, -, -, h, -, -, -
+        for (int k = 0; k < 3; ++k) fwrite(in[3 + k].data(), sizeof(double), n, out);       // v
+        for (int k = 0; k < 3; ++k) fwrite(in[k].data(), sizeof(double), n, out);           // x
+        fclose(out);
+        printf("emu_pairs: %d steps, n=%lld dim=%d pairs=%llu\n", nsteps, (long long)n, dim, pairs);
+        return 0;
+    }
     const Result base = run(WALK);
     static const char *NAMES[] = {"walk", "list", "list_f64", "records"};
     unsigned long long overflow = 0;

@@ -45,11 +45,11 @@ def emu_binary():
     return out
 
 
-def run_emulation(binary, tmp_path, case, fields, fast, stride, cx_shift=-1):
+def run_emulation(binary, tmp_path, case, fields, fast, stride, cx_shift=-1, nsteps=0):
     n = len(fields["m"])
     inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
     with open(inp, "wb") as fp:
-        fp.write(struct.pack("<4i", int(fast), int(stride), int(cx_shift), len(PARAMS)))
+        fp.write(struct.pack("<6i", int(fast), int(stride), int(cx_shift), len(PARAMS), int(nsteps), 0))
         fp.write(struct.pack("<q", n))
         fp.write(struct.pack("<7d", *case.box_min, *case.box_max, case.h))
         for name in PARAMS:
@@ -64,10 +64,12 @@ def run_emulation(binary, tmp_path, case, fields, fast, stride, cx_shift=-1):
     assert r.returncode == 0, r.stderr + r.stdout
     raw = outp.read_bytes()
     meta = struct.unpack("<6q", raw[:48])
-    arr = np.frombuffer(raw[48:], dtype="<f8").reshape(10, n)
+    arr = np.frombuffer(raw[48:], dtype="<f8").reshape(-1, n)
     names = ["rho", "rho_bg", "rho_p", "h", "P_bg", "P_p", "P"]
     out = {k: arr[i] for i, k in enumerate(names)}
     out["v"] = arr[7:10].T
+    if nsteps:   # whole steps: only rho, h, v and x are meaningful
+        out = {"rho": arr[0], "h": arr[3], "v": arr[7:10].T, "x": arr[10:13].T}
     return dict(n=meta[0], dim=meta[1], pairs_density=meta[2], pairs_force=meta[3], overflow=meta[4],
                 cx_shift=meta[5]), out
 
@@ -87,7 +89,6 @@ def finish_step(o):
     o.create_cell_list()
     for op in POST:
         o.apply(op)
-    pairs = o.pair_count() if False else None
     o.apply("wcsph.balance_of_momentum")
     pairs = o.pair_count()
     o.apply("wcsph.accelerate")
@@ -144,4 +145,21 @@ def test_disordered_particles(emu_binary, tmp_path):
     pairs = finish_step(o)
     assert meta["pairs_force"] == pairs
     for f in ("rho", "h", "P", "v"):
+        assert n_mismatch(got[f], o.field(f)) == 0, f
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_whole_steps_equal_the_oracle_bit_for_bit(emu_binary, tmp_path, name):
+    """25 fused steps (accelerate!, move!, cell list, density pass, force pass + kick), the pair
+    passes cycling through walk / list / list_f64 / records: x, v, rho, h of every particle equal
+    the oracle's verlet_step! sequence exactly"""
+    case = CASES[name]()
+    fields = {k: case.fields[k] for k in ("x", "v", "m", "h", "rho", "rho_p", "type")}
+    nsteps = 25
+    meta, got = run_emulation(emu_binary, tmp_path, case, fields, fast=0, stride=40, nsteps=nsteps)
+    o = load_oracle(case)
+    o.create_cell_list()
+    o.step("wcsph", nsteps)
+    assert len(o) == case.n == meta["n"]
+    for f in ("x", "v", "rho", "h"):
         assert n_mismatch(got[f], o.field(f)) == 0, f
