@@ -16,6 +16,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "cell_gather.cuh"
 #include "sphmw_internal.h"
 
 // ---------------------------------------------------------------------------
@@ -230,52 +231,6 @@ __global__ void k_cell_order(const uint32_t *__restrict__ cell_start, int64_t nc
         }
         src[j] = s;
     }
-}
-
-struct GatherList {
-    const double *from[NSLOT];
-    double *to[NSLOT];
-    int count;
-    // quantised mirror of the sorted positions (pair_list.cuh): where the particle sits inside
-    // its own cell, 10 bits per axis (h/1024)
-    int xpos[3];  // entry of x0/x1/x2 in the lists above (-1: no such component)
-    double h;
-    uint32_t *xq;
-    // packed neighbour record A {x, y, z, m} (SPHMW_FLAG_PACKED_RECORDS; null otherwise)
-    int mpos;
-    NbRec *recA;
-};
-
-__global__ void k_gather(GatherList gl, const uint32_t *__restrict__ src,
-                         const uint32_t *__restrict__ idx, uint32_t *__restrict__ idx_out,
-                         uint32_t *__restrict__ pos_of_idx, const uint32_t *__restrict__ key,
-                         uint32_t *__restrict__ key_out, const uint32_t *__restrict__ tag,
-                         uint32_t *__restrict__ tag_out, const uint32_t *__restrict__ cellx,
-                         uint32_t *__restrict__ cellx_out, int64_t n_new) {
-    int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (slot >= n_new) return;
-    uint32_t s = src[slot];
-    uint32_t id = idx[s];
-    idx_out[slot] = id;
-    if (pos_of_idx) pos_of_idx[id] = (uint32_t)slot;
-    key_out[slot] = key[s];
-    tag_out[slot] = tag[s];
-    cellx_out[slot] = cellx[s];
-    uint32_t qm = 0;
-    double ra[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int f = 0; f < gl.count; ++f) {
-        const double v = gl.from[f][s];
-        gl.to[f][slot] = v;
-        if (f == gl.mpos) ra[3] = v;
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-            if (f == gl.xpos[a]) {
-                ra[a] = v;
-                qm |= nl_q10_axis(v, gl.h) << (10 * a);
-            }
-    }
-    gl.xq[slot] = qm;
-    if (gl.recA) nb_store(gl.recA + slot, ra[0], ra[1], ra[2], ra[3]);
 }
 
 __global__ void k_renumber(uint32_t *__restrict__ idx, const uint32_t *__restrict__ pos_of_idx,

@@ -1,6 +1,6 @@
 // CPU emulation harness of the pair kernels of libsphmw — TEST INFRASTRUCTURE, never shipped.
 //
-// Compiles the device headers (csrc/pair_list.cuh, wcsph_ops.cuh, kernels_sph.cuh) with g++
+// Compiles the device headers (csrc/pair_list.cuh, wcsph_ops.cuh, kernels_sph.cuh, cell_gather.cuh) with g++
 // against tests/emu/cuda_runtime.h and runs the kernels one "thread" at a time:
 //   walk        the cell walk of _apply_binary! (src/core.jl:94-112), as k_binary does it
 //   list        k_binary_build (integer pre-test) + k_binary_list
@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "cuda_runtime.h"
+#include "cell_gather.cuh"
 #include "pair_list.cuh"
 #include "sphmw_internal.h"
 #include "wcsph_ops.cuh"
@@ -236,17 +237,38 @@ int main(int argc, char **argv) {
         st.alt[s].assign(n, 0.0);
     }
     for (int k = 0; k < 3; ++k) st.rec[k].assign(n, NbRec{0, 0, 0, 0});
-    for (int64_t p = 0; p < n; ++p) {
-        const uint32_t i = order[p];
-        st.idx[p] = i;
-        st.key[p] = pkey[i];
-        st.cellx[p] = col[i];
-        st.cell_start[pkey[i] + 1] += 1;
-        for (int k = 0; k < 11; ++k) st.cur[IN_SLOTS[k]][p] = in[k][i];
-        uint32_t w = 0;
-        for (int a = 0; a < dim; ++a) w |= nl_q10_axis(in[a][i], g.h) << (10 * a);
-        st.xq[p] = w;
-        st.rec[0][p] = NbRec{in[0][i], in[1][i], dim == 3 ? in[2][i] : 0.0, in[6][i]};
+    // the permutation itself is the library's k_gather (csrc/cell_gather.cuh): fields, indices,
+    // keys, the pre-test mirror and neighbour record A
+    for (int64_t i = 0; i < n; ++i) st.cell_start[pkey[i] + 1] += 1;
+    {
+        std::vector<uint32_t> ident(n), tag_in(n, 0u), tag_out(n), pos_of_idx(n);
+        std::iota(ident.begin(), ident.end(), 0u);
+        GatherList gl;
+        memset(&gl, 0, sizeof(gl));
+        gl.count = 0;
+        for (int a = 0; a < 3; ++a) gl.xpos[a] = -1;
+        gl.mpos = -1;
+        for (int k = 0; k < 11; ++k) {
+            const int slot = IN_SLOTS[k];
+            if (dim == 2 && (slot == S_X2 || slot == S_V2)) continue;  // 2D systems keep no third component
+            gl.from[gl.count] = in[k].data();
+            gl.to[gl.count] = st.cur[slot].data();
+            if (slot >= S_X0 && slot <= S_X2) gl.xpos[slot - S_X0] = gl.count;
+            if (slot == S_M) gl.mpos = gl.count;
+            ++gl.count;
+        }
+        gl.h = g.h;
+        gl.xq = st.xq.data();
+        gl.recA = st.rec[0].data();
+        launch(n, [&] {
+            k_gather(gl, order.data(), ident.data(), st.idx.data(), pos_of_idx.data(), pkey.data(), st.key.data(),
+                     tag_in.data(), tag_out.data(), col.data(), st.cellx.data(), n);
+        });
+        for (int64_t p = 0; p < n; ++p)
+            if (pos_of_idx[st.idx[p]] != (uint32_t)p) {
+                fprintf(stderr, "emu_pairs: k_gather left an inconsistent inverse map\n");
+                return 3;
+            }
     }
     for (long long c = 0; c <= g.pkey_max; ++c) st.cell_start[c + 1] += st.cell_start[c];
     const size_t warps = (size_t)((n + 31) / 32);

@@ -2,7 +2,7 @@
 against the oracle — no GPU needed.
 
 tests/emu/emu_pairs.cpp includes the very headers nvcc compiles (csrc/pair_list.cuh,
-wcsph_ops.cuh, kernels_sph.cuh, sphmw_internal.h; csrc/grid_setup.cpp) behind a stand-in
+wcsph_ops.cuh, kernels_sph.cuh, cell_gather.cuh, sphmw_internal.h; csrc/grid_setup.cpp) behind a stand-in
 <cuda_runtime.h>, builds the cell-sorted layout, and runs the two fused passes of verlet_step!
 (wcsph_perturbed_witch.jl:316-331) four ways: the cell walk, the recorded/replayed pair list with
 the integer and with the FP64 pre-test, and the packed-record variant.  It exits non-zero unless
@@ -37,7 +37,7 @@ def emu_binary():
     out = EMU / "build" / "emu_pairs"
     out.parent.mkdir(exist_ok=True)
     deps = [EMU / "emu_pairs.cpp", EMU / "cuda_runtime.h", CSRC / "pair_list.cuh", CSRC / "wcsph_ops.cuh",
-            CSRC / "kernels_sph.cuh", CSRC / "sphmw_internal.h", CSRC / "grid_setup.cpp"]
+            CSRC / "kernels_sph.cuh", CSRC / "cell_gather.cuh", CSRC / "sphmw_internal.h", CSRC / "grid_setup.cpp"]
     if not out.exists() or any(d.stat().st_mtime > out.stat().st_mtime for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wno-attributes", "-DSPHMW_EMU",
                         f"-I{EMU}", f"-I{ROOT / 'include'}", f"-I{CSRC}", str(EMU / "emu_pairs.cpp"),
