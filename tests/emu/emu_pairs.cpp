@@ -87,7 +87,8 @@ struct State {
 static const int WRITTEN[] = {S_RHO, S_RHO_BG, S_RHO_P, S_H, S_P_BG, S_P_P, S_P, S_PR2, S_CS};
 
 struct Result {
-    std::vector<double> fields[9], vnew[3];
+    std::vector<double> fields[9], vnew[3], vold[3];
+    std::vector<uint32_t> column;  // cell column of every particle (reference index order)
     unsigned long long pairs_density = 0, pairs_force = 0, overflow = 0;
     bool same_as(const Result &o) const {
         for (int k = 0; k < 9; ++k)
@@ -98,7 +99,7 @@ struct Result {
     }
 };
 
-enum Variant { WALK, LIST_Q10, LIST_F64, RECORDS };
+enum Variant { WALK, LIST_Q10, LIST_F64, RECORDS, SLAB_LIST, SLAB_RECORDS };
 
 template <int DIM, class DensityOp, class ForceOp>
 static Result run_variant(State st, const Grid &g, const Params &prm, Variant v, int stride) {
@@ -127,9 +128,26 @@ static Result run_variant(State st, const Grid &g, const Params &prm, Variant v,
     } else if (v == LIST_F64) {
         launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_F64>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cf, pl); });
         launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cf, pl); });
-    } else {
+    } else if (v == RECORDS) {
         launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q10, true>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cf, pl); });
         launch(n, [&] { k_binary_list<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cf, pl); });
+    } else {
+        // the column filters of a slab context (pair_ops.cu filter_for_depth): the density pass
+        // covers all but the outermost column of each side, the force pass all but the outermost
+        // two (split into two launches like the overlapped schedule); skipped particles carry
+        // their velocity over.  Compared with the cell walk on the columns that were evaluated.
+        const int W = (int)g.lim[0];
+        const ColFilter cd{1, 1, W - 2, 1, 0, 1};
+        const ColFilter cedge{1, 2, 3, W - 4, W - 3, 1}, cint{1, 4, W - 5, 1, 0, 0};
+        if (v == SLAB_LIST) {
+            launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q10>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cd, pl); });
+            launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge, pl); });
+            launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[3], cint, pl); });
+        } else {
+            launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q10, true>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cd, pl); });
+            launch(n, [&] { k_binary_list<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge, pl); });
+            launch(n, [&] { k_binary_list<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[3], cint, pl); });
+        }
     }
     r.pairs_density = counters[0];
     r.pairs_force = counters[1];
@@ -141,9 +159,15 @@ static Result run_variant(State st, const Grid &g, const Params &prm, Variant v,
     }
     for (int k = 0; k < 3; ++k) {
         r.vnew[k].assign(n, 0.0);
+        r.vold[k].assign(n, 0.0);
         if (k < DIM)
-            for (int64_t p = 0; p < n; ++p) r.vnew[k][st.idx[p]] = st.alt[S_V0 + k][p];
+            for (int64_t p = 0; p < n; ++p) {
+                r.vnew[k][st.idx[p]] = st.alt[S_V0 + k][p];
+                r.vold[k][st.idx[p]] = st.cur[S_V0 + k][p];
+            }
     }
+    r.column.resize(n);
+    for (int64_t p = 0; p < n; ++p) r.column[st.idx[p]] = st.cellx[p];
     return r;
 }
 
@@ -330,7 +354,7 @@ int main(int argc, char **argv) {
         return 0;
     }
     const Result base = run(WALK);
-    static const char *NAMES[] = {"walk", "list", "list_f64", "records"};
+    static const char *NAMES[] = {"walk", "list", "list_f64", "records", "slab_list", "slab_records"};
     unsigned long long overflow = 0;
     for (Variant v : {LIST_Q10, LIST_F64, RECORDS}) {
         const Result r = run(v);
@@ -340,6 +364,28 @@ int main(int argc, char **argv) {
             return 1;
         }
         overflow = std::max(overflow, r.overflow);
+    }
+    if (g.lim[0] >= 10) {
+        const int W = (int)g.lim[0];
+        for (Variant v : {SLAB_LIST, SLAB_RECORDS}) {
+            const Result r = run(v);
+            for (int64_t i = 0; i < n; ++i) {
+                const int c = (int)r.column[i];
+                bool ok = true;
+                if (c >= 1 && c <= W - 2)
+                    for (int k = 0; k < 9; ++k) ok = ok && !memcmp(&r.fields[k][i], &base.fields[k][i], sizeof(double));
+                for (int k = 0; k < 3; ++k) {
+                    const double want = (c >= 2 && c <= W - 3) ? base.vnew[k][i] : r.vold[k][i];
+                    // interior launch has copy = 0: columns 0, 1, W-2, W-1 are copied by the edge launch
+                    ok = ok && !memcmp(&r.vnew[k][i], &want, sizeof(double));
+                }
+                if (!ok) {
+                    fprintf(stderr, "emu_pairs: slab-filtered variant %d differs at particle %lld (column %d of %d)\n",
+                            (int)v, (long long)i, c, W);
+                    return 1;
+                }
+            }
+        }
     }
     FILE *out = fopen(argv[2], "wb");
     if (!out) {
@@ -352,7 +398,8 @@ int main(int argc, char **argv) {
     for (int k = 0; k < 7; ++k) fwrite(base.fields[k].data(), sizeof(double), n, out);  // rho .. P
     for (int k = 0; k < 3; ++k) fwrite(base.vnew[k].data(), sizeof(double), n, out);
     fclose(out);
-    printf("emu_pairs: n=%lld dim=%d pairs=%llu overflow=%llu cx_shift=%d: walk == list == list_f64 == records\n",
+    printf("emu_pairs: n=%lld dim=%d pairs=%llu overflow=%llu cx_shift=%d: walk == list == list_f64 == records"
+           " (== slab-filtered launches on their columns)\n",
            (long long)n, dim, base.pairs_force, overflow, g.cx_shift);
     return 0;
 }
