@@ -1031,8 +1031,16 @@ static int ensure_pair_list(sphmw_ctx *c) {
     if (stride < 4) stride = 4;
     if (stride > 96) stride = 96;  // 48 KB of queue per block
     const size_t warps = (size_t)((c->cap + 31) / 32);
-    CUDA_TRY(cudaMalloc(&c->pl.list, sizeof(uint32_t) * warps * (size_t)stride * 32));
-    CUDA_TRY(cudaMalloc(&c->pl.cnt, sizeof(uint32_t) * (size_t)c->cap));
+    uint32_t *list = nullptr, *cnt = nullptr;
+    if (cudaMalloc(&list, sizeof(uint32_t) * warps * (size_t)stride * 32) != cudaSuccess ||
+        cudaMalloc(&cnt, sizeof(uint32_t) * (size_t)c->cap) != cudaSuccess) {
+        cudaFree(list);
+        (void)cudaGetLastError();  // out of memory is not fatal here: the caller walks the cells instead
+        sphmw_set_error("no device memory for the pair list (%zu MB)", sizeof(uint32_t) * warps * (size_t)stride * 32 >> 20);
+        return SPHMW_E_CAPACITY;
+    }
+    c->pl.list = list;
+    c->pl.cnt = cnt;
     c->pl.stride = stride;
     c->pl.overflow = c->d_counters + 2;
     return SPHMW_OK;
@@ -1067,7 +1075,12 @@ static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Field
     if (pc) CUDA_TRY(cudaMemsetAsync(pc, 0, sizeof(unsigned long long), c->stream));
     const bool lists = !(c->flags & SPHMW_FLAG_NO_PAIR_LIST);
     const bool replay = lists && c->pl.list && c->pl_gen == c->cell_gen;
-    const bool record = lists && !replay && (c->want_list || (c->flags & SPHMW_FLAG_PAIR_LIST_EAGER));
+    bool record = lists && !replay && (c->want_list || (c->flags & SPHMW_FLAG_PAIR_LIST_EAGER));
+    if (record && ensure_pair_list(c) != SPHMW_OK) {
+        // the list is an optimisation: without memory for it every pass walks the cells
+        c->flags |= SPHMW_FLAG_NO_PAIR_LIST;
+        record = false;
+    }
     c->passes_this_gen += 1;
     const unsigned blocks = grid_for(c->n, NL_BLOCK);
     const bool rec = REC && c->rec[0] && c->rec[1] && c->rec[2] && c->rec_gen == c->cell_gen;
@@ -1090,7 +1103,6 @@ static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Field
         else
             k_binary_list<3, Op><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
     } else if (record) {
-        TRY(ensure_pair_list(c));
         c->pl.xq = c->xq;
         // pre-test of the recording pass: integers on the 10-bit cell-relative mirror, or
         // (SPHMW_FLAG_NO_PRETEST) the exact FP64 test only
