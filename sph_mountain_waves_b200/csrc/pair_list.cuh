@@ -14,6 +14,7 @@
 // stride, or that was outside the recording pass's column filter, has cnt == NL_NONE and
 // walks the cells with the original loop.
 #pragma once
+#include "q_access.cuh"
 #include "sphmw_internal.h"
 
 // the loop of k_binary, for particles without a list
@@ -80,7 +81,7 @@ __device__ __forceinline__ void nl_entry_rec_density(Op &op, const Params &prm, 
     }
     if ((r2 > g.r2_max) || (q == (uint32_t)p)) return;
     double r = sqrt(r2);
-    op.template pair_m<DIM>(prm, A.d, dx, dy, dz, r);
+    op.template pair_q<DIM>(prm, RecAQ{A.d}, dx, dy, dz, r);
     ++accepted;
 }
 // force closure: all three records are requested up front (the exact test rejects few entries)
@@ -101,7 +102,7 @@ __device__ __forceinline__ void nl_entry_rec_force(Op &op, const Params &prm, co
     }
     if ((r2 > g.r2_max) || (q == (uint32_t)p)) return;
     double r = sqrt(r2);
-    op.template pair_rec<DIM>(prm, A.d, B, C, dx, dy, dz, r);
+    op.template pair_q<DIM>(prm, RecQ{A.d, B, C}, dx, dy, dz, r);
     ++accepted;
 }
 

@@ -10,13 +10,9 @@
 #include <math.h>
 
 #include "kernels_sph.cuh"
+#include "q_access.cuh"
 #include "sphmw_internal.h"
 
-// Julia's max(a,b) propagates NaN (Base.max); fmax does not.
-__device__ __forceinline__ double jl_max(double a, double b) {
-    if (a != a || b != b) return a + b;
-    return a < b ? b : a;
-}
 
 // wcsph_perturbed_witch.jl:177-189
 __device__ __forceinline__ double background_density(const Params &c, double y) {
@@ -91,10 +87,72 @@ struct U_wcsph_move {
 struct PairOpBase {
     template <int DIM>
     static __device__ void skip(const Fields &, const Fields &, int64_t) {}
-    // packed neighbour records (pair_list.cuh): 0 the operator does not use them, 1 it has
-    // pair_m (needs record A), 2 it has pair_rec (needs A, B, C)
+    // packed neighbour records (pair_list.cuh): 0 the operator does not use them, 1 it needs
+    // record A, 2 it needs A, B, C
     static constexpr int REC_KIND = 0;
+    // shared-memory tiles (pair_tile.cuh): number of field arrays the operator stages (0: the
+    // operator has no tiled variant)
+    template <int DIM>
+    static constexpr int tile_fields() { return 0; }
 };
+
+// what the fused density pass leaves behind for p (shared by the strict and fast variants)
+template <int DIM>
+__device__ __forceinline__ void wcsph_density_finish(const Fields &f, const Params &c, int64_t p, double rho) {
+    double y = PF(S_X1);
+    double rbg = background_density(c, y);  // finalize_density!
+    double rho_p = rho - rbg;
+    double rfl = jl_max(rho, c.rho_floor);  // update_smoothing!
+    double m = PF(S_M);
+    double hn = DIM == 2 ? c.eta * sqrt(m / rfl) : c.eta * cbrt(m / rfl);
+    double pbg = c.R_mass * c.T_bg * rbg;  // compute_pressure! (same rho_bg(y) value)
+    double pp = sph_pow2(c.c) * rho_p;
+    double P = pbg + pp;
+    PF(S_RHO) = rho;
+    PF(S_RHO_BG) = rbg;
+    PF(S_RHO_P) = rho_p;
+    PF(S_H) = hn;
+    PF(S_P_BG) = pbg;
+    PF(S_P_P) = pp;
+    PF(S_P) = P;
+    PF(S_PR2) = pp / sph_pow2(rfl);
+    PF(S_CS) = sqrt(c.gamma * P / rfl);
+}
+// accelerate! folded into the force pass's finish() (wcsph_perturbed_witch.jl:298-303)
+template <int DIM>
+__device__ __forceinline__ void wcsph_force_finish(const Fields &f, const Fields &out, const Params &c, int64_t p,
+                                                   double v0, double v1, double v2, double dv0, double dv1,
+                                                   double dv2) {
+    double n0 = v0, n1 = v1, n2 = v2;
+    if (PF(S_TYPE) == c.fluid) {
+        const double rho_p = PF(S_RHO_P), rho = PF(S_RHO);
+        const bool sponge = PF(S_X1) >= c.sponge_z0;
+        const double hdt = 0.5 * c.dt;
+        n0 = v0 + hdt * (dv0 + -c.g * 0.0 * rho_p / rho + (sponge ? c.sponge_y * 0.0 : 0.0));
+        n1 = v1 + hdt * (dv1 + -c.g * 1.0 * rho_p / rho + (sponge ? c.sponge_y * 1.0 : 0.0));
+        if (DIM == 3)
+            n2 = v2 + hdt * (dv2 + -c.g * 0.0 * rho_p / rho + (sponge ? c.sponge_y * 0.0 : 0.0));
+    }
+    out.s[S_V0][p] = n0;
+    out.s[S_V1][p] = n1;
+    if (DIM == 3) out.s[S_V2][p] = n2;
+}
+
+// fields the two fused passes stage in a shared-memory tile (pair_tile.cuh), in array order.
+// Density: x, y, (z), m.  Force: x, y, (z), vx, vy, (vz), h, m, P'/rho^2 and, in 2D where the
+// tile is small, rho and c_s as well (3D: those two are gathered from global memory, only on the
+// artificial-viscosity branch).
+template <int DIM>
+__host__ __device__ constexpr int wcsph_density_tile_index(int slot) {
+    return slot == S_X0 ? 0 : slot == S_X1 ? 1 : (DIM == 3 && slot == S_X2) ? 2 : slot == S_M ? DIM : -1;
+}
+template <int DIM>
+__host__ __device__ constexpr int wcsph_force_tile_index(int slot) {
+    return slot == S_X0 ? 0 : slot == S_X1 ? 1 : (DIM == 3 && slot == S_X2) ? 2
+         : slot == S_V0 ? DIM : slot == S_V1 ? DIM + 1 : (DIM == 3 && slot == S_V2) ? DIM + 2
+         : slot == S_H ? 2 * DIM : slot == S_M ? 2 * DIM + 1 : slot == S_PR2 ? 2 * DIM + 2
+         : (DIM == 2 && slot == S_RHO) ? 2 * DIM + 3 : (DIM == 2 && slot == S_CS) ? 2 * DIM + 4 : -1;
+}
 
 // ---- fused operators of the fast path (sphmw_step, scheme "wcsph") --------
 // reset_density! + compute_density! + finalize_density! + update_smoothing! +
@@ -102,42 +160,28 @@ struct PairOpBase {
 // per-particle invariants of the pair force.
 struct B_wcsph_density_fused : PairOpBase {
     static constexpr int REC_KIND = 1;
+    template <int DIM>
+    static constexpr int tile_fields() { return DIM + 1; }
+    template <int DIM>
+    static constexpr int tile_index(int slot) { return wcsph_density_tile_index<DIM>(slot); }
     double rho, hp;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &, int64_t p) {
         rho = 0.0;  // reset_density!
         hp = PF(S_H);
     }
-    template <int DIM>
-    __device__ void pair(const Fields &f, const Params &, int64_t, int64_t q, double, double,
-                         double, double r) {
-        rho += QF(S_M) * sph_W<DIM>(hp, r);
+    template <int DIM, class Q>
+    __device__ void pair_q(const Params &, const Q &q, double, double, double, double r) {
+        rho += QG(S_M) * sph_W<DIM>(hp, r);
     }
-    // the same with the neighbour's mass out of its packed record (SPHMW_FLAG_PACKED_RECORDS)
     template <int DIM>
-    __device__ void pair_m(const Params &, double qm, double, double, double, double r) {
-        rho += qm * sph_W<DIM>(hp, r);
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        pair_q<DIM>(c, GlobalQ{f, q}, dx, dy, dz, r);
     }
     template <int DIM>
     __device__ void finish(const Fields &f, const Fields &, const Params &c, int64_t p) {
-        double y = PF(S_X1);
-        double rbg = background_density(c, y);  // finalize_density!
-        double rho_p = rho - rbg;
-        double rfl = jl_max(rho, c.rho_floor);  // update_smoothing!
-        double m = PF(S_M);
-        double hn = DIM == 2 ? c.eta * sqrt(m / rfl) : c.eta * cbrt(m / rfl);
-        double pbg = c.R_mass * c.T_bg * rbg;  // compute_pressure! (same rho_bg(y) value)
-        double pp = sph_pow2(c.c) * rho_p;
-        double P = pbg + pp;
-        PF(S_RHO) = rho;
-        PF(S_RHO_BG) = rbg;
-        PF(S_RHO_P) = rho_p;
-        PF(S_H) = hn;
-        PF(S_P_BG) = pbg;
-        PF(S_P_P) = pp;
-        PF(S_P) = P;
-        PF(S_PR2) = pp / sph_pow2(rfl);
-        PF(S_CS) = sqrt(c.gamma * P / rfl);
+        wcsph_density_finish<DIM>(f, c, p, rho);
     }
 };
 
@@ -146,6 +190,10 @@ struct B_wcsph_density_fused : PairOpBase {
 // goes to the `out` field set because other threads still read the old one.
 struct B_wcsph_momentum_fused : PairOpBase {
     static constexpr int REC_KIND = 2;
+    template <int DIM>
+    static constexpr int tile_fields() { return DIM == 2 ? 9 : 9; }
+    template <int DIM>
+    static constexpr int tile_index(int slot) { return wcsph_force_tile_index<DIM>(slot); }
     double dv0, dv1, dv2, v0, v1, v2, hp, prho, pr2, cs;
     // the velocity is double-buffered: a skipped (ghost) particle carries its value over
     template <int DIM>
@@ -165,78 +213,41 @@ struct B_wcsph_momentum_fused : PairOpBase {
         pr2 = PF(S_PR2);
         cs = PF(S_CS);
     }
+    template <int DIM, class Q>
+    __device__ void pair_q(const Params &c, const Q &q, double dx, double dy, double dz, double r) {
+        double vx = v0 - QG(S_V0), vy = v1 - QG(S_V1);
+        double dot_product = dx * vx + dy * vy;
+        if (DIM == 3) {
+            double vz = v2 - QG(S_V2);
+            dot_product = dot_product + dz * vz;
+        }
+        double h_ij = 0.5 * (hp + QG(S_H));
+        double ker = sph_rDW<DIM>(h_ij, r);
+        double qm = QG(S_M);
+        double fc = -qm * (pr2 + QG(S_PR2)) * ker;
+        dv0 += fc * dx;
+        dv1 += fc * dy;
+        if (DIM == 3) dv2 += fc * dz;
+        if (dot_product < 0.0) {
+            double qrho = q.rho_floored(c);
+            double c_ij = 0.5 * (cs + QG(S_CS));
+            double rho_ij = 0.5 * (prho + qrho);
+            double mu_ij = (h_ij * dot_product) / (r * r + c.eps * h_ij * h_ij);
+            double pi_ij = (-c.alpha * c_ij * mu_ij + c.beta * mu_ij * mu_ij) / rho_ij;
+            double fv = -qm * pi_ij * ker;
+            dv0 += fv * dx;
+            dv1 += fv * dy;
+            if (DIM == 3) dv2 += fv * dz;
+        }
+    }
     template <int DIM>
     __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
                          double dz, double r) {
-        double vx = v0 - QF(S_V0), vy = v1 - QF(S_V1);
-        double dot_product = dx * vx + dy * vy;
-        if (DIM == 3) {
-            double vz = v2 - QF(S_V2);
-            dot_product = dot_product + dz * vz;
-        }
-        double h_ij = 0.5 * (hp + QF(S_H));
-        double ker = sph_rDW<DIM>(h_ij, r);
-        double qm = QF(S_M);
-        double fc = -qm * (pr2 + QF(S_PR2)) * ker;
-        dv0 += fc * dx;
-        dv1 += fc * dy;
-        if (DIM == 3) dv2 += fc * dz;
-        if (dot_product < 0.0) {
-            double qrho = jl_max(QF(S_RHO), c.rho_floor);
-            double c_ij = 0.5 * (cs + QF(S_CS));
-            double rho_ij = 0.5 * (prho + qrho);
-            double mu_ij = (h_ij * dot_product) / (r * r + c.eps * h_ij * h_ij);
-            double pi_ij = (-c.alpha * c_ij * mu_ij + c.beta * mu_ij * mu_ij) / rho_ij;
-            double fv = -qm * pi_ij * ker;
-            dv0 += fv * dx;
-            dv1 += fv * dy;
-            if (DIM == 3) dv2 += fv * dz;
-        }
-    }
-    // the same with the neighbour's fields out of its packed records: qm = A.d,
-    // B = {vx, vy, vz, h}, C = {P'/rho^2, max(rho, rho_floor), c_s}
-    template <int DIM>
-    __device__ void pair_rec(const Params &c, double qm, const NbRec &B, const NbRec &C, double dx, double dy,
-                             double dz, double r) {
-        double vx = v0 - B.a, vy = v1 - B.b;
-        double dot_product = dx * vx + dy * vy;
-        if (DIM == 3) {
-            double vz = v2 - B.c;
-            dot_product = dot_product + dz * vz;
-        }
-        double h_ij = 0.5 * (hp + B.d);
-        double ker = sph_rDW<DIM>(h_ij, r);
-        double fc = -qm * (pr2 + C.a) * ker;
-        dv0 += fc * dx;
-        dv1 += fc * dy;
-        if (DIM == 3) dv2 += fc * dz;
-        if (dot_product < 0.0) {
-            double qrho = C.b;
-            double c_ij = 0.5 * (cs + C.c);
-            double rho_ij = 0.5 * (prho + qrho);
-            double mu_ij = (h_ij * dot_product) / (r * r + c.eps * h_ij * h_ij);
-            double pi_ij = (-c.alpha * c_ij * mu_ij + c.beta * mu_ij * mu_ij) / rho_ij;
-            double fv = -qm * pi_ij * ker;
-            dv0 += fv * dx;
-            dv1 += fv * dy;
-            if (DIM == 3) dv2 += fv * dz;
-        }
+        pair_q<DIM>(c, GlobalQ{f, q}, dx, dy, dz, r);
     }
     template <int DIM>
     __device__ void finish(const Fields &f, const Fields &out, const Params &c, int64_t p) {
-        double n0 = v0, n1 = v1, n2 = v2;
-        if (PF(S_TYPE) == c.fluid) {  // accelerate!
-            const double rho_p = PF(S_RHO_P), rho = PF(S_RHO);
-            const bool sponge = PF(S_X1) >= c.sponge_z0;
-            const double hdt = 0.5 * c.dt;
-            n0 = v0 + hdt * (dv0 + -c.g * 0.0 * rho_p / rho + (sponge ? c.sponge_y * 0.0 : 0.0));
-            n1 = v1 + hdt * (dv1 + -c.g * 1.0 * rho_p / rho + (sponge ? c.sponge_y * 1.0 : 0.0));
-            if (DIM == 3)
-                n2 = v2 + hdt * (dv2 + -c.g * 0.0 * rho_p / rho + (sponge ? c.sponge_y * 0.0 : 0.0));
-        }
-        out.s[S_V0][p] = n0;
-        out.s[S_V1][p] = n1;
-        if (DIM == 3) out.s[S_V2][p] = n2;
+        wcsph_force_finish<DIM>(f, out, c, p, v0, v1, v2, dv0, dv1, dv2);
     }
 };
 // ---- fast-arithmetic variants of the two fused passes (SPHMW_FLAG_FAST_MATH) ----------
@@ -257,6 +268,10 @@ __device__ __forceinline__ double fast_sqrt_pos(double a) {
 
 struct B_wcsph_density_fast : PairOpBase {
     static constexpr int REC_KIND = 1;
+    template <int DIM>
+    static constexpr int tile_fields() { return DIM + 1; }
+    template <int DIM>
+    static constexpr int tile_index(int slot) { return wcsph_density_tile_index<DIM>(slot); }
     double rho, hp, inv_h, cw;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &, int64_t p) {
@@ -266,9 +281,8 @@ struct B_wcsph_density_fast : PairOpBase {
         // 7/pi / h^2  or  21/(2 pi) / h^3
         cw = DIM == 2 ? 2.228169203286535 * (inv_h * inv_h) : 3.3422538049298023 * (inv_h * inv_h * inv_h);
     }
-    template <int DIM>
-    __device__ void pair(const Fields &f, const Params &, int64_t, int64_t q, double dx, double dy,
-                         double dz, double) {
+    template <int DIM, class Q>
+    __device__ void pair_q(const Params &, const Q &q, double dx, double dy, double dz, double) {
         double r2 = fma(dx, dx, dy * dy);
         if (DIM == 3) r2 = fma(dz, dz, r2);
         double x = fast_sqrt_pos(r2) * inv_h;
@@ -276,44 +290,25 @@ struct B_wcsph_density_fast : PairOpBase {
         double t = 1.0 - x;
         double t2 = t * t;
         double w = cw * (t2 * t2) * fma(4.0, x, 1.0);
-        rho = fma(QF(S_M), w, rho);
+        rho = fma(QG(S_M), w, rho);
     }
     template <int DIM>
-    __device__ void pair_m(const Params &, double qm, double dx, double dy, double dz, double) {
-        double r2 = fma(dx, dx, dy * dy);
-        if (DIM == 3) r2 = fma(dz, dz, r2);
-        double x = fast_sqrt_pos(r2) * inv_h;
-        if (x > 1.0) return;
-        double t = 1.0 - x;
-        double t2 = t * t;
-        double w = cw * (t2 * t2) * fma(4.0, x, 1.0);
-        rho = fma(qm, w, rho);
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        pair_q<DIM>(c, GlobalQ{f, q}, dx, dy, dz, r);
     }
     template <int DIM>
     __device__ void finish(const Fields &f, const Fields &, const Params &c, int64_t p) {
-        double y = PF(S_X1);
-        double rbg = background_density(c, y);
-        double rho_p = rho - rbg;
-        double rfl = jl_max(rho, c.rho_floor);
-        double m = PF(S_M);
-        double hn = DIM == 2 ? c.eta * sqrt(m / rfl) : c.eta * cbrt(m / rfl);
-        double pbg = c.R_mass * c.T_bg * rbg;
-        double pp = sph_pow2(c.c) * rho_p;
-        double P = pbg + pp;
-        PF(S_RHO) = rho;
-        PF(S_RHO_BG) = rbg;
-        PF(S_RHO_P) = rho_p;
-        PF(S_H) = hn;
-        PF(S_P_BG) = pbg;
-        PF(S_P_P) = pp;
-        PF(S_P) = P;
-        PF(S_PR2) = pp / sph_pow2(rfl);
-        PF(S_CS) = sqrt(c.gamma * P / rfl);
+        wcsph_density_finish<DIM>(f, c, p, rho);
     }
 };
 
 struct B_wcsph_momentum_fast : PairOpBase {
     static constexpr int REC_KIND = 2;
+    template <int DIM>
+    static constexpr int tile_fields() { return DIM == 2 ? 9 : 9; }
+    template <int DIM>
+    static constexpr int tile_index(int slot) { return wcsph_force_tile_index<DIM>(slot); }
     double dv0, dv1, dv2, v0, v1, v2, hp, prho, pr2, cs;
     template <int DIM>
     static __device__ void skip(const Fields &f, const Fields &out, int64_t p) {
@@ -332,16 +327,15 @@ struct B_wcsph_momentum_fast : PairOpBase {
         pr2 = PF(S_PR2);
         cs = PF(S_CS);
     }
-    template <int DIM>
-    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
-                         double dz, double) {
+    template <int DIM, class Q>
+    __device__ void pair_q(const Params &c, const Q &q, double dx, double dy, double dz, double) {
         double r2 = fma(dx, dx, dy * dy);
-        double dot_product = fma(dy, v1 - QF(S_V1), dx * (v0 - QF(S_V0)));
+        double dot_product = fma(dy, v1 - QG(S_V1), dx * (v0 - QG(S_V0)));
         if (DIM == 3) {
             r2 = fma(dz, dz, r2);
-            dot_product = fma(dz, v2 - QF(S_V2), dot_product);
+            dot_product = fma(dz, v2 - QG(S_V2), dot_product);
         }
-        double h_ij = 0.5 * (hp + QF(S_H));
+        double h_ij = 0.5 * (hp + QG(S_H));
         double inv_h = 1.0 / h_ij;
         double x = fast_sqrt_pos(r2) * inv_h;
         if (x > 1.0) return;  // rDwendland: 0 outside its own support (kernels.jl:142-144)
@@ -351,11 +345,11 @@ struct B_wcsph_momentum_fast : PairOpBase {
         // -140/pi (1-x)^3 / h^4   or   -210/pi (1-x)^3 / h^5
         double ker = DIM == 2 ? -44.563384065730695 * (t * t * t) * ih4
                               : -66.84507609859604 * (t * t * t) * (ih4 * inv_h);
-        double qm = QF(S_M);
-        double fc = -qm * (pr2 + QF(S_PR2)) * ker;
+        double qm = QG(S_M);
+        double fc = -qm * (pr2 + QG(S_PR2)) * ker;
         if (dot_product < 0.0) {
-            double qrho = jl_max(QF(S_RHO), c.rho_floor);
-            double c_ij = 0.5 * (cs + QF(S_CS));
+            double qrho = q.rho_floored(c);
+            double c_ij = 0.5 * (cs + QG(S_CS));
             double rho_ij = 0.5 * (prho + qrho);
             // mu = h dot / D,  pi = (-alpha c mu + beta mu^2) / rho_ij, with one reciprocal
             double D = fma(c.eps * h_ij, h_ij, r2);
@@ -370,54 +364,13 @@ struct B_wcsph_momentum_fast : PairOpBase {
         if (DIM == 3) dv2 = fma(fc, dz, dv2);
     }
     template <int DIM>
-    __device__ void pair_rec(const Params &c, double qm, const NbRec &B, const NbRec &C, double dx, double dy,
-                             double dz, double) {
-        double r2 = fma(dx, dx, dy * dy);
-        double dot_product = fma(dy, v1 - B.b, dx * (v0 - B.a));
-        if (DIM == 3) {
-            r2 = fma(dz, dz, r2);
-            dot_product = fma(dz, v2 - B.c, dot_product);
-        }
-        double h_ij = 0.5 * (hp + B.d);
-        double inv_h = 1.0 / h_ij;
-        double x = fast_sqrt_pos(r2) * inv_h;
-        if (x > 1.0) return;
-        double t = 1.0 - x;
-        double ih2 = inv_h * inv_h;
-        double ih4 = ih2 * ih2;
-        double ker = DIM == 2 ? -44.563384065730695 * (t * t * t) * ih4
-                              : -66.84507609859604 * (t * t * t) * (ih4 * inv_h);
-        double fc = -qm * (pr2 + C.a) * ker;
-        if (dot_product < 0.0) {
-            double qrho = C.b;
-            double c_ij = 0.5 * (cs + C.c);
-            double rho_ij = 0.5 * (prho + qrho);
-            double D = fma(c.eps * h_ij, h_ij, r2);
-            double R = 1.0 / (D * rho_ij);
-            double hd = h_ij * dot_product;
-            double mu = hd * rho_ij * R;
-            double pi_ij = hd * R * fma(c.beta, mu, -c.alpha * c_ij);
-            fc = fma(-qm * pi_ij, ker, fc);
-        }
-        dv0 = fma(fc, dx, dv0);
-        dv1 = fma(fc, dy, dv1);
-        if (DIM == 3) dv2 = fma(fc, dz, dv2);
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy,
+                         double dz, double r) {
+        pair_q<DIM>(c, GlobalQ{f, q}, dx, dy, dz, r);
     }
     template <int DIM>
     __device__ void finish(const Fields &f, const Fields &out, const Params &c, int64_t p) {
-        double n0 = v0, n1 = v1, n2 = v2;
-        if (PF(S_TYPE) == c.fluid) {
-            const double rho_p = PF(S_RHO_P), rho = PF(S_RHO);
-            const bool sponge = PF(S_X1) >= c.sponge_z0;
-            const double hdt = 0.5 * c.dt;
-            n0 = v0 + hdt * (dv0 + -c.g * 0.0 * rho_p / rho + (sponge ? c.sponge_y * 0.0 : 0.0));
-            n1 = v1 + hdt * (dv1 + -c.g * 1.0 * rho_p / rho + (sponge ? c.sponge_y * 1.0 : 0.0));
-            if (DIM == 3)
-                n2 = v2 + hdt * (dv2 + -c.g * 0.0 * rho_p / rho + (sponge ? c.sponge_y * 0.0 : 0.0));
-        }
-        out.s[S_V0][p] = n0;
-        out.s[S_V1][p] = n1;
-        if (DIM == 3) out.s[S_V2][p] = n2;
+        wcsph_force_finish<DIM>(f, out, c, p, v0, v1, v2, dv0, dv1, dv2);
     }
 };
 #undef PF
