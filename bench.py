@@ -53,12 +53,16 @@ def parse():
     ap.add_argument("--no-strict", action="store_true")
     ap.add_argument("--no-overlap", action="store_true",
                     help="slabs: plain halo exchange between the drift and the cell list (no overlap)")
+    ap.add_argument("--python-transport", action="store_true",
+                    help="slabs: move the halo records with torch.distributed from Python (round-1 path) instead "
+                         "of the library's own ncclSend/ncclRecv (csrc/slab_comm.cu)")
     ap.add_argument("--device-gen", action="store_true",
                     help="generate the lattice on the GPU (sphmw_generate_mountain_wave) instead of numpy")
     ap.add_argument("--cpu-sample", default="bell_hill_3d_1M")
-    ap.add_argument("--flags", type=int, default=1,
-                    help="SPHMW_FLAG_*: 0 strict (bit-identical sums), 1 FAST_MATH (default), 2 CELL_PAIRS, "
-                         "+4 NO_PAIR_LIST (walk the cells in every pass), +16 NO_PRETEST, +32 PACKED_RECORDS (experimental)")
+    ap.add_argument("--flags", type=int, default=0,
+                    help="SPHMW_FLAG_*: 0 strict arithmetic (default: FP64 sums bit-identical to the oracle), "
+                         "1 FAST_MATH, 2 CELL_PAIRS, +4 NO_PAIR_LIST (walk the cells in every pass), +16 NO_PRETEST, "
+                         "+64 TILES (shared-memory tiles, experimental), +128 NO_PACKED_RECORDS (SoA gathers)")
     return ap.parse_args()
 
 
@@ -225,6 +229,8 @@ def run_ours(args):
             run = SlabRun.bell_hill_3d(nx, ny, nz, rank=rank, world=world, device=local,
                                        stream=stream.cuda_stream, flags=args.flags,
                                        device_gen=args.device_gen)
+        if world > 1 and not args.python_transport:
+            run.use_library_transport()
         run.create_cell_list()
         n_local = run.n_owned
         n_total = run.n_global
@@ -273,14 +279,14 @@ def run_ours(args):
         k_ms += rep.get(kname + "_edge", (0.0, 0))[0]
         k_calls = max(k_calls, args.steps)
         per_launch_s = (k_ms / max(k_calls, 1)) * 1e-3
-        alg_bytes = run.n_resident * BYTES["K_C"]
+        alg_bytes = n_local * BYTES["K_C"]  # the particles this rank owns (ghosts are not its work)
         achieved = alg_bytes / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
         total_kernel_ms = sum(v[0] for v in rep.values())
         # DRAM traffic of that kernel per launch: from the committed ncu capture of this very
         # workload/arithmetic on one GPU (never measured under the timed run), else null
         traffic = None
         try:
-            tj = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text())
+            tj = json.loads((ROOT / "profiles" / "r02_ncu_traffic.json").read_text())
             rec = tj.get(args.workload, {}).get(f"flags{args.flags}")
             if rec and world == rec["n_gpus"]:
                 traffic = (rec["dram_bytes_read"] + rec["dram_bytes_write"]) / 1e9
@@ -293,13 +299,13 @@ def run_ours(args):
             "alg_bytes_per_particle": BYTES["K_C"], "ms_per_launch": per_launch_s * 1e3,
             "share_of_step": (k_ms / total_kernel_ms) if total_kernel_ms else None,
             "per_kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(rep.items())},
-            "step_bytes_frac": (run.n_resident * BYTES["step"] * args.steps / (ms * 1e-3) / 1e9) / peak_gbs,
+            "step_bytes_frac": (n_local * BYTES["step"] * args.steps / (ms * 1e-3) / 1e9) / peak_gbs,
         }
 
-        # ---- the same step with strict arithmetic (bit-identical sums), for reference ----
-        strict_ms = None
-        if args.flags == 1 and not args.no_strict:
-            run.sys.set_flags(0)
+        # ---- the same step with the other arithmetic (fast <-> strict), for reference ----------
+        other_ms = None
+        if (args.flags & ~1) == 0 and not args.no_strict:
+            run.sys.set_flags(args.flags ^ 1)
             step(1)
             barrier()
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -310,7 +316,7 @@ def run_ours(args):
             ts = torch.tensor([s0.elapsed_time(s1) / 3], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-            strict_ms = float(ts.item())
+            other_ms = float(ts.item())
             run.sys.set_flags(args.flags)
 
         # ---- end to end through the public API with HOST buffers ------------------
@@ -352,11 +358,14 @@ def run_ours(args):
                        "pair_interactions_per_s": pairs_force * 2 / (ms_max * 1e-3 / args.steps)
                        if pairs_force else None,
                        "pairs_per_binary_pass": pairs_force,
-                       "strict_arithmetic_ms_per_step": strict_ms,
+                       ("fast_arithmetic_ms_per_step" if not (args.flags & 1) else "strict_arithmetic_ms_per_step"): other_ms,
                        "pair_list": pair_list,
-                       "halo_exchange": ("overlapped with the interior force pass (step_phase 2/3)"
-                                         if world > 1 and not (args.flags & 2) and not args.no_overlap
-                                         else ("plain" if world > 1 else None))},
+                       "halo_exchange": (("overlapped with the interior force pass"
+                                          if not (args.flags & 2) and not args.no_overlap else "plain") +
+                                         (", ncclSend/ncclRecv inside libsphmw (one group per step)"
+                                          if not args.python_transport else ", torch.distributed from Python")
+                                         if world > 1 else None),
+                       "comm": run.comm_info() if world > 1 and not args.python_transport else None},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clk.summary(),
         }

@@ -80,10 +80,24 @@ typedef struct sphmw_config {
 #define SPHMW_FLAG_NO_PAIR_LIST 4
 #define SPHMW_FLAG_PAIR_LIST_EAGER 8
 #define SPHMW_FLAG_NO_PRETEST 16
-/* Fused "wcsph" step only, experimental (default off): the replaying passes read their
- * neighbours from three packed 32-byte records with 256-bit loads instead of eleven 8-byte
- * gathers (+96 B per particle; same bits).  Ignored together with NO_PAIR_LIST / CELL_PAIRS. */
+/* Fused "wcsph" step only.  By default its two pair passes read their neighbours from three packed
+ * 32-byte records ({x,y,z,m} written by the cell-list gather, {v,h} and {P'/rho^2, rho, c_s} written
+ * by the density pass) with one 256-bit load each instead of eleven 8-byte gathers (+96 B per
+ * particle; the records are bit copies of the SoA fields, so no sum changes).  Measured on B200,
+ * 64 M particles: step 48.5 -> 42.1 ms (profiles/r02_pair_kernels.md).  NO_PACKED_RECORDS: gather
+ * from the SoA arrays.  PACKED_RECORDS (the round-1 opt-in bit) is accepted and ignored.
+ * Ignored together with NO_PAIR_LIST / CELL_PAIRS. */
 #define SPHMW_FLAG_PACKED_RECORDS 32
+#define SPHMW_FLAG_NO_PACKED_RECORDS 128
+/* Fused "wcsph" step only, experimental (default off).  TILES: the two pair passes stage the
+ * neighbourhood of every block of 128 particles in shared memory (coalesced 16-byte copies, or
+ * cp.async.bulk/TMA when built with TILE_STAGE_TMA) and gather neighbour fields from there; the
+ * pair list then holds 16-bit tile slots of the accepted neighbours (same visiting order, same
+ * bits).  Correct (CPU emulation and GPU tests) but 2.5x slower than the record path on B200:
+ * a tile of 115 KB per 4 warps leaves 8 warps per SM and the per-thread dependent chains are no
+ * longer hidden (profiles/r02_pair_kernels.md).  Ignored together with NO_PAIR_LIST / CELL_PAIRS /
+ * NO_PRETEST. */
+#define SPHMW_FLAG_TILES 64
 
 int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out);
 int sphmw_destroy(sphmw_ctx *ctx);
@@ -189,6 +203,11 @@ int sphmw_pair_count(sphmw_ctx *ctx, int64_t *n);
  * out[2] particles whose candidates did not fit the stride (they walk the cells instead),
  * out[3] bytes of device memory held by the list.  Blocks. */
 int sphmw_pair_list_info(sphmw_ctx *ctx, int64_t out[4]);
+/* shared-memory tiles of the fused pair passes (current cell list): out[0] blocks of 128 particles,
+ * out[1] blocks whose neighbourhood is staged in shared memory, out[2] slots of the largest
+ * neighbourhood, out[3] slots of all staged neighbourhoods, out[4] slots a tile can hold,
+ * out[5] blocks spread over too many rows of cells to be tiled.  Blocks. */
+int sphmw_tile_info(sphmw_ctx *ctx, int64_t out[6]);
 
 /* Host-only test hooks (no device, no context).
  * sphmw_pretest_pairs: the integer pre-test of the pair-list recording pass on n pairs
@@ -274,6 +293,23 @@ int sphmw_halo_pack_begin(sphmw_ctx *ctx, double *dev_buf_left, double *dev_buf_
 int sphmw_halo_pack_finish(sphmw_ctx *ctx, int64_t cap_records, int64_t counts[5]);
 int sphmw_halo_pack_wait(sphmw_ctx *ctx, void *cuda_stream);
 int sphmw_slab_counts(sphmw_ctx *ctx, int64_t *n_resident, int64_t *n_owned);
+
+/* Halo transport INSIDE the library (csrc/slab_comm.cu) — what makes a slab context a drop-in for
+ * the reference's single-threaded caller (its parallelism is internal to apply_binary!,
+ * src/core.jl:125-142): after sphmw_comm_init, sphmw_create_cell_list and sphmw_step(ctx, "wcsph", n)
+ * work on a slab context exactly as on a whole-domain one; the records travel by ncclSend/ncclRecv
+ * between x-adjacent ranks on a second CUDA stream, beside the interior force pass, one NCCL group
+ * per step with the record count in the first row (read on the device), one host wait per step.
+ *   sphmw_comm_unique_id   128 bytes (an ncclUniqueId) made by ONE rank and handed to all others by
+ *                          whatever means the host has (MPI, a file, torch.distributed ...)
+ *   sphmw_comm_init        collective; rank r holds the r-th slab from the left; halo_capacity =
+ *                          records one message buffer holds, the same value on every rank
+ *   sphmw_comm_info        out = {world, exchanges, renegotiated message sizes, rows per step
+ *                          (both directions), particles lost through the global box, capacity}
+ * NCCL is loaded with dlopen("libnccl.so.2") at the first of these calls. */
+int sphmw_comm_unique_id(void *id128);
+int sphmw_comm_init(sphmw_ctx *ctx, int32_t rank, int32_t world, const void *id128, int64_t halo_capacity);
+int sphmw_comm_info(sphmw_ctx *ctx, int64_t out[6]);
 /* global particle index of every resident particle (physical order) */
 int sphmw_set_index(sphmw_ctx *ctx, const int64_t *global_idx, int64_t n);
 /* physical-order read-back: indices + tags (0 owned, 1 ghost), and raw fields */

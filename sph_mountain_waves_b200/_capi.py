@@ -85,6 +85,10 @@ _SIGS = {
     "sphmw_pretest_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int32, C.c_void_p]),
     "sphmw_slab_column_sets": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "sphmw_pair_list_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "sphmw_tile_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "sphmw_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "sphmw_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_char_p, C.c_int64]),
+    "sphmw_comm_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "sphmw_reduce": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double)]),
     "sphmw_kernel_eval": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]),
     "sphmw_pvd_open": (C.c_int, [_P, C.c_char_p]),

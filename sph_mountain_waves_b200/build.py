@@ -22,7 +22,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # an FMA; bit-exact neighbour sets and reproducible FP64 sums depend on it.
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,-O2",
                      "-Xcudafe", "--diag_suppress=177", f"-I{ROOT / 'include'}", f"-I{CSRC}"]
-SOURCES = ["api.cu", "cell_list.cu", "pair_ops.cu", "halo.cu", "lattice.cu", "frame_io.cpp", "grid_setup.cpp"]
+SOURCES = ["api.cu", "cell_list.cu", "pair_ops.cu", "halo.cu", "slab_comm.cu", "lattice.cu", "frame_io.cpp", "grid_setup.cpp"]
 
 
 def _nvcc() -> str:
@@ -64,7 +64,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
         objs = list(ex.map(compile_one, SOURCES))
     if force or _stale(LIB, objs):
         cmd = [nvcc, "-ccbin", ccbin, "-shared"] + ARCH + ["-o", str(LIB)] + [str(o) for o in objs] + \
-              ["-lcudart", "-lz"]
+              ["-lcudart", "-lz", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

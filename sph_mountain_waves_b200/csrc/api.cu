@@ -285,6 +285,10 @@ extern "C" int sphmw_destroy(sphmw_ctx *c) {
     if (!c) return SPHMW_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    sphmw_comm_free(c);
+    if (c->h_slab_check) cudaFreeHost(c->h_slab_check);
+    for (auto e : c->slab_check_event)
+        if (e) cudaEventDestroy(e);
     for (int s = 0; s < NSLOT; ++s) {
         cudaFree(c->cur.s[s]);
         cudaFree(c->alt.s[s]);
@@ -296,7 +300,7 @@ extern "C" int sphmw_destroy(sphmw_ctx *c) {
     cudaFree(c->cell_start); cudaFree(c->scan_tmp); cudaFree(c->removed);
     cudaFree(c->mv_old); cudaFree(c->mv_new);
     cudaFree(c->d_counters); cudaFree(c->staging); cudaFree(c->reduce_tmp);
-    cudaFree(c->xq); cudaFree(c->pl.list); cudaFree(c->pl.cnt);
+    cudaFree(c->xq); cudaFree(c->pl.list); cudaFree(c->pl.list16); cudaFree(c->pl.cnt); cudaFree(c->tile_tab);
     for (int k = 0; k < 3; ++k) cudaFree(c->rec[k]);
     if (c->h_removed) cudaFreeHost(c->h_removed);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -362,9 +366,11 @@ int sphmw_ensure_records(sphmw_ctx *c) {
 
 int sphmw_ensure_slot(sphmw_ctx *c, int slot) {
     if (c->allocated[slot]) return SPHMW_OK;
-    CUDA_TRY(cudaMalloc(&c->cur.s[slot], sizeof(double) * c->cap));
-    CUDA_TRY(cudaMalloc(&c->alt.s[slot], sizeof(double) * c->cap));
-    CUDA_TRY(cudaMemsetAsync(c->cur.s[slot], 0, sizeof(double) * c->cap, c->stream));
+    // + 4: the bulk copies of the tiled pair kernels fetch whole groups of 4 particles
+    CUDA_TRY(cudaMalloc(&c->cur.s[slot], sizeof(double) * (c->cap + 4)));
+    CUDA_TRY(cudaMalloc(&c->alt.s[slot], sizeof(double) * (c->cap + 4)));
+    CUDA_TRY(cudaMemsetAsync(c->cur.s[slot], 0, sizeof(double) * (c->cap + 4), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->alt.s[slot], 0, sizeof(double) * (c->cap + 4), c->stream));
     c->allocated[slot] = true;
     c->stale[slot] = false;
     return SPHMW_OK;
@@ -622,6 +628,7 @@ extern "C" int sphmw_kernel_eval(const char *name, const double *h, const double
 extern "C" int sphmw_create_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     if (!c) return SPHMW_E_INVALID;
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->comm) return sphmw_comm_create_cell_list(c, n_alive);  // slab context: halo exchange, then the sort
     return sphmw_build_cell_list(c, n_alive);
 }
 extern "C" int sphmw_apply(sphmw_ctx *c, const char *op, int32_t self) {
@@ -655,6 +662,11 @@ extern "C" int sphmw_pair_list_info(sphmw_ctx *c, int64_t out[4]) {
     if (!c || !out) return SPHMW_E_INVALID;
     CUDA_TRY(cudaSetDevice(c->device));
     return sphmw_pair_list_stats(c, out);
+}
+extern "C" int sphmw_tile_info(sphmw_ctx *c, int64_t out[6]) {
+    if (!c || !out) return SPHMW_E_INVALID;
+    CUDA_TRY(cudaSetDevice(c->device));
+    return sphmw_tile_stats(c, out);
 }
 // ---- host-only test hooks (no device, no context) --------------------------------------
 extern "C" int sphmw_pretest_pairs(const double *xp, const double *xq, int64_t n, double h, int32_t dim,

@@ -10,6 +10,7 @@
 // warp-aggregated ranks, exclusive scan, scatter), followed by an in-cell
 // ordering by reference index that makes the result independent of the atomics'
 // arrival order (deterministic, like the reference's sorted insertion under a lock).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -57,12 +58,14 @@ __global__ void k_keys(const double *__restrict__ x0, const double *__restrict__
             key[pos] = k;
             cellx[pos] = ci;
         }
-        unsigned m = __ballot_sync(0xffffffffu, dead);
-        // removed[1]: the owned particles that stay — the rank's share of the global count
-        unsigned mo = __ballot_sync(0xffffffffu, live && !dead && tag[pos] == TAG_OWNED);
-        if ((threadIdx.x & 31) == 0) {
-            if (m) atomicAdd(&removed[0], (uint32_t)__popc(m));
-            if (mo) atomicAdd(&removed[1], (uint32_t)__popc(mo));
+        // removed[0]: dropped particles; removed[1]: the owned particles that stay — the rank's
+        // share of the global count.  Counted per block (one pair of atomics per 256 particles:
+        // per-warp atomics on two fixed addresses made this kernel 5x slower per particle)
+        const int nd = __syncthreads_count(dead);
+        const int no = __syncthreads_count(live && !dead && tag[pos] == TAG_OWNED);
+        if (threadIdx.x == 0) {
+            if (nd) atomicAdd(&removed[0], (uint32_t)nd);
+            if (no) atomicAdd(&removed[1], (uint32_t)no);
         }
         return;
     }
@@ -319,9 +322,43 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
         TIMED(c, "cell_scatter");
         k_scatter<<<grid_for(n, 256), 256, 0, c->stream>>>(c->key, c->rank, c->cell_start, n, c->src);
     }
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    const int64_t k = c->h_removed[0];
-    const uint32_t owned_live = c->h_removed[1];  // slab mode only (else the first removed index)
+    // How many particles are dropped.  A whole-domain context has to ask the device (and replays
+    // the reference's renumbering below).  A slab context knows from the halo pack (halo.cu:
+    // ghosts and migrants of the last exchange + particles the pack dropped) and does not wait;
+    // what the device counted is checked against it one build later, when the copy has long landed.
+    int64_t k;
+    uint32_t owned_live;
+    if (c->slab_lo >= 0 && c->slab_dead_known && !getenv("SPHMW_SLAB_SYNC_BUILD")) {
+        if (!c->h_slab_check) {
+            CUDA_TRY(cudaMallocHost(&c->h_slab_check, sizeof(uint32_t) * 2 * 4));
+            for (int e = 0; e < 4; ++e) CUDA_TRY(cudaEventCreateWithFlags(&c->slab_check_event[e], cudaEventDisableTiming));
+        }
+        if (c->slab_checks > 0) {
+            const int prev = (int)((c->slab_checks - 1) & 3);
+            CUDA_TRY(cudaEventSynchronize(c->slab_check_event[prev]));
+            if ((int64_t)c->h_slab_check[2 * prev] != c->slab_check_want[prev][0] ||
+                (int64_t)c->h_slab_check[2 * prev + 1] != c->slab_check_want[prev][1]) {
+                sphmw_set_error("slab bookkeeping diverged: the device dropped %u particles and kept %u owned ones, "
+                                "the host expected %lld and %lld", c->h_slab_check[2 * prev], c->h_slab_check[2 * prev + 1],
+                                (long long)c->slab_check_want[prev][0], (long long)c->slab_check_want[prev][1]);
+                return SPHMW_E_STATE;
+            }
+        }
+        const int cur = (int)(c->slab_checks & 3);
+        CUDA_TRY(cudaMemcpyAsync(c->h_slab_check + 2 * cur, c->removed, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost,
+                                 c->stream));
+        CUDA_TRY(cudaEventRecord(c->slab_check_event[cur], c->stream));
+        k = c->slab_dead_expected;
+        owned_live = (uint32_t)c->n_owned;
+        c->slab_check_want[cur][0] = k;
+        c->slab_check_want[cur][1] = c->n_owned;
+        c->slab_checks += 1;
+    } else {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        k = c->h_removed[0];
+        owned_live = c->h_removed[1];  // slab mode only (else the first removed index)
+    }
+    c->slab_dead_known = false;
     if (k > 0 && c->slab_lo < 0) {
         if (k > c->removed_cap) {
             sphmw_set_error("more than %lld particles left the domain in one step",
@@ -367,7 +404,7 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     for (int a = 0; a < 3; ++a) gl.xpos[a] = -1;
     gl.mpos = -1;
     gl.recA = nullptr;
-    if ((c->flags & SPHMW_FLAG_PACKED_RECORDS) && c->allocated[S_M] && !c->stale[S_M]) {
+    if (sphmw_use_records(c) && c->allocated[S_M] && !c->stale[S_M]) {
         TRY(sphmw_ensure_records(c));
         gl.recA = c->rec[0];
         c->rec_gen = c->cell_gen;

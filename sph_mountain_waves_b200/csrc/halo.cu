@@ -122,11 +122,28 @@ static int ensure_carried(sphmw_ctx *c) {
 
 extern "C" int sphmw_halo_record_doubles(void) { return HALO_RECORD; }
 
+// row 0 of a message (slab_comm.cu): {records, migrants among them}; the records follow
+__global__ void k_halo_header(const uint32_t *__restrict__ counters, double *msg_l, double *msg_r) {
+    if (threadIdx.x == 0 && msg_l) {
+        msg_l[0] = (double)counters[0];
+        msg_l[1] = (double)counters[2];
+    }
+    if (threadIdx.x == 1 && msg_r) {
+        msg_r[0] = (double)counters[1];
+        msg_r[1] = (double)counters[3];
+    }
+}
+
 // enqueue: classify + pack (all particles, or the edge columns of an overlapped step out of the
 // alt buffers), then read the counters back asynchronously and mark the point with an event
+// msg_left/right: when not null, the record counts are also written, on the device, to row 0 of
+// these messages (the records themselves start one row further, at dev_buf_*)
 static int pack_enqueue(sphmw_ctx *c, double *dev_buf_left, double *dev_buf_right, int64_t cap_records,
-                        bool edge_only) {
+                        bool edge_only, double *msg_left = nullptr, double *msg_right = nullptr) {
     TRY(ensure_carried(c));
+    // what the next cell-list build will find dead: last exchange's ghosts and migrants, plus
+    // the particles this pack is about to drop (added by pack_collect)
+    c->slab_dead_expected = c->n - c->n_owned;
     const int has_left = dev_buf_left != nullptr, has_right = dev_buf_right != nullptr;
     // [0..4] belong to this pack; [5] (escapes counted by the previous interior advance) is read
     // together with them and cleared afterwards
@@ -149,15 +166,23 @@ static int pack_enqueue(sphmw_ctx *c, double *dev_buf_left, double *dev_buf_righ
                 dev_buf_right, (uint32_t)cap_records, c->halo_counters, c->cellx, cf);
         CUDA_TRY(cudaGetLastError());
     }
+    if (msg_left || msg_right) {
+        k_halo_header<<<1, 32, 0, c->stream>>>(c->halo_counters, msg_left, msg_right);
+        c->launches += 1;
+    }
     CUDA_TRY(cudaMemcpyAsync(c->h_halo_counters, c->halo_counters, sizeof(uint32_t) * 8,
                              cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->halo_counters + 5, 0, sizeof(uint32_t), c->stream));
     CUDA_TRY(cudaEventRecord(c->pack_event, c->stream));
     return SPHMW_OK;
 }
+int sphmw_halo_pack_enqueue(sphmw_ctx *c, double *msg_left, double *msg_right, int64_t cap_records, bool edge_only) {
+    return pack_enqueue(c, msg_left ? msg_left + HALO_RECORD : nullptr, msg_right ? msg_right + HALO_RECORD : nullptr,
+                        cap_records, edge_only, msg_left, msg_right);
+}
 
-static int pack_collect(sphmw_ctx *c, int64_t cap_records, int64_t counts[5]) {
-    CUDA_TRY(cudaEventSynchronize(c->pack_event));
+static int pack_collect(sphmw_ctx *c, int64_t cap_records, int64_t counts[5], bool wait = true) {
+    if (wait) CUDA_TRY(cudaEventSynchronize(c->pack_event));
     for (int k = 0; k < 5; ++k) counts[k] = c->h_halo_counters[k];
     if (c->h_halo_counters[5] != 0) {
         sphmw_set_error("overlapped halo exchange: %u particle(s) crossed more than one cell column in a "
@@ -171,8 +196,14 @@ static int pack_collect(sphmw_ctx *c, int64_t cap_records, int64_t counts[5]) {
         return SPHMW_E_CAPACITY;
     }
     c->n_owned -= counts[2] + counts[3] + counts[4];
+    c->slab_dead_expected += counts[4];
+    c->slab_dead_known = true;
     c->cell_list_valid = false;
     return SPHMW_OK;
+}
+// the counters are already on the host (the caller waited for something later in the stream)
+int sphmw_halo_pack_collect_nowait(sphmw_ctx *c, int64_t cap_records, int64_t counts[5]) {
+    return pack_collect(c, cap_records, counts, false);
 }
 
 // counts[0..4] = records to the left, to the right, migrants among them (left, right), lost.

@@ -21,6 +21,7 @@
 #include "cell_pairs.cuh"
 #include "kernels_sph.cuh"
 #include "pair_list.cuh"
+#include "pair_tile.cuh"
 #include "sphmw_internal.h"
 #include "ops_menu.cuh"
 #include "wcsph_ops.cuh"
@@ -317,7 +318,7 @@ static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Field
     unsigned long long *pc = c->count_pairs ? c->d_counters : nullptr;
     if (pc) CUDA_TRY(cudaMemsetAsync(pc, 0, sizeof(unsigned long long), c->stream));
     const bool lists = !(c->flags & SPHMW_FLAG_NO_PAIR_LIST);
-    const bool replay = lists && c->pl.list && c->pl_gen == c->cell_gen;
+    const bool replay = lists && c->pl.list && c->pl_gen == c->cell_gen && c->pl_format == 0;
     bool record = lists && !replay && (c->want_list || (c->flags & SPHMW_FLAG_PAIR_LIST_EAGER));
     if (record && ensure_pair_list(c) != SPHMW_OK) {
         // the list is an optimisation: without memory for it every pass walks the cells
@@ -353,6 +354,7 @@ static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Field
         const size_t smem = sizeof(uint32_t) * (size_t)c->pl.stride * NL_BLOCK;
         TIMED(c, name);
         c->pl_gen = c->cell_gen;
+        c->pl_format = 0;
         c->pl_builds += 1;
         if constexpr (REC) {
             if (rec) {
@@ -383,6 +385,145 @@ static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Field
             k_binary<3, Op><<<blocks, 128, 0, c->stream>>>(NL_ARGS);
     }
 #undef NL_ARGS
+    CUDA_TRY(cudaGetLastError());
+    return SPHMW_OK;
+}
+
+// ---------------------------------------------------------------------------
+// tiled passes (pair_tile.cuh): neighbourhood of each block staged in shared memory
+// ---------------------------------------------------------------------------
+static int ensure_tile_buffers(sphmw_ctx *c) {
+    if (c->pl.list16 && c->tile_tab) return SPHMW_OK;
+    int stride = c->grid.dim == 3 ? 40 : 32;
+    if (const char *e = getenv("SPHMW_PAIR_LIST_STRIDE")) stride = atoi(e);
+    stride = (stride + 1) & ~1;
+    if (stride < 4) stride = 4;
+    if (stride > 96) stride = 96;
+    if (c->pl.list && c->pl.stride != stride) stride = c->pl.stride & ~1;  // one stride per context
+    const size_t warps = (size_t)((c->cap + 31) / 32);
+    const size_t blocks = (size_t)((c->cap + TM_BLOCK - 1) / TM_BLOCK);
+    uint32_t *l16 = nullptr, *tab = nullptr, *cnt = c->pl.cnt;
+    bool ok = cudaMalloc(&l16, sizeof(uint32_t) * warps * (size_t)(stride / 2) * 32) == cudaSuccess &&
+              cudaMalloc(&tab, sizeof(uint32_t) * blocks * TM_WORDS) == cudaSuccess;
+    if (ok && !cnt) ok = cudaMalloc(&cnt, sizeof(uint32_t) * (size_t)c->cap) == cudaSuccess;
+    if (!ok) {
+        cudaFree(l16);
+        cudaFree(tab);
+        (void)cudaGetLastError();
+        sphmw_set_error("no device memory for the tiled pair list");
+        return SPHMW_E_CAPACITY;
+    }
+    c->pl.list16 = l16;
+    c->tile_tab = tab;
+    c->pl.cnt = cnt;
+    c->pl.stride = stride;
+    c->pl.overflow = c->d_counters + 2;
+    return SPHMW_OK;
+}
+
+static int ensure_tile_map(sphmw_ctx *c) {
+    if (c->tile_gen == c->cell_gen) return SPHMW_OK;
+    const int64_t nblocks = (c->n + TM_BLOCK - 1) / TM_BLOCK;
+    TIMED(c, "tile_map");
+    k_tile_map<<<grid_for(nblocks * 32, 128), 128, 0, c->stream>>>(c->grid, c->key, c->cellx, c->cell_start, c->n,
+                                                                  nblocks, c->tile_tab);
+    CUDA_TRY(cudaGetLastError());
+    c->tile_gen = c->cell_gen;
+    return SPHMW_OK;
+}
+
+// blocks / blocks with a tile / largest tile / slots of all tiles / capacity / blocks over too many rows
+__global__ void k_tile_stats(const uint32_t *__restrict__ tab, int64_t nblocks, int max_pieces, uint32_t cap,
+                             unsigned long long *__restrict__ out) {
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const uint32_t *rec = tab + (size_t)b * TM_WORDS;
+    const bool pieces_ok = rec[1] <= (uint32_t)max_pieces;
+    if (pieces_ok && rec[2] <= cap) {
+        atomicAdd(&out[0], 1ull);
+        atomicAdd(&out[2], (unsigned long long)rec[2]);
+    }
+    if (pieces_ok) atomicMax(&out[1], (unsigned long long)rec[2]);
+    else atomicAdd(&out[3], 1ull);
+}
+
+int sphmw_tile_stats(sphmw_ctx *c, int64_t out[6]) {
+    for (int k = 0; k < 6; ++k) out[k] = 0;
+    out[4] = c->grid.dim == 3 ? TileGeom<3>::CAP : TileGeom<2>::CAP;
+    if (!c->tile_tab || c->tile_gen != c->cell_gen || c->n == 0) return SPHMW_OK;
+    const int64_t nblocks = (c->n + TM_BLOCK - 1) / TM_BLOCK;
+    unsigned long long *d = c->d_counters + 3;
+    CUDA_TRY(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * 4, c->stream));
+    k_tile_stats<<<grid_for(nblocks, 256), 256, 0, c->stream>>>(c->tile_tab, nblocks, tm_max_pieces(c->grid),
+                                                               (uint32_t)out[4], d);
+    CUDA_TRY(cudaMemcpyAsync(c->h_counters + 3, d, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    out[0] = nblocks;
+    out[1] = (int64_t)c->h_counters[3];
+    out[2] = (int64_t)c->h_counters[4];
+    out[3] = (int64_t)c->h_counters[5];
+    out[5] = (int64_t)c->h_counters[6];
+    return SPHMW_OK;
+}
+
+template <class K>
+static int tile_smem_attr(K kernel, int bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return SPHMW_OK;
+}
+
+static bool tiles_enabled(const sphmw_ctx *c) {
+    return (c->flags & SPHMW_FLAG_TILES) &&
+           !(c->flags & (SPHMW_FLAG_NO_PAIR_LIST | SPHMW_FLAG_CELL_PAIRS | SPHMW_FLAG_NO_PRETEST));
+}
+
+// One fused pass through the tiled kernels: the first pass of a cell-list generation records
+// (k_tile_build), later ones replay (k_tile_list).
+template <class Op>
+static int run_tiled(sphmw_ctx *c, const char *name, int self, const Fields &out, ColFilter cf) {
+    if (!c->cell_list_valid) {
+        sphmw_set_error("%s: create_cell_list must be called after positions change", name);
+        return SPHMW_E_STATE;
+    }
+    if (c->n == 0) return SPHMW_OK;
+    TRY(ensure_tile_buffers(c));
+    TRY(ensure_tile_map(c));
+    unsigned long long *pc = c->count_pairs ? c->d_counters : nullptr;
+    if (pc) CUDA_TRY(cudaMemsetAsync(pc, 0, sizeof(unsigned long long), c->stream));
+    c->passes_this_gen += 1;
+    c->pl.xq = c->xq;
+    const unsigned blocks = grid_for(c->n, TM_BLOCK);
+    const bool replay = c->pl_gen == c->cell_gen && c->pl_format == 1;
+#define TL_ARGS c->cur, out, c->prm, c->grid, c->key, c->cellx, c->cell_start, c->n, self, pc, cf, c->pl, c->tile_tab
+    if (replay) {
+        static bool attr2 = false, attr3 = false;
+        TIMED(c, name);
+        if (c->grid.dim == 2) {
+            constexpr int smem = tile_bytes_list<2, Op>();
+            if (!attr2) { TRY(tile_smem_attr(k_tile_list<2, Op>, smem)); attr2 = true; }
+            k_tile_list<2, Op><<<blocks, TM_BLOCK, smem, c->stream>>>(TL_ARGS);
+        } else {
+            constexpr int smem = tile_bytes_list<3, Op>();
+            if (!attr3) { TRY(tile_smem_attr(k_tile_list<3, Op>, smem)); attr3 = true; }
+            k_tile_list<3, Op><<<blocks, TM_BLOCK, smem, c->stream>>>(TL_ARGS);
+        }
+    } else {
+        static int attr2 = 0, attr3 = 0;
+        TIMED(c, name);
+        c->pl_gen = c->cell_gen;
+        c->pl_format = 1;
+        c->pl_builds += 1;
+        if (c->grid.dim == 2) {
+            const int smem = tile_bytes_build<2, Op>(c->pl.stride);
+            if (attr2 != smem) { TRY(tile_smem_attr(k_tile_build<2, Op>, smem)); attr2 = smem; }
+            k_tile_build<2, Op><<<blocks, TM_BLOCK, smem, c->stream>>>(TL_ARGS);
+        } else {
+            const int smem = tile_bytes_build<3, Op>(c->pl.stride);
+            if (attr3 != smem) { TRY(tile_smem_attr(k_tile_build<3, Op>, smem)); attr3 = smem; }
+            k_tile_build<3, Op><<<blocks, TM_BLOCK, smem, c->stream>>>(TL_ARGS);
+        }
+    }
+#undef TL_ARGS
     CUDA_TRY(cudaGetLastError());
     return SPHMW_OK;
 }
@@ -627,8 +768,13 @@ static int step_wcsph_fused_pre(sphmw_ctx *c) {
 // the packed neighbour records)
 static int run_fused_density(sphmw_ctx *c) {
     // owned columns + the first ghost column (its sums are complete thanks to the second)
-    const bool rec = (c->flags & SPHMW_FLAG_PACKED_RECORDS) != 0;
+    const bool rec = sphmw_use_records(c);
     const char *name = "wcsph.density_fused";
+    if (tiles_enabled(c)) {
+        const ColFilter cf = filter_for_depth(c, 1);
+        if (c->flags & SPHMW_FLAG_FAST_MATH) return run_tiled<B_wcsph_density_fast>(c, name, 0, c->cur, cf);
+        return run_tiled<B_wcsph_density_fused>(c, name, 0, c->cur, cf);
+    }
     if (c->flags & SPHMW_FLAG_FAST_MATH)
         return rec ? run_binary<B_wcsph_density_fast, true>(c, name, 0, c->cur, 1)
                    : run_binary<B_wcsph_density_fast>(c, name, 0, c->cur, 1);
@@ -636,7 +782,11 @@ static int run_fused_density(sphmw_ctx *c) {
                : run_binary<B_wcsph_density_fused>(c, name, 0, c->cur, 1);
 }
 static int run_fused_force(sphmw_ctx *c, const char *name, const ColFilter &cf) {
-    const bool rec = (c->flags & SPHMW_FLAG_PACKED_RECORDS) != 0;
+    const bool rec = sphmw_use_records(c);
+    if (tiles_enabled(c)) {
+        if (c->flags & SPHMW_FLAG_FAST_MATH) return run_tiled<B_wcsph_momentum_fast>(c, name, 0, c->alt, cf);
+        return run_tiled<B_wcsph_momentum_fused>(c, name, 0, c->alt, cf);
+    }
     if (c->flags & SPHMW_FLAG_FAST_MATH)
         return rec ? run_binary_cols<B_wcsph_momentum_fast, true>(c, name, 0, c->alt, cf)
                    : run_binary_cols<B_wcsph_momentum_fast>(c, name, 0, c->alt, cf);
@@ -828,9 +978,14 @@ int sphmw_step_scheme_phase(sphmw_ctx *c, const char *scheme, int phase) {
     return SPHMW_E_INVALID;
 }
 
+int sphmw_step_wcsph_phase(sphmw_ctx *c, int phase) { return sphmw_step_scheme_phase(c, "wcsph", phase); }
+
 int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps) {
     if (c->slab_lo >= 0 && nsteps > 0) {
-        sphmw_set_error("step: a slab context is stepped with step_phase around the halo exchange");
+        // with a communicator (sphmw_comm_init) the halo exchange is the library's business
+        if (c->comm) return sphmw_comm_step(c, scheme, nsteps);
+        sphmw_set_error("step: a slab context without a communicator (sphmw_comm_init) is stepped with "
+                        "step_phase around the caller's halo exchange");
         return SPHMW_E_STATE;
     }
     for (int k = 0; k < nsteps; ++k) {

@@ -1,0 +1,305 @@
+// x-slab halo transport inside the library (SURVEY.md §8b "multi-GPU is internal to the ctx",
+// §8e): ncclSend/ncclRecv between x-adjacent ranks on a second, high-priority CUDA stream,
+// driven by sphmw_step / sphmw_create_cell_list themselves, so that a single-threaded caller —
+// the reference's caller is one (src/core.jl:125-142) — steps a slab context with the very calls
+// it uses on one GPU.
+//
+// One exchange = ONE ncclGroup per step.  A message is a fixed number of rows of HALO_RECORD
+// doubles agreed between the two ranks; row 0 is written on the device by the pack
+// ({records, migrants}), so no count has to travel first and the sender's host never has to
+// know it before the send is queued.  The sizes are agreed once (a header-only round at the first
+// exchange: count * 1.12 + 1024 rows) and renegotiated, with one extra blocking round, only when a
+// count outgrows them.  Per step the host waits once — for the two received headers, which arrive
+// while the interior force pass is still running on the main stream — and the cell-list build of
+// a slab context no longer waits at all (cell_list.cu: the dead count follows from the pack).
+//
+// NCCL is loaded with dlopen at sphmw_comm_init (libnccl.so.2 — inside a PyTorch process that is
+// the copy torch already loaded), so libsphmw.so itself has no link-time dependency on it.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "sphmw_internal.h"
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.lib) return SPHMW_OK;
+    void *lib = nullptr;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+        lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) {
+        sphmw_set_error("NCCL is not available: %s", dlerror());
+        return SPHMW_E_UNSUPPORTED_OP;
+    }
+#define NCCL_SYM(field, sym)                                                    \
+    *(void **)(&g_nccl.field) = dlsym(lib, sym);                                \
+    if (!g_nccl.field) {                                                        \
+        sphmw_set_error("NCCL library lacks %s", sym);                          \
+        return SPHMW_E_UNSUPPORTED_OP;                                          \
+    }
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    NCCL_SYM(Send, "ncclSend")
+    NCCL_SYM(Recv, "ncclRecv")
+    NCCL_SYM(GroupStart, "ncclGroupStart")
+    NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+    g_nccl.lib = lib;
+    return SPHMW_OK;
+}
+
+#define NCCL_TRY(expr)                                                                          \
+    do {                                                                                        \
+        ncclResult_t _r = (expr);                                                               \
+        if (_r != ncclSuccess) {                                                                \
+            sphmw_set_error("%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(_r), __FILE__, __LINE__); \
+            return SPHMW_E_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+struct SlabComm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    bool has[2] = {false, false};  // a neighbour on the left / right
+    int peer[2] = {-1, -1};
+    cudaStream_t stream = nullptr;  // high priority: the transfer runs beside the interior force pass
+    int64_t cap = 0;                // records a message buffer holds (+ the header row)
+    double *send[2] = {nullptr, nullptr}, *recv[2] = {nullptr, nullptr};
+    int64_t send_rows[2] = {0, 0}, recv_rows[2] = {0, 0};  // agreed message sizes (0: not yet)
+    double *h_head = nullptr;       // pinned: the two received headers
+    cudaEvent_t recv_event = nullptr;
+    int64_t exchanges = 0, renegotiations = 0;
+    int64_t lost = 0;
+};
+
+extern "C" int sphmw_comm_unique_id(void *id128) {
+    if (!id128) return SPHMW_E_INVALID;
+    TRY(nccl_load());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return SPHMW_OK;
+}
+
+void sphmw_comm_free(sphmw_ctx *c) {
+    SlabComm *m = c->comm;
+    if (!m) return;
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(m->send[s]);
+        cudaFree(m->recv[s]);
+    }
+    if (m->h_head) cudaFreeHost(m->h_head);
+    if (m->recv_event) cudaEventDestroy(m->recv_event);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    c->comm = nullptr;
+}
+
+// rank r of `world` ranks holds the r-th slab from the left; halo_capacity = records one message
+// buffer can hold — the SAME value on every rank (message sizes are derived from it on both ends).
+// Collective: every rank of the communicator calls it.
+extern "C" int sphmw_comm_init(sphmw_ctx *c, int32_t rank, int32_t world, const void *id128, int64_t halo_capacity) {
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world || halo_capacity <= 0) {
+        sphmw_set_error("comm_init: bad argument");
+        return SPHMW_E_INVALID;
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->slab_lo < 0) { sphmw_set_error("comm_init: context has no slab"); return SPHMW_E_STATE; }
+    if (c->comm) { sphmw_set_error("comm_init: context already has a communicator"); return SPHMW_E_STATE; }
+    TRY(nccl_load());
+    SlabComm *m = new SlabComm();
+    c->comm = m;
+    m->rank = rank;
+    m->world = world;
+    m->has[0] = c->slab_lo > 0;
+    m->has[1] = c->slab_hi < c->global_cols;
+    if (m->has[0] != (rank > 0) || m->has[1] != (rank < world - 1)) {
+        sphmw_set_error("comm_init: rank %d of %d does not match the slab [%lld,%lld) of %lld columns", rank, world,
+                        (long long)c->slab_lo, (long long)c->slab_hi, (long long)c->global_cols);
+        sphmw_comm_free(c);
+        return SPHMW_E_INVALID;
+    }
+    m->peer[0] = rank - 1;
+    m->peer[1] = rank + 1;
+    m->cap = halo_capacity;
+    int rc = [&]() -> int {
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof(id));
+        NCCL_TRY(g_nccl.CommInitRank(&m->comm, world, id, rank));
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaEventCreateWithFlags(&m->recv_event, cudaEventDisableTiming));
+        CUDA_TRY(cudaMallocHost(&m->h_head, sizeof(double) * 2 * HALO_RECORD));
+        for (int s = 0; s < 2; ++s)
+            if (m->has[s]) {
+                const size_t bytes = sizeof(double) * HALO_RECORD * (size_t)(m->cap + 1);
+                CUDA_TRY(cudaMalloc(&m->send[s], bytes));
+                CUDA_TRY(cudaMalloc(&m->recv[s], bytes));
+                CUDA_TRY(cudaMemsetAsync(m->send[s], 0, bytes, c->stream));
+                CUDA_TRY(cudaMemsetAsync(m->recv[s], 0, bytes, c->stream));
+            }
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return SPHMW_OK;
+    }();
+    if (rc != SPHMW_OK) sphmw_comm_free(c);
+    return rc;
+}
+
+extern "C" int sphmw_comm_info(sphmw_ctx *c, int64_t out[6]) {
+    if (!c || !out) return SPHMW_E_INVALID;
+    for (int k = 0; k < 6; ++k) out[k] = 0;
+    if (!c->comm) return SPHMW_OK;
+    out[0] = c->comm->world;
+    out[1] = c->comm->exchanges;
+    out[2] = c->comm->renegotiations;
+    out[3] = c->comm->send_rows[0] + c->comm->send_rows[1];
+    out[4] = c->comm->lost;
+    out[5] = c->comm->cap;
+    return SPHMW_OK;
+}
+
+static int64_t rows_for(int64_t count) { return 1 + count + count / 8 + 1024; }
+
+// one group: `rows[s]` rows to/from each neighbour; the received headers follow to pinned memory
+static int comm_round(sphmw_ctx *c, const int64_t srows[2], const int64_t rrows[2]) {
+    SlabComm *m = c->comm;
+    NCCL_TRY(g_nccl.GroupStart());
+    for (int s = 0; s < 2; ++s) {
+        if (!m->has[s]) continue;
+        if (srows[s] > 0)
+            NCCL_TRY(g_nccl.Send(m->send[s], (size_t)srows[s] * HALO_RECORD, ncclDouble, m->peer[s], m->comm, m->stream));
+        if (rrows[s] > 0)
+            NCCL_TRY(g_nccl.Recv(m->recv[s], (size_t)rrows[s] * HALO_RECORD, ncclDouble, m->peer[s], m->comm, m->stream));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    for (int s = 0; s < 2; ++s)
+        if (m->has[s] && rrows[s] > 0)
+            CUDA_TRY(cudaMemcpyAsync(m->h_head + s * HALO_RECORD, m->recv[s], sizeof(double) * HALO_RECORD,
+                                     cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaEventRecord(m->recv_event, m->stream));
+    return SPHMW_OK;
+}
+
+// records packed (pack_event recorded on the main stream) -> neighbours -> unpacked.
+// The host waits once, for the received headers.
+static int comm_transfer_and_unpack(sphmw_ctx *c) {
+    SlabComm *m = c->comm;
+    CUDA_TRY(cudaStreamWaitEvent(m->stream, c->pack_event, 0));
+    const bool agreed = (!m->has[0] || m->send_rows[0] > 0) && (!m->has[1] || m->send_rows[1] > 0);
+    const int64_t one[2] = {1, 1};
+    if (agreed) TRY(comm_round(c, m->send_rows, m->recv_rows));
+    else TRY(comm_round(c, one, one));  // first exchange: headers only
+    CUDA_TRY(cudaEventSynchronize(m->recv_event));
+    // the pack's counters were copied to the host before pack_event
+    int64_t counts[5];
+    TRY(sphmw_halo_pack_collect_nowait(c, m->cap, counts));
+    m->lost += counts[4];
+    int64_t in_count[2] = {0, 0}, in_migr[2] = {0, 0};
+    for (int s = 0; s < 2; ++s)
+        if (m->has[s]) {
+            in_count[s] = (int64_t)m->h_head[s * HALO_RECORD];
+            in_migr[s] = (int64_t)m->h_head[s * HALO_RECORD + 1];
+            if (in_count[s] > m->cap) {
+                sphmw_set_error("halo message of %lld records exceeds the buffer capacity %lld", (long long)in_count[s],
+                                (long long)m->cap);
+                return SPHMW_E_CAPACITY;
+            }
+        }
+    // a count that does not fit the agreed size (or no size yet): both ends see it — the sender in
+    // its own counters, the receiver in the header — and repeat that direction with a new size
+    int64_t srows[2] = {0, 0}, rrows[2] = {0, 0};
+    bool again = false;
+    for (int s = 0; s < 2; ++s) {
+        if (!m->has[s]) continue;
+        if (counts[s] + 1 > m->send_rows[s]) {
+            m->send_rows[s] = std::min<int64_t>(rows_for(counts[s]), m->cap + 1);
+            srows[s] = m->send_rows[s];
+            again = true;
+        }
+        if (in_count[s] + 1 > m->recv_rows[s]) {
+            m->recv_rows[s] = std::min<int64_t>(rows_for(in_count[s]), m->cap + 1);
+            rrows[s] = m->recv_rows[s];
+            again = true;
+        }
+    }
+    if (again) {
+        m->renegotiations += agreed ? 1 : 0;
+        TRY(comm_round(c, srows, rrows));
+        CUDA_TRY(cudaEventSynchronize(m->recv_event));
+    }
+    m->exchanges += 1;
+    // the main stream appends what arrived (the transfer is complete: the host has waited for it)
+    for (int s = 0; s < 2; ++s)
+        if (m->has[s] && in_count[s] > 0)
+            TRY(sphmw_halo_unpack(c, m->recv[s] + HALO_RECORD, in_count[s], in_migr[s]));
+    return SPHMW_OK;
+}
+
+static int comm_exchange_all(sphmw_ctx *c) {
+    SlabComm *m = c->comm;
+    TRY(sphmw_halo_pack_enqueue(c, m->send[0], m->send[1], m->cap, false));
+    return comm_transfer_and_unpack(c);
+}
+
+// ≙ create_cell_list!(sys) on a slab context: halo exchange, then the sort
+int sphmw_comm_create_cell_list(sphmw_ctx *c, int64_t *n_alive) {
+    if (c->overlap_stage != 0) { sphmw_set_error("create_cell_list: an overlapped step is in flight"); return SPHMW_E_STATE; }
+    TRY(comm_exchange_all(c));
+    return sphmw_build_cell_list(c, n_alive);
+}
+
+// nsteps of the fused "wcsph" step (wcsph_perturbed_witch.jl:309-332) on a slab context.  All
+// but the last step run the overlapped schedule of pair_ops.cu: the edge columns are advanced and
+// packed first and their records travel while the interior columns are in the force pass.
+int sphmw_comm_step(sphmw_ctx *c, const char *scheme, int nsteps) {
+    SlabComm *m = c->comm;
+    if (strcmp(scheme, "wcsph")) {
+        sphmw_set_error("step: only the fused 'wcsph' scheme runs on slabs");
+        return SPHMW_E_UNSUPPORTED_OP;
+    }
+    if (nsteps <= 0) return SPHMW_OK;
+    const bool overlap = nsteps > 1 && !(c->flags & SPHMW_FLAG_CELL_PAIRS) && !getenv("SPHMW_NO_OVERLAP");
+    if (!overlap) {
+        for (int k = 0; k < nsteps; ++k) {
+            TRY(sphmw_step_wcsph_phase(c, 0));
+            TRY(comm_exchange_all(c));
+            TRY(sphmw_step_wcsph_phase(c, 1));
+        }
+        return SPHMW_OK;
+    }
+    TRY(sphmw_step_wcsph_phase(c, 0));
+    TRY(comm_exchange_all(c));
+    for (int k = 0; k + 1 < nsteps; ++k) {
+        TRY(sphmw_step_wcsph_phase(c, 2));                                          // edge columns first
+        TRY(sphmw_halo_pack_enqueue(c, m->send[0], m->send[1], m->cap, true));    // their records
+        c->overlap_stage = 2;
+        TRY(sphmw_step_wcsph_phase(c, 3));                                          // interior, enqueued only
+        c->overlap_stage = 0;
+        TRY(comm_transfer_and_unpack(c));  // travels beside the interior force pass
+    }
+    return sphmw_step_wcsph_phase(c, 1);
+}

@@ -200,6 +200,7 @@ __device__ __forceinline__ void nb_store(NbRec *p, double a, double b, double c,
 
 struct PairList {
     uint32_t *list;
+    uint32_t *list16;  // tiled kernels (pair_tile.cuh): 16-bit tile slots, two per word
     uint32_t *cnt;
     NbRec *recA, *recB, *recC;  // null unless SPHMW_FLAG_PACKED_RECORDS
     // 10-bit-per-axis mirror: the position inside its own cell in units of h/1024, x | y<<10 | z<<20
@@ -242,6 +243,15 @@ struct sphmw_ctx {
     uint32_t *pos_of_idx = nullptr;               // inverse map (whole-domain contexts only)
     uint32_t *tag = nullptr, *tag_alt = nullptr;  // TAG_OWNED / TAG_GHOST / TAG_DEAD per position
     int64_t n_owned = 0;                          // slab mode: resident particles this rank owns
+    // dead particles the next cell-list build will meet (halo.cu: ghosts and migrants of the last
+    // exchange + particles dropped by the pack): with it the build needs no host round trip
+    int64_t slab_dead_expected = 0;
+    bool slab_dead_known = false;
+    uint32_t *h_slab_check = nullptr;             // pinned ring: what the device counted, verified one build later
+    cudaEvent_t slab_check_event[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t slab_check_want[4][2] = {};           // the host's figures for the same builds
+    uint64_t slab_checks = 0;
+    struct SlabComm *comm = nullptr;              // NCCL halo transport (slab_comm.cu)
     uint32_t *halo_counters = nullptr;            // device: [0] left records [1] right records
                                                   // [2] left migrants [3] right migrants [4] lost
     uint32_t *h_halo_counters = nullptr;          // pinned mirror
@@ -271,6 +281,10 @@ struct sphmw_ctx {
     bool want_list = false;        // build the list in the next binary pass
     int passes_this_gen = 0;       // binary passes since the last cell-list build
     int64_t pl_builds = 0;
+    int pl_format = 0;             // what the valid list holds: 0 global positions, 1 tile slots
+    // neighbourhood tiles (tile_map.cuh): one record per block of TM_BLOCK particles
+    uint32_t *tile_tab = nullptr;
+    uint64_t tile_gen = ~0ull;     // cell-list generation the records were built for
 
     double *staging = nullptr;  // 3*cap doubles
     double *reduce_tmp = nullptr;
@@ -293,6 +307,12 @@ struct sphmw_ctx {
     std::vector<cudaEvent_t> event_pool;
     int64_t launches = 0;
 };
+
+// the fused pair passes read packed neighbour records unless told otherwise (sphmw.h)
+static inline bool sphmw_use_records(const sphmw_ctx *c) {
+    return !(c->flags & (SPHMW_FLAG_NO_PACKED_RECORDS | SPHMW_FLAG_NO_PAIR_LIST | SPHMW_FLAG_CELL_PAIRS |
+                         SPHMW_FLAG_TILES | SPHMW_FLAG_NO_PRETEST));
+}
 
 // error plumbing -----------------------------------------------------------
 void sphmw_set_error(const char *fmt, ...);
@@ -334,6 +354,7 @@ int64_t sphmw_list_ops(char *buf, int64_t cap);
 int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n);
 int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added);
 int sphmw_pair_list_stats(sphmw_ctx *c, int64_t out[4]);
+int sphmw_tile_stats(sphmw_ctx *c, int64_t out[6]);
 int sphmw_ensure_records(sphmw_ctx *c);  // api.cu: allocate the packed neighbour records
 // column sets of the overlapped slab step (local column indices)
 struct SlabCols {
@@ -345,6 +366,13 @@ SlabCols sphmw_slab_cols(const sphmw_ctx *c);
 SlabCols sphmw_slab_cols_of(int W, bool has_left, bool has_right);
 // implemented in cell_list.cu
 int sphmw_exclusive_scan_u32(sphmw_ctx *c, uint32_t *data, int64_t n);
+// implemented in halo.cu / slab_comm.cu
+int sphmw_halo_pack_enqueue(sphmw_ctx *c, double *msg_left, double *msg_right, int64_t cap_records, bool edge_only);
+int sphmw_halo_pack_collect_nowait(sphmw_ctx *c, int64_t cap_records, int64_t counts[5]);
+int sphmw_comm_step(sphmw_ctx *c, const char *scheme, int nsteps);
+int sphmw_comm_create_cell_list(sphmw_ctx *c, int64_t *n_alive);
+void sphmw_comm_free(sphmw_ctx *c);
+int sphmw_step_wcsph_phase(sphmw_ctx *c, int phase);  // pair_ops.cu
 // implemented in frame_io.cpp
 int sphmw_write_vtp(const char *path, int64_t n, const double *points3n, int nfields,
                     const char *const *names, const int *ncomps, const double *const *data);

@@ -93,7 +93,7 @@ struct PairOpBase {
     // shared-memory tiles (pair_tile.cuh): number of field arrays the operator stages (0: the
     // operator has no tiled variant)
     template <int DIM>
-    static constexpr int tile_fields() { return 0; }
+    __host__ __device__ static constexpr int tile_fields() { return 0; }
 };
 
 // what the fused density pass leaves behind for p (shared by the strict and fast variants)
@@ -161,9 +161,9 @@ __host__ __device__ constexpr int wcsph_force_tile_index(int slot) {
 struct B_wcsph_density_fused : PairOpBase {
     static constexpr int REC_KIND = 1;
     template <int DIM>
-    static constexpr int tile_fields() { return DIM + 1; }
+    __host__ __device__ static constexpr int tile_fields() { return DIM + 1; }
     template <int DIM>
-    static constexpr int tile_index(int slot) { return wcsph_density_tile_index<DIM>(slot); }
+    __host__ __device__ static constexpr int tile_index(int slot) { return wcsph_density_tile_index<DIM>(slot); }
     double rho, hp;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &, int64_t p) {
@@ -191,9 +191,9 @@ struct B_wcsph_density_fused : PairOpBase {
 struct B_wcsph_momentum_fused : PairOpBase {
     static constexpr int REC_KIND = 2;
     template <int DIM>
-    static constexpr int tile_fields() { return DIM == 2 ? 9 : 9; }
+    __host__ __device__ static constexpr int tile_fields() { return DIM == 2 ? 9 : 9; }
     template <int DIM>
-    static constexpr int tile_index(int slot) { return wcsph_force_tile_index<DIM>(slot); }
+    __host__ __device__ static constexpr int tile_index(int slot) { return wcsph_force_tile_index<DIM>(slot); }
     double dv0, dv1, dv2, v0, v1, v2, hp, prho, pr2, cs;
     // the velocity is double-buffered: a skipped (ghost) particle carries its value over
     template <int DIM>
@@ -269,9 +269,9 @@ __device__ __forceinline__ double fast_sqrt_pos(double a) {
 struct B_wcsph_density_fast : PairOpBase {
     static constexpr int REC_KIND = 1;
     template <int DIM>
-    static constexpr int tile_fields() { return DIM + 1; }
+    __host__ __device__ static constexpr int tile_fields() { return DIM + 1; }
     template <int DIM>
-    static constexpr int tile_index(int slot) { return wcsph_density_tile_index<DIM>(slot); }
+    __host__ __device__ static constexpr int tile_index(int slot) { return wcsph_density_tile_index<DIM>(slot); }
     double rho, hp, inv_h, cw;
     template <int DIM>
     __device__ void init(const Fields &f, const Params &, int64_t p) {
@@ -306,9 +306,9 @@ struct B_wcsph_density_fast : PairOpBase {
 struct B_wcsph_momentum_fast : PairOpBase {
     static constexpr int REC_KIND = 2;
     template <int DIM>
-    static constexpr int tile_fields() { return DIM == 2 ? 9 : 9; }
+    __host__ __device__ static constexpr int tile_fields() { return DIM == 2 ? 9 : 9; }
     template <int DIM>
-    static constexpr int tile_index(int slot) { return wcsph_force_tile_index<DIM>(slot); }
+    __host__ __device__ static constexpr int tile_index(int slot) { return wcsph_force_tile_index<DIM>(slot); }
     double dv0, dv1, dv2, v0, v1, v2, hp, prho, pr2, cs;
     template <int DIM>
     static __device__ void skip(const Fields &f, const Fields &out, int64_t p) {

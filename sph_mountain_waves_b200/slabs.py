@@ -243,6 +243,8 @@ class SlabRun:
         self.case_info = {}
         self._pinned = None
         self._owned_host = None
+        self._lib_comm = False
+        self._in_flight = None
 
     @property
     def world(self):
@@ -383,13 +385,55 @@ class SlabRun:
         b = self.backend
         sl, sr, ml, mr = b.pack()
         (rl, nml), (rr, nmr) = exchange(self.plan, sl, sr, ml, mr, b.empty)
+        self._wait_for_records(b)
         b.unpack(rl, nml)
         b.unpack(rr, nmr)
+        self._in_flight = (rl, rr)   # keep the receive tensors until the next exchange: unpack is asynchronous
+
+    @staticmethod
+    def _wait_for_records(b):
+        """The receives complete on torch's current stream, the unpack kernel runs on the context's
+        own stream: the host waits for the former before it queues the latter."""
+        import torch
+        if getattr(b, "dev", None) is not None:
+            torch.cuda.current_stream(b.dev).synchronize()
+
+    # ------------------------------------------------------------------ transport inside the library
+    def use_library_transport(self, halo_capacity: Optional[int] = None):
+        """Hand the halo exchange to libsphmw (csrc/slab_comm.cu: ncclSend/ncclRecv on its own
+        stream, driven by sphmw_step / sphmw_create_cell_list).  Collective over torch.distributed:
+        rank 0 creates the NCCL id, everybody joins."""
+        import torch
+        import torch.distributed as dist
+        if self.backend is None or self.plan.world == 1 or self._lib_comm:
+            return self
+        lib = _capi.lib()
+        dev = torch.device("cuda", self.sys.device)
+        ident = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if self.plan.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            check(lib.sphmw_comm_unique_id(buf))
+            ident = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(ident, 0)
+        cap = torch.tensor([int(halo_capacity or self.backend.cap)], dtype=torch.int64, device=dev)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX)   # the same capacity on every rank
+        raw = bytes(ident.cpu().tolist())
+        check(lib.sphmw_comm_init(self.sys.ctx, self.plan.rank, self.plan.world, raw, int(cap.item())))
+        self._lib_comm = True
+        return self
+
+    def comm_info(self) -> dict:
+        out = (C.c_int64 * 6)()
+        check(_capi.lib().sphmw_comm_info(self.sys.ctx, out))
+        return {"world": out[0], "exchanges": out[1], "renegotiations": out[2], "message_rows": out[3],
+                "lost": out[4], "capacity": out[5]}
 
     def create_cell_list(self):
         """≙ create_cell_list!(sys): (halo exchange +) sort.  Ghosts exist from here on."""
         if self.backend is None:
             self.sys.create_cell_list()
+        elif self._lib_comm:
+            self.sys.create_cell_list(want_count=False)   # the library exchanges the halo itself
         else:
             self._halo()
             self.backend.build()
@@ -403,6 +447,13 @@ class SlabRun:
             self.sys.step(nsteps)
             return
         if nsteps <= 0:
+            return
+        if self._lib_comm:
+            if overlap:
+                self.sys.step(nsteps)
+            else:
+                for _ in range(nsteps):
+                    self.sys.step(1)      # single steps take the plain schedule
             return
         if not (overlap and nsteps > 1 and getattr(b, "can_overlap", False)):
             for _ in range(nsteps):
@@ -425,6 +476,7 @@ class SlabRun:
             comm.synchronize()                     # records have arrived (and the sends have left)
             b.unpack(rl, nml)
             b.unpack(rr, nmr)
+            self._in_flight = (rl, rr)
         b.post()
 
     # ------------------------------------------------------------------ read-back (tests)
@@ -536,14 +588,23 @@ class LocalCluster:
             r.backend.build()
 
     def _handover(self, packs):
+        import torch
+        keep = []
         for r, run in enumerate(self.runs):
             dev = run.backend.dev
+            inbox = []
             if r > 0:
                 sl, sr, ml, mr = packs[r - 1]
-                run.backend.unpack(sr.to(dev), mr)      # my left neighbour's right-going records
+                inbox.append((sr.to(dev), mr))          # my left neighbour's right-going records
             if r < len(self.runs) - 1:
                 sl, sr, ml, mr = packs[r + 1]
-                run.backend.unpack(sl.to(dev), ml)      # my right neighbour's left-going records
+                inbox.append((sl.to(dev), ml))          # my right neighbour's left-going records
+            # the copies run on torch's current stream, the unpack on the context's own
+            torch.cuda.current_stream(dev).synchronize()
+            for rec, migr in inbox:
+                run.backend.unpack(rec, migr)
+            keep.append(inbox)
+        self._in_flight = keep   # alive until the next handover: unpack is asynchronous
 
     def step(self, nsteps: int, overlap: bool = True):
         if nsteps <= 0:

@@ -285,7 +285,14 @@ class ParticleSystem:
         """stride, lists built, particles that overflowed the stride, device bytes"""
         out = (C.c_int64 * 4)()
         check(_capi.lib().sphmw_pair_list_info(self.ctx, out))
-        return {"stride": out[0], "builds": out[1], "overflow": out[2], "bytes": out[3]}
+        info = {"stride": out[0], "builds": out[1], "overflow": out[2], "bytes": out[3]}
+        t = (C.c_int64 * 6)()
+        check(_capi.lib().sphmw_tile_info(self.ctx, t))
+        if t[0]:
+            info["tiles"] = {"blocks": t[0], "staged": t[1], "max_slots": t[2],
+                             "mean_slots": (t[3] / t[1]) if t[1] else None, "capacity": t[4],
+                             "too_many_rows": t[5]}
+        return info
 
     def sync(self):
         if self._ctx is not None:

@@ -28,11 +28,16 @@
 #include "cuda_runtime.h"
 #include "cell_gather.cuh"
 #include "pair_list.cuh"
+#include "pair_tile.cuh"
 #include "sphmw_internal.h"
 #include "wcsph_ops.cuh"
 
 uint3 threadIdx, blockIdx, blockDim;
 uint32_t nl_queue[96 * NL_BLOCK];
+// the tiled kernels' shared window (pair_tile.cuh) and the sync-point bookkeeping of their emulation
+alignas(16) unsigned char emu_tile_smem[256 * 1024];
+int emu_phase = 0, emu_sync_seen = 0;
+bool emu_block_or = false;
 
 void sphmw_set_error(const char *fmt, ...) {
     va_list ap;
@@ -51,6 +56,26 @@ static void launch(int64_t n, F &&thread_body) {
             threadIdx = uint3{t, 0, 0};
             thread_body();
         }
+    }
+}
+
+// A tiled kernel has four block-wide sync points (selection vote, table loaded, slot positions
+// written, fields copied):
+// every "thread" runs up to sync point k in pass k — what precedes a sync point is idempotent —
+// and to the end in the last pass.
+template <class F>
+static void launch_tiled(int64_t n, F &&thread_body) {
+    blockDim = uint3{TM_BLOCK, 1, 1};
+    for (int64_t b = 0; b * TM_BLOCK < n; ++b) {
+        blockIdx = uint3{(unsigned)b, 0, 0};
+        emu_block_or = false;
+        memset(emu_tile_smem, 0xA5, sizeof(emu_tile_smem));  // stale bytes must never be read
+        for (emu_phase = 0; emu_phase < 5; ++emu_phase)
+            for (unsigned t = 0; t < TM_BLOCK; ++t) {
+                threadIdx = uint3{t, 0, 0};
+                emu_sync_seen = 0;
+                thread_body();
+            }
     }
 }
 
@@ -73,7 +98,7 @@ static void walk_thread(Fields f, Fields out, Params prm, Grid g, const uint32_t
 struct State {
     int64_t n = 0;
     std::vector<double> cur[NSLOT], alt[NSLOT];
-    std::vector<uint32_t> key, cellx, cell_start, idx, xq, list, cnt;
+    std::vector<uint32_t> key, cellx, cell_start, idx, xq, list, cnt, list16, tile_tab;
     std::vector<NbRec> rec[3];
     Fields fcur{}, falt{};
     void bind() {
@@ -90,6 +115,7 @@ struct Result {
     std::vector<double> fields[9], vnew[3], vold[3];
     std::vector<uint32_t> column;  // cell column of every particle (reference index order)
     unsigned long long pairs_density = 0, pairs_force = 0, overflow = 0;
+    long long tiled_blocks = 0, blocks = 0;  // tiles variants: blocks with a staged tile
     bool same_as(const Result &o) const {
         for (int k = 0; k < 9; ++k)
             if (memcmp(fields[k].data(), o.fields[k].data(), sizeof(double) * fields[k].size())) return false;
@@ -99,7 +125,7 @@ struct Result {
     }
 };
 
-enum Variant { WALK, LIST_Q10, LIST_F64, RECORDS, SLAB_LIST, SLAB_RECORDS };
+enum Variant { WALK, LIST_Q10, LIST_F64, RECORDS, TILES, SLAB_LIST, SLAB_RECORDS, SLAB_TILES };
 
 template <int DIM, class DensityOp, class ForceOp>
 static Result run_variant(State st, const Grid &g, const Params &prm, Variant v, int stride) {
@@ -117,6 +143,8 @@ static Result run_variant(State st, const Grid &g, const Params &prm, Variant v,
     pl.recA = st.rec[0].data();
     pl.recB = st.rec[1].data();
     pl.recC = st.rec[2].data();
+    pl.list16 = st.list16.data();
+    const uint32_t *tab = st.tile_tab.data();
     const uint32_t *key = st.key.data(), *cellx = st.cellx.data(), *cs = st.cell_start.data();
     // density pass (in place), then force pass (new velocity into alt)
     if (v == WALK) {
@@ -131,6 +159,14 @@ static Result run_variant(State st, const Grid &g, const Params &prm, Variant v,
     } else if (v == RECORDS) {
         launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q10, true>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cf, pl); });
         launch(n, [&] { k_binary_list<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cf, pl); });
+    } else if (v == TILES) {
+        for (size_t b = 0; b * TM_WORDS < st.tile_tab.size(); ++b) {
+            const uint32_t *rec = tab + b * TM_WORDS;
+            r.blocks += 1;
+            r.tiled_blocks += rec[1] <= (uint32_t)tm_max_pieces(g) && rec[2] <= (uint32_t)TileGeom<DIM>::CAP;
+        }
+        launch_tiled(n, [&] { k_tile_build<DIM, DensityOp>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cf, pl, tab); });
+        launch_tiled(n, [&] { k_tile_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cf, pl, tab); });
     } else {
         // the column filters of a slab context (pair_ops.cu filter_for_depth): the density pass
         // covers all but the outermost column of each side, the force pass all but the outermost
@@ -143,6 +179,10 @@ static Result run_variant(State st, const Grid &g, const Params &prm, Variant v,
             launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q10>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cd, pl); });
             launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge, pl); });
             launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[3], cint, pl); });
+        } else if (v == SLAB_TILES) {
+            launch_tiled(n, [&] { k_tile_build<DIM, DensityOp>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cd, pl, tab); });
+            launch_tiled(n, [&] { k_tile_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge, pl, tab); });
+            launch_tiled(n, [&] { k_tile_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[3], cint, pl, tab); });
         } else {
             launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q10, true>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cd, pl); });
             launch(n, [&] { k_binary_list<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge, pl); });
@@ -257,8 +297,8 @@ int main(int argc, char **argv) {
     st.xq.assign(n + 4, 0u);
     st.cell_start.assign(g.pkey_max + 2, 0u);
     for (int s = 0; s < NSLOT; ++s) {
-        st.cur[s].assign(n, 0.0);
-        st.alt[s].assign(n, 0.0);
+        st.cur[s].assign(n + 4, 0.0);  // + 4: bulk copies fetch whole groups of 4 particles
+        st.alt[s].assign(n + 4, 0.0);
     }
     for (int k = 0; k < 3; ++k) st.rec[k].assign(n, NbRec{0, 0, 0, 0});
     // the permutation itself is the library's k_gather (csrc/cell_gather.cuh): fields, indices,
@@ -298,6 +338,12 @@ int main(int argc, char **argv) {
     const size_t warps = (size_t)((n + 31) / 32);
     st.list.assign(warps * (size_t)stride * 32, 0u);
     st.cnt.assign(n, 0u);
+    st.list16.assign(warps * (size_t)((stride + 1) / 2) * 32, 0u);
+    // the tile map of this cell list (csrc/tile_map.cuh), one record per block
+    const int64_t nblocks = (n + TM_BLOCK - 1) / TM_BLOCK;
+    st.tile_tab.assign((size_t)nblocks * TM_WORDS, 0u);
+    for (int64_t b = 0; b < nblocks; ++b)
+        tm_build_record(g, st.key.data(), st.cellx.data(), st.cell_start.data(), n, b, st.tile_tab.data() + (size_t)b * TM_WORDS);
     return 0;
     };
     State st;
@@ -330,7 +376,7 @@ int main(int argc, char **argv) {
             });
             st = State();
             if (build_state(st)) return 3;
-            const Result r = run((Variant)(step % 4));
+            const Result r = run((Variant)(step % 5));
             pairs = r.pairs_force;
             for (int64_t i = 0; i < n; ++i) {
                 in[8][i] = r.fields[0][i];   // rho
@@ -354,10 +400,12 @@ int main(int argc, char **argv) {
         return 0;
     }
     const Result base = run(WALK);
-    static const char *NAMES[] = {"walk", "list", "list_f64", "records", "slab_list", "slab_records"};
+    static const char *NAMES[] = {"walk", "list", "list_f64", "records", "tiles", "slab_list", "slab_records", "slab_tiles"};
     unsigned long long overflow = 0;
-    for (Variant v : {LIST_Q10, LIST_F64, RECORDS}) {
+    long long tiled_blocks = 0, blocks = 0;
+    for (Variant v : {LIST_Q10, LIST_F64, RECORDS, TILES}) {
         const Result r = run(v);
+        if (v == TILES) tiled_blocks = r.tiled_blocks, blocks = r.blocks;
         if (!r.same_as(base)) {
             fprintf(stderr, "emu_pairs: variant '%s' differs from the cell walk (pairs %llu/%llu vs %llu/%llu)\n",
                     NAMES[v], r.pairs_density, r.pairs_force, base.pairs_density, base.pairs_force);
@@ -367,7 +415,7 @@ int main(int argc, char **argv) {
     }
     if (g.lim[0] >= 10) {
         const int W = (int)g.lim[0];
-        for (Variant v : {SLAB_LIST, SLAB_RECORDS}) {
+        for (Variant v : {SLAB_LIST, SLAB_RECORDS, SLAB_TILES}) {
             const Result r = run(v);
             for (int64_t i = 0; i < n; ++i) {
                 const int c = (int)r.column[i];
@@ -398,8 +446,8 @@ int main(int argc, char **argv) {
     for (int k = 0; k < 7; ++k) fwrite(base.fields[k].data(), sizeof(double), n, out);  // rho .. P
     for (int k = 0; k < 3; ++k) fwrite(base.vnew[k].data(), sizeof(double), n, out);
     fclose(out);
-    printf("emu_pairs: n=%lld dim=%d pairs=%llu overflow=%llu cx_shift=%d: walk == list == list_f64 == records"
-           " (== slab-filtered launches on their columns)\n",
-           (long long)n, dim, base.pairs_force, overflow, g.cx_shift);
+    printf("emu_pairs: n=%lld dim=%d pairs=%llu overflow=%llu cx_shift=%d tiled=%lld/%lld: walk == list == list_f64 =="
+           " records == tiles (== slab-filtered launches on their columns)\n",
+           (long long)n, dim, base.pairs_force, overflow, g.cx_shift, tiled_blocks, blocks);
     return 0;
 }

@@ -13,6 +13,7 @@ to match the oracle exactly — neighbour order, accepted set and arithmetic.
 This checks the kernels' LOGIC on the CPU; parity of the compiled device code is the job of the
 `-m gpu` tests.  Nothing here is a product path.
 """
+import re
 import struct
 import subprocess
 from pathlib import Path
@@ -37,7 +38,8 @@ def emu_binary():
     out = EMU / "build" / "emu_pairs"
     out.parent.mkdir(exist_ok=True)
     deps = [EMU / "emu_pairs.cpp", EMU / "cuda_runtime.h", CSRC / "pair_list.cuh", CSRC / "wcsph_ops.cuh",
-            CSRC / "kernels_sph.cuh", CSRC / "cell_gather.cuh", CSRC / "sphmw_internal.h", CSRC / "grid_setup.cpp"]
+            CSRC / "kernels_sph.cuh", CSRC / "cell_gather.cuh", CSRC / "sphmw_internal.h", CSRC / "grid_setup.cpp",
+            CSRC / "pair_tile.cuh", CSRC / "tile_map.cuh", CSRC / "q_access.cuh"]
     if not out.exists() or any(d.stat().st_mtime > out.stat().st_mtime for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wno-attributes", "-DSPHMW_EMU",
                         f"-I{EMU}", f"-I{ROOT / 'include'}", f"-I{CSRC}", str(EMU / "emu_pairs.cpp"),
@@ -70,8 +72,9 @@ def run_emulation(binary, tmp_path, case, fields, fast, stride, cx_shift=-1, nst
     out["v"] = arr[7:10].T
     if nsteps:   # whole steps: only rho, h, v and x are meaningful
         out = {"rho": arr[0], "h": arr[3], "v": arr[7:10].T, "x": arr[10:13].T}
+    m = re.search(r"tiled=(\d+)/(\d+)", r.stdout)
     return dict(n=meta[0], dim=meta[1], pairs_density=meta[2], pairs_force=meta[3], overflow=meta[4],
-                cx_shift=meta[5]), out
+                cx_shift=meta[5], tiled=int(m.group(1)) if m else None, blocks=int(m.group(2)) if m else None), out
 
 
 def advanced_state(case, warm_steps=1):
@@ -98,6 +101,10 @@ def finish_step(o):
 CASES = {
     "hill3d": lambda: cases.bell_hill_3d(24, 12, 10, h_m=3000.0, a=8e3, U=20.0),
     "witch2d": lambda: cases.mountain_wave_2d(n_y=24.0, dom_length=80e3, h_m=3000.0, a=10e3, U=20.0),
+    # long rows of cells: most blocks of 128 particles sit in one or two chunk rows, so the tiled
+    # kernels (csrc/pair_tile.cuh) stage their neighbourhood instead of falling back to the walk
+    "long3d": lambda: cases.bell_hill_3d(100, 8, 6, h_m=2000.0, a=8e3, U=20.0),
+    "long2d": lambda: cases.mountain_wave_2d(n_y=16.0, dom_length=400e3, h_m=3000.0, a=10e3, U=20.0),
 }
 
 
@@ -112,14 +119,18 @@ def test_strict_kernels_equal_the_oracle_bit_for_bit(emu_binary, tmp_path, name,
     pairs = finish_step(o)
     assert meta["n"] == case.n and meta["dim"] == case.dim and meta["overflow"] == 0
     assert meta["pairs_density"] == meta["pairs_force"] == pairs
+    if name.startswith("long") and cx_shift < 0:
+        assert meta["tiled"] >= 0.6 * meta["blocks"], meta  # the tiled path really ran
     for f in ("rho", "rho_bg", "rho_p", "h", "P_bg", "P_p", "P", "v"):
         assert n_mismatch(got[f], o.field(f)) == 0, f
 
 
 @pytest.mark.parametrize("name", list(CASES))
 def test_fast_kernels_within_tolerance_and_overflow_path(emu_binary, tmp_path, name):
-    """FAST_MATH closures (FMA, reciprocals): same pairs, fields within 1e-13 of the oracle; a
-    stride of 8 makes every particle overflow its list and walk the cells inside the list kernels"""
+    """FAST_MATH closures (FMA, reciprocals): same pairs, fields within the north star's 1e-10 of the
+    oracle under the per-component + element-wise metric of util.rel_err (absolute differences are
+    ~1 ulp of |v|, i.e. 2e-13 of the smallest velocity component's scale); a stride of 8 makes every
+    particle overflow its list and walk the cells inside the list kernels"""
     case = CASES[name]()
     o, fields = advanced_state(case)
     pairs = None
@@ -130,7 +141,8 @@ def test_fast_kernels_within_tolerance_and_overflow_path(emu_binary, tmp_path, n
         assert meta["pairs_density"] == meta["pairs_force"] == pairs
         assert (meta["overflow"] > 0) == (stride == 8)
         for f in ("rho", "h", "P", "v"):
-            assert rel_err(got[f], o.field(f)) <= 1e-13, (stride, f)
+            assert rel_err(got[f], o.field(f)) <= 1e-10, (stride, f)
+            assert rel_err(got[f], o.field(f), floor=1.0) <= 1e-12, (stride, f)   # per component only
 
 
 def test_disordered_particles(emu_binary, tmp_path):

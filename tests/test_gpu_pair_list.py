@@ -212,22 +212,32 @@ def test_cutoff_boundary_in_3d_across_cell_faces(gpu):
 
 
 # ---------------------------------------------------------------------------------------
-# SPHMW_FLAG_PACKED_RECORDS (experimental, default off): written after the round's GPU budget was
-# spent, so it has only ever been compiled.  Opt in with SPHMW_TEST_EXPERIMENTAL=1.
+# Variants of the fused pair passes.  Default: packed neighbour records (three 32-byte records,
+# 256-bit loads); NO_RECORDS: eleven SoA gathers; TILES: neighbourhood of each block staged in
+# shared memory (csrc/pair_tile.cuh).  All must give the same bits.
 # ---------------------------------------------------------------------------------------
-PACKED = 32
-experimental = pytest.mark.skipif(os.environ.get("SPHMW_TEST_EXPERIMENTAL") != "1",
-                                  reason="experimental path, never run on a GPU yet: set SPHMW_TEST_EXPERIMENTAL=1")
+NO_RECORDS = 128
+TILES = 64
 
 
-@experimental
-@pytest.mark.parametrize("make", [small_2d, small_3d])
+def long_3d():
+    """rows of ~60 cells: most blocks of 128 particles sit in one or two chunk rows, so the tiled
+    kernels stage their neighbourhood instead of falling back to the cell walk"""
+    return cases.bell_hill_3d(100, 8, 6, h_m=2000.0, a=8e3, U=20.0)
+
+
+def long_2d():
+    return cases.mountain_wave_2d(n_y=16.0, dom_length=400e3, h_m=3000.0, a=10e3, U=20.0)
+
+
+@pytest.mark.parametrize("make", [small_2d, small_3d, long_2d, long_3d])
 @pytest.mark.parametrize("arith", [0, FAST_MATH])
-def test_packed_records_same_bits(gpu, make, arith):
-    """neighbours read from three 32-byte records with 256-bit loads: bit copies of the SoA
-    fields, so nothing may change"""
+@pytest.mark.parametrize("variant", [NO_RECORDS, TILES])
+def test_pair_pass_variants_same_bits(gpu, make, arith, variant):
+    """records (default) vs SoA gathers vs shared-memory tiles: the neighbour data are bit copies
+    of the SoA fields and the visiting order is the same, so nothing may change"""
     case = make()
-    a, b = load_gpu(case, flags=arith), load_gpu(case, flags=arith | PACKED)
+    a, b = load_gpu(case, flags=arith), load_gpu(case, flags=arith | variant)
     for s in (a, b):
         s.create_cell_list()
         s.count_pairs(True)
@@ -235,16 +245,19 @@ def test_packed_records_same_bits(gpu, make, arith):
     assert a.pair_count() == b.pair_count() > 0
     for f in FIELDS:
         assert bits_equal(a.field(f), b.field(f)), f
+    if variant == TILES and make in (long_2d, long_3d):
+        t = b.pair_list_info()["tiles"]
+        assert t["staged"] >= 0.6 * t["blocks"], t  # the tiled path really ran
 
 
-@experimental
-def test_packed_records_on_slabs_with_the_overlapped_schedule(gpu):
+@pytest.mark.parametrize("variant", [0, TILES])
+def test_pair_pass_variants_on_slabs_with_the_overlapped_schedule(gpu, variant):
     from sph_mountain_waves_b200.slabs import LocalCluster, SlabRun
     case = cases.bell_hill_3d(48, 10, 8, h_m=3000.0, a=8e3, U=20.0)
-    whole = load_gpu(case, flags=FAST_MATH)
+    whole = load_gpu(case, flags=FAST_MATH | NO_RECORDS)
     whole.create_cell_list()
     whole.step(12)
-    cluster = LocalCluster([SlabRun.from_global_case(case, r, 3, flags=FAST_MATH | PACKED) for r in range(3)])
+    cluster = LocalCluster([SlabRun.from_global_case(case, r, 3, flags=FAST_MATH | variant) for r in range(3)])
     cluster.create_cell_list()
     cluster.step(12)
     _, got = cluster.gather(("x", "v", "rho", "h"))
@@ -252,11 +265,11 @@ def test_packed_records_on_slabs_with_the_overlapped_schedule(gpu):
         assert np.array_equal(arr, whole.field(f)), f
 
 
-@experimental
-def test_packed_records_with_overflowing_lists(gpu, monkeypatch):
+@pytest.mark.parametrize("variant", [0, TILES])
+def test_pair_pass_variants_with_overflowing_lists(gpu, monkeypatch, variant):
     monkeypatch.setenv("SPHMW_PAIR_LIST_STRIDE", "12")
-    case = small_3d()
-    a, b = load_gpu(case, flags=NO_LIST), load_gpu(case, flags=PACKED)
+    case = long_3d() if variant == TILES else small_3d()
+    a, b = load_gpu(case, flags=NO_LIST), load_gpu(case, flags=variant)
     for s in (a, b):
         s.create_cell_list()
         s.step(3)

@@ -1,0 +1,33 @@
+"""The real multi-GPU path: world-size-2 (and 4) torchrun runs that step slab contexts through the
+NCCL transports — inside the library (csrc/slab_comm.cu) and the torch.distributed one
+(slabs.exchange) — with the overlapped schedule, and compare bitwise with the whole-domain run.
+Needs as many GPUs as ranks (skipped otherwise: NCCL ranks cannot share a device)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _gpus():
+    try:
+        import torch
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,flags", [(2, 0), (2, 1), (4, 0)])
+def test_nccl_transports_match_the_whole_domain_run(world, flags):
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           str(ROOT / "tests" / "mp" / "slab_nccl_worker.py"), "12", str(flags)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+    assert r.returncode == 0 and "SLAB_NCCL_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
