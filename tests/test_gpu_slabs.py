@@ -5,7 +5,7 @@ import pytest
 
 from sph_mountain_waves_b200 import cases
 from sph_mountain_waves_b200.slabs import LocalCluster, SlabRun
-from util import load_gpu, load_oracle, rel_err
+from util import load_gpu, load_oracle, field_err, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -75,7 +75,7 @@ def test_slab_run_against_oracle(gpu):
     cluster.step(5)
     _, got = cluster.gather(("x", "v", "rho", "h"))
     for f, a in got.items():
-        assert rel_err(a, o.field(f)) <= 1e-10, f
+        assert field_err(case, f, a, o.field(f)) <= 1e-10, f
 
 
 def test_overlapped_step_refuses_fast_particles(gpu):
