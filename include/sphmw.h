@@ -47,7 +47,7 @@ typedef struct sphmw_ctx sphmw_ctx;
  * boundarybox(domain) (structs.jl:63-65); 2D is detected exactly like the
  * reference: key_lim[3] == 1 (structs.jl:70).
  * Slab fields (multi-GPU, no reference equivalent): this context owns the global
- * cell columns [slab_lo, slab_hi) along x and keeps one ghost column each side;
+ * cell columns [slab_lo, slab_hi) along x and keeps two ghost columns each side;
  * slab_lo = slab_hi = -1 means "whole domain". */
 typedef struct sphmw_config {
     double box_min[3];

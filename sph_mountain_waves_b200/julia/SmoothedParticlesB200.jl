@@ -38,7 +38,7 @@ const libsphmw = get(ENV, "LIBSPHMW", joinpath(@__DIR__, "libsphmw.so"))
 abstract type AbstractParticle end
 abstract type Shape end          # geometry.jl adds the shapes and boundarybox (structs.jl:19)
 
-struct SphmwConfig               # == `struct sphmw_config` (include/sphmw.h), 96 bytes
+struct SphmwConfig               # == `struct sphmw_config` (include/sphmw.h), 88 bytes
     box_min::NTuple{3,Cdouble}
     box_max::NTuple{3,Cdouble}
     h::Cdouble
