@@ -36,26 +36,43 @@ def rDwendland3(h, r):                                    # kernels.jl:188-195
     return np.where(x > 1.0, 0.0, -210 / np.pi * (1 - x) ** 3 / h ** 5)
 
 
-def numpy_wcsph_step(case):
-    """verlet_step!, src/current/wcsph_perturbed_witch.jl:309-332, on plain arrays"""
-    p = case.params
-    f = {k: v.copy() for k, v in case.fields.items()}
-    dim3 = case.dim == 3
-    W, rDW = (wendland3, rDwendland3) if dim3 else (wendland2, rDwendland2)
+def _accelerate(f, p, Dv):                               # :298-303, :245-256
     fluid = f["type"] == p["fluid"]
     ey = np.array([0.0, 1.0, 0.0])
+    buoy = -p["g"] * ey[None, :] * (f["rho_p"] / f["rho"])[:, None]
+    sn = np.sin(np.pi / 2 * (1 - (p["z_t"] - p["z_b"]) / p["z_b"]))
+    damp = np.where((f["x"][:, 1] >= p["z_t"] - p["z_b"])[:, None], -p["gamma_r"] * sn ** 2 * ey[None, :], 0.0)
+    f["v"] = np.where(fluid[:, None], f["v"] + 0.5 * p["dt"] * (Dv + buoy + damp), f["v"])
 
-    def accelerate(Dv):                                   # :298-303, :245-256
-        buoy = -p["g"] * ey[None, :] * (f["rho_p"] / f["rho"])[:, None]
-        sn = np.sin(np.pi / 2 * (1 - (p["z_t"] - p["z_b"]) / p["z_b"]))
-        damp = np.where((f["x"][:, 1] >= p["z_t"] - p["z_b"])[:, None], -p["gamma_r"] * sn ** 2 * ey[None, :], 0.0)
-        f["v"] = np.where(fluid[:, None], f["v"] + 0.5 * p["dt"] * (Dv + buoy + damp), f["v"])
 
-    accelerate(f["Dv"])
+def numpy_step_kick_drift(f, p):
+    """accelerate! + move!, wcsph_perturbed_witch.jl:311-312"""
+    _accelerate(f, p, f["Dv"])
+    fluid = f["type"] == p["fluid"]
     f["x"] = np.where(fluid[:, None], f["x"] + p["dt"] * f["v"], f["x"])            # move! :292-296
-    d, r, mask = neighbours(f["x"], case.h)
+
+
+def neighbour_pairs(x, h):
+    """ordered pairs (i, j), i != j, with |x_i - x_j| <= h (core.jl:104-105), found with a k-d tree
+    (scipy) instead of the cell list; the distance test itself is redone in plain FP64"""
+    from scipy.spatial import cKDTree
+    tree = cKDTree(x)
+    und = tree.query_pairs(h * (1 + 1e-9), output_type="ndarray")
+    i = np.concatenate([und[:, 0], und[:, 1]])
+    j = np.concatenate([und[:, 1], und[:, 0]])
+    d = x[i] - x[j]
+    r = np.sqrt((d * d).sum(-1))
+    keep = r <= h
+    return i[keep], j[keep], d[keep], r[keep]
+
+
+def numpy_step_sums(f, p, h_cut, dim3):
+    """:316-331 — density, smoothing length, pressure, pair force, second accelerate!"""
+    W, rDW = (wendland3, rDwendland3) if dim3 else (wendland2, rDwendland2)
+    n = len(f["m"])
+    i, j, d, r = neighbour_pairs(f["x"], h_cut)
     # compute_density! :226-228 (no self term), finalize_density! :230-233, update_smoothing! :235-238
-    f["rho"] = (mask * f["m"][None, :] * W(f["h"][:, None], r)).sum(1)
+    f["rho"] = np.bincount(i, weights=f["m"][j] * W(f["h"][i], r), minlength=n)
     rho_bg = p["rho0"] * np.exp(-f["x"][:, 1] * p["g"] / (p["R_mass"] * p["T_bg"]))   # :177-179
     f["rho_p"] = f["rho"] - rho_bg
     rfl = np.maximum(f["rho"], p["rho_floor"])
@@ -64,22 +81,28 @@ def numpy_wcsph_step(case):
     P_p = p["c"] ** 2 * f["rho_p"]
     P = p["R_mass"] * p["T_bg"] * rho_bg + P_p
     # balance_of_momentum! :261-286
-    v_pq = f["v"][:, None, :] - f["v"][None, :, :]
-    dot = (d * v_pq).sum(-1)
-    h_ij = 0.5 * (f["h"][:, None] + f["h"][None, :])
+    dot = (d * (f["v"][i] - f["v"][j])).sum(-1)
+    h_ij = 0.5 * (f["h"][i] + f["h"][j])
     ker = rDW(h_ij, r)
     pr = P_p / rfl ** 2
-    fc = -f["m"][None, :] * (pr[:, None] + pr[None, :]) * ker
+    fc = -f["m"][j] * (pr[i] + pr[j]) * ker
     cs = np.sqrt(p["gamma"] * P / rfl)
-    c_ij = 0.5 * (cs[:, None] + cs[None, :])
-    rho_ij = 0.5 * (rfl[:, None] + rfl[None, :])
     mu = h_ij * dot / (r * r + p["eps"] * h_ij * h_ij)
-    pi_ij = (-p["alpha"] * c_ij * mu + p["beta"] * mu * mu) / rho_ij
-    fv = np.where(dot < 0.0, -f["m"][None, :] * pi_ij * ker, 0.0)
-    Dv = ((mask * (fc + fv))[:, :, None] * d).sum(1)
-    accelerate(Dv)
+    pi_ij = (-p["alpha"] * 0.5 * (cs[i] + cs[j]) * mu + p["beta"] * mu * mu) / (0.5 * (rfl[i] + rfl[j]))
+    fv = np.where(dot < 0.0, -f["m"][j] * pi_ij * ker, 0.0)
+    Dv = np.stack([np.bincount(i, weights=(fc + fv) * d[:, k], minlength=n) for k in range(3)], axis=1)
+    _accelerate(f, p, Dv)
+    f["Dv"] = np.zeros_like(f["v"])                       # accelerate! zeroes Dv (:302)
     f["P"], f["P_p"], f["Dv_last"] = P, P_p, Dv
-    return f, int(mask.sum())
+    return len(i)
+
+
+def numpy_wcsph_step(case):
+    """verlet_step!, src/current/wcsph_perturbed_witch.jl:309-332, on plain arrays"""
+    f = {k: v.copy() for k, v in case.fields.items()}
+    numpy_step_kick_drift(f, case.params)
+    npairs = numpy_step_sums(f, case.params, case.h, case.dim == 3)
+    return f, npairs
 
 
 @pytest.mark.parametrize("make", [
@@ -132,3 +155,62 @@ def test_hopkins_pressure_and_total_force_against_numpy():
     fv = np.where(dot < 0.0, -f["m"][None, :] * pi_ij * rDwendland2(h_ij, r), 0.0)
     Dv = ((mask * (fc + fv))[:, :, None] * d).sum(1)
     assert rel_err(o.field("Dv"), Dv) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# Whole runs: 50 x verlet_step! with create_cell_list!'s removal, restated independently
+# ---------------------------------------------------------------------------------------------
+def numpy_remove_outside(case, f):
+    """create_cell_list!'s removal, src/core.jl:60-81: particles outside the bounding box (closed
+    intervals, geometry.jl:24-30) are overwritten, in DESCENDING index order, by the particles
+    counted from the end, then the vector is shortened."""
+    x = f["x"]
+    lo, hi = np.asarray(case.box_min), np.asarray(case.box_max)
+    inside = np.all((lo[None, :] <= x) & (x <= hi[None, :]), axis=1)
+    removal = np.nonzero(~inside)[0][::-1]
+    n = len(x)
+    for i, idx in enumerate(removal, start=1):
+        for a in f.values():
+            a[idx] = a[n - i]
+    keep = n - len(removal)
+    for k in list(f):
+        f[k] = f[k][:keep].copy()
+    return len(removal)
+
+
+def numpy_wcsph_run(case, nsteps):
+    """nsteps of verlet_step! (wcsph_perturbed_witch.jl:309-332) with brute-force neighbours; the
+    removal is create_cell_list!'s (:313), between the drift and the sums"""
+    f = {k: v.copy() for k, v in case.fields.items()}
+    removed = 0
+    for _ in range(nsteps):
+        numpy_step_kick_drift(f, case.params)
+        removed += numpy_remove_outside(case, f)
+        for k in ("P", "P_p", "Dv_last"):
+            f.pop(k, None)
+        numpy_step_sums(f, case.params, case.h, case.dim == 3)
+    return f, removed
+
+
+@pytest.mark.parametrize("make,nsteps", [
+    (lambda: cases.mountain_wave_2d(n_y=12.0, dom_length=30e3, h_m=3000.0, a=6e3, U=25.0), 50),
+    (lambda: cases.bell_hill_3d(10, 8, 6, h_m=3000.0, a=4e3, U=25.0), 50),
+])
+def test_fifty_steps_with_removal_against_numpy_restatement(make, nsteps):
+    """A second, independent whole-run restatement (brute-force neighbours, no cell list, numpy
+    formulas) against the C oracle over 50 steps, with particles leaving the box on the way — the
+    oracle's cell list, swap-from-end removal (core.jl:72-81) and step sequence are what would
+    break this by many orders of magnitude.  Summation order differs: agreement to rounding."""
+    case = make()
+    rng = np.random.default_rng(3)
+    fl = np.nonzero(case.fields["type"] == 0.0)[0]
+    # a handful of fluid particles shot through the top fence: they leave within the run
+    top = fl[np.argsort(case.fields["x"][fl, 1])[-6:]]
+    case.fields["v"][top, 1] = 10000.0 + 800.0 * rng.uniform(size=len(top))
+    o = load_oracle(case)
+    o.create_cell_list()
+    o.step("wcsph", nsteps)
+    ref, removed = numpy_wcsph_run(case, nsteps)
+    assert removed > 0 and len(o) == case.n - removed == len(ref["m"])
+    for name in ("x", "v", "rho", "h", "m", "type"):
+        assert rel_err(o.field(name), ref[name]) < 1e-9, name
