@@ -235,8 +235,25 @@ int sphmw_kernel_eval(const char *name, const double *h, const double *r, double
  * written as VTK PolyData (.vtp, appended raw, one Verts cell per particle) plus
  * a .pvd collection whose timestep values are the frame counter (IO.jl:73). */
 int sphmw_pvd_open(sphmw_ctx *ctx, const char *dir);
+/* save_frame captures the frame on the device (reference index order, components interleaved as
+ * the .vtp stores them), copies it to pinned host memory on a side stream and writes the file on a
+ * worker thread: the call returns once the capture is queued and the time loop goes on.  pvd_close
+ * (and sphmw_destroy) wait for the files. */
 int sphmw_pvd_save_frame(sphmw_ctx *ctx, const char *const *fields, int32_t nfields);
 int sphmw_pvd_close(sphmw_ctx *ctx);
+
+/* The same capture for callers that want the arrays instead of a file.  sphmw_frame_capture: snapshot
+ * of the named fields now, device -> pinned host copy queued on a side stream, *slot = 0 or 1 (two
+ * captures can be in flight).  sphmw_frame_wait: waits for that copy; host[f] points at field f
+ * (n x ncomp doubles, components interleaved; reference index order, physical order on a slab
+ * context) inside the library's pinned buffer, valid until the second capture from now.
+ * sphmw_upload_async stages a field on the copy stream (host memory borrowed until the commit);
+ * sphmw_upload_commit makes the staged batch the particle state (count n, indices 0..n-1 in upload
+ * order) on the main stream without waiting on the host. */
+int sphmw_frame_capture(sphmw_ctx *ctx, const char *const *fields, int32_t nfields, int32_t *slot);
+int sphmw_frame_wait(sphmw_ctx *ctx, int32_t slot, const double **host, int32_t nfields, int64_t *n);
+int sphmw_upload_async(sphmw_ctx *ctx, const char *field, const double *buf, int64_t n, int32_t ncomp);
+int sphmw_upload_commit(sphmw_ctx *ctx);
 
 /* ≙ the file half of import_particles!(sys, path, ctor) — src/IO.jl:83-122 (ReadVTK.jl): a
  * host-only reader of the PolyData files WriteVTK (and sphmw_pvd_save_frame) writes.  Array 0
@@ -255,6 +272,8 @@ int sphmw_vtp_write(const char *path, int64_t n, const double *points3n, int32_t
  * context's stream).  names: newline-separated, ms/calls: one entry per name. */
 int sphmw_timing_enable(sphmw_ctx *ctx, int32_t enable);
 int sphmw_timing_reset(sphmw_ctx *ctx);
+/* time only the kernels whose name starts with prefix (NULL or "": all) */
+int sphmw_timing_filter(sphmw_ctx *ctx, const char *prefix);
 int64_t sphmw_timing_report(sphmw_ctx *ctx, char *names, int64_t cap, double *ms,
                             int64_t *calls, int32_t max_entries);
 /* number of kernels this library launched on ctx since creation */

@@ -86,6 +86,11 @@ _SIGS = {
     "sphmw_slab_column_sets": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "sphmw_pair_list_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "sphmw_tile_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "sphmw_timing_filter": (C.c_int, [_P, C.c_char_p]),
+    "sphmw_frame_capture": (C.c_int, [_P, C.POINTER(C.c_char_p), C.c_int32, C.POINTER(C.c_int32)]),
+    "sphmw_frame_wait": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_int64)]),
+    "sphmw_upload_async": (C.c_int, [_P, C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
+    "sphmw_upload_commit": (C.c_int, [_P]),
     "sphmw_comm_unique_id": (C.c_int, [C.c_void_p]),
     "sphmw_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_char_p, C.c_int64]),
     "sphmw_comm_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),

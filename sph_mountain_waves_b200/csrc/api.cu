@@ -142,6 +142,7 @@ static void timing_resolve(sphmw_ctx *c) {
 KernelTimer::KernelTimer(sphmw_ctx *ctx, const char *name) : c(ctx), pending_index(-1) {
     c->launches += 1;
     if (!c->timing) return;
+    if (!c->timing_prefix.empty() && strncmp(name, c->timing_prefix.c_str(), c->timing_prefix.size())) return;
     if (c->timing_pending.size() >= 8192) timing_resolve(c);
     TimingEntry t;
     t.name_id = timing_name_id(c, name);
@@ -158,6 +159,14 @@ extern "C" int sphmw_timing_enable(sphmw_ctx *c, int32_t enable) {
     if (!c) return SPHMW_E_INVALID;
     if (!enable) timing_resolve(c);
     c->timing = enable != 0;
+    return SPHMW_OK;
+}
+// only kernels whose name starts with `prefix` are timed (NULL or "": all) — two event records per
+// launch are not free when a step is a few milliseconds of ~30 launches
+extern "C" int sphmw_timing_filter(sphmw_ctx *c, const char *prefix) {
+    if (!c) return SPHMW_E_INVALID;
+    timing_resolve(c);
+    c->timing_prefix = prefix ? prefix : "";
     return SPHMW_OK;
 }
 extern "C" int sphmw_timing_reset(sphmw_ctx *c) {
@@ -286,6 +295,7 @@ extern "C" int sphmw_destroy(sphmw_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     sphmw_comm_free(c);
+    sphmw_frame_async_free(c);
     if (c->h_slab_check) cudaFreeHost(c->h_slab_check);
     for (auto e : c->slab_check_event)
         if (e) cudaEventDestroy(e);

@@ -206,39 +206,17 @@ extern "C" int sphmw_pvd_open(sphmw_ctx *c, const char *dir) {
     return SPHMW_OK;
 }
 
-// ≙ save_frame!(data, sys, vars...) — IO.jl:53-75 (+ capture_frame :37-46)
+// ≙ save_frame!(data, sys, vars...) — IO.jl:53-75 (+ capture_frame :37-46).  The frame is
+// captured on the device at this point of the stream (frame_async.cu: index order, components
+// interleaved), copied to pinned host memory on a side stream and written by a worker thread; the
+// call returns as soon as the capture is queued, so the time loop goes on while the file is made.
 extern "C" int sphmw_pvd_save_frame(sphmw_ctx *c, const char *const *fields, int32_t nfields) {
     if (!c || (nfields > 0 && !fields)) { sphmw_set_error("null argument"); return SPHMW_E_INVALID; }
     if (!c->pvd_open) { sphmw_set_error("save_frame: no pvd file is open"); return SPHMW_E_STATE; }
-    const int64_t n = c->n;
-    std::vector<std::vector<double>> soa(nfields + 1), aos(nfields + 1);
-    std::vector<int> ncomps(nfields + 1);
-    std::vector<const char *> names(nfields + 1);
-    names[0] = "x";
-    for (int f = 0; f < nfields; ++f) names[f + 1] = fields[f];
-    for (int f = 0; f <= nfields; ++f) {
-        const FieldDesc *d = sphmw_find_field(names[f]);
-        if (!d) {
-            sphmw_set_error("Variable %s does not exist!", names[f]);  // structs.jl:128-133
-            return SPHMW_E_UNKNOWN_FIELD;
-        }
-        ncomps[f] = d->ncomp;
-        soa[f].resize((size_t)d->ncomp * n);
-        if (n) TRY(sphmw_download(c, names[f], soa[f].data(), n, d->ncomp));
-        if (d->ncomp == 1) {
-            aos[f].swap(soa[f]);
-        } else {
-            aos[f].resize((size_t)d->ncomp * n);
-            for (int k = 0; k < d->ncomp; ++k)
-                for (int64_t i = 0; i < n; ++i) aos[f][(size_t)i * d->ncomp + k] = soa[f][(size_t)k * n + i];
-        }
-    }
-    std::vector<const double *> ptrs(nfields);
-    for (int f = 0; f < nfields; ++f) ptrs[f] = aos[f + 1].data();
+    if (cudaSetDevice(c->device) != cudaSuccess) { sphmw_set_error("cudaSetDevice failed"); return SPHMW_E_CUDA; }
     std::string fname = "frame" + std::to_string(c->pvd_frame) + ".vtp";
     std::string path = c->pvd_dir + "/" + fname;
-    TRY(sphmw_write_vtp(path.c_str(), n, aos[0].data(), nfields, names.data() + 1, ncomps.data() + 1,
-                        ptrs.data()));
+    TRY(sphmw_pvd_save_frame_async(c, fields, nfields, path));
     c->pvd_entries.push_back(fname);
     c->pvd_frame += 1;
     return SPHMW_OK;
@@ -248,6 +226,7 @@ extern "C" int sphmw_pvd_save_frame(sphmw_ctx *c, const char *const *fields, int
 extern "C" int sphmw_pvd_close(sphmw_ctx *c) {
     if (!c) return SPHMW_E_INVALID;
     if (!c->pvd_open) { sphmw_set_error("save_pvd_file: no pvd file is open"); return SPHMW_E_STATE; }
+    TRY(sphmw_frame_async_drain(c));  // every frame is on disk before the collection names it
     std::string path = c->pvd_dir + "/result.pvd";
     TRY(sphmw_write_pvd(path.c_str(), c->pvd_entries));
     c->pvd_open = false;

@@ -252,6 +252,7 @@ struct sphmw_ctx {
     int64_t slab_check_want[4][2] = {};           // the host's figures for the same builds
     uint64_t slab_checks = 0;
     struct SlabComm *comm = nullptr;              // NCCL halo transport (slab_comm.cu)
+    struct FrameAsync *frame_async = nullptr;     // asynchronous frame output / upload prefetch (frame_async.cu)
     uint32_t *halo_counters = nullptr;            // device: [0] left records [1] right records
                                                   // [2] left migrants [3] right migrants [4] lost
     uint32_t *h_halo_counters = nullptr;          // pinned mirror
@@ -300,6 +301,7 @@ struct sphmw_ctx {
 
     // timing
     bool timing = false;
+    std::string timing_prefix;  // time only kernels with this name prefix (empty: all)
     std::vector<std::string> timing_names;
     std::vector<double> timing_ms;
     std::vector<int64_t> timing_calls;
@@ -373,6 +375,10 @@ int sphmw_comm_step(sphmw_ctx *c, const char *scheme, int nsteps);
 int sphmw_comm_create_cell_list(sphmw_ctx *c, int64_t *n_alive);
 void sphmw_comm_free(sphmw_ctx *c);
 int sphmw_step_wcsph_phase(sphmw_ctx *c, int phase);  // pair_ops.cu
+// implemented in frame_async.cu
+int sphmw_pvd_save_frame_async(sphmw_ctx *c, const char *const *fields, int nfields, const std::string &path);
+int sphmw_frame_async_drain(sphmw_ctx *c);
+void sphmw_frame_async_free(sphmw_ctx *c);
 // implemented in frame_io.cpp
 int sphmw_write_vtp(const char *path, int64_t n, const double *points3n, int nfields,
                     const char *const *names, const int *ncomps, const double *const *data);

@@ -542,32 +542,46 @@ class SlabRun:
         n0 = self._n0
         h2d = sum(self._pinned[f].numel() * 8 for f in carried)
         d2h = 0
+        names = (C.c_char_p * len(out_fields))(*[canonical(f).encode() for f in out_fields])
+        comps = sum(FIELD_NCOMP[canonical(f)] for f in out_fields)
+
+        def prefetch():
+            # the next cycle's inputs travel on the library's copy stream while this cycle steps
+            for f in carried:
+                check(lib.sphmw_upload_async(sys.ctx, canonical(f).encode(), C.c_void_p(self._pinned[f].data_ptr()),
+                                             n0, FIELD_NCOMP[canonical(f)]))
+
+        def wait(slot):
+            ptrs = (C.c_void_p * len(out_fields))()
+            n = C.c_int64()
+            check(lib.sphmw_frame_wait(sys.ctx, slot, ptrs, len(out_fields), C.byref(n)))
+            return n.value
+
         barrier()
         t0 = time.perf_counter()
-        for _ in range(cycles):
-            if slab:
-                check(lib.sphmw_resize(sys.ctx, 0))
-                check(lib.sphmw_resize(sys.ctx, n0))
-            for f in carried:
-                sys.upload_ptr(f, self._pinned[f].data_ptr(), n0)
+        prefetch()
+        pending = None
+        for k in range(cycles):
+            check(lib.sphmw_upload_commit(sys.ctx))       # staged fields -> particle state (no host wait)
             if slab:
                 check(lib.sphmw_set_index(sys.ctx, _capi.ptr(self._gidx), n0))
+            if k + 1 < cycles:
+                prefetch()
             self.create_cell_list()
             self.step(every)
-            n = sys.n_device
-            for f in out_fields:
-                nc = FIELD_NCOMP[canonical(f)]
-                p = self._pinned["out:" + f].data_ptr()
-                if slab:
-                    check(lib.sphmw_download_raw(sys.ctx, canonical(f).encode(), C.c_void_p(p), n, nc))
-                else:
-                    sys.download_ptr(f, p, n)
-                d2h += nc * n * 8
+            slot = C.c_int32()
+            check(lib.sphmw_frame_capture(sys.ctx, names, len(out_fields), C.byref(slot)))   # D2H beside the next cycle
+            if pending is not None:
+                d2h += comps * wait(pending) * 8
+            pending = slot.value
+        d2h += comps * wait(pending) * 8
         barrier()
         dt = time.perf_counter() - t0
         return {"seconds": dt, "steps": cycles * every, "h2d_bytes": h2d * cycles, "d2h_bytes": d2h,
-                "what": f"{cycles} x (upload {len(carried)} carried fields from pinned host, create_cell_list, "
-                        f"{every} steps = one frame interval, download x + {len(self.export)} export fields)"}
+                "what": f"{cycles} x (upload {len(carried)} carried fields from pinned host [sphmw_upload_async/commit: "
+                        f"the next cycle's copy runs beside this cycle's steps], create_cell_list, {every} steps = one "
+                        f"frame interval, x + {len(self.export)} export fields to pinned host [sphmw_frame_capture/wait: "
+                        f"device snapshot, copy beside the next cycle])"}
 
 
 class LocalCluster:

@@ -344,7 +344,9 @@ class ParticleSystem:
         check(_capi.lib().sphmw_pair_count(self.ctx, C.byref(n)))
         return n.value
 
-    def timing(self, enable: bool = True):
+    def timing(self, enable: bool = True, prefix: str = ""):
+        """per-kernel CUDA-event timers; `prefix` limits them to the kernels named so"""
+        check(_capi.lib().sphmw_timing_filter(self.ctx, prefix.encode()))
         check(_capi.lib().sphmw_timing_enable(self.ctx, 1 if enable else 0))
 
     def timing_reset(self):

@@ -53,7 +53,8 @@ typedef struct {
     double *x, *v, *m, *h, *rho, *rho_p, *type; /* x, v: component-major (3 x n) */
 } Cloud;
 
-/* cubic lattice nx x ny x nz, hydrostatic density, a sheared wind so that the pair force works */
+/* cubic lattice nx x ny x nz, density falling with height, a sheared wind so that the pair force works;
+ * only + - * / so that a numpy restatement of the inputs (tests/test_gpu_capi_c.py) has the same bits */
 static Cloud make_cloud(int nx, int ny, int nz) {
     Cloud c;
     c.n = (int64_t)nx * ny * nz;
@@ -71,8 +72,8 @@ static Cloud make_cloud(int nx, int ny, int nz) {
             for (int k = 0; k < nz; ++k, ++p) {
                 const double x = (i + 0.5) * dr, y = (j + 0.5) * dr, z = (k + 0.5) * dr;
                 c.x[p] = x, c.x[c.n + p] = y, c.x[2 * c.n + p] = z;
-                c.v[p] = 20.0 + 5.0 * sin(0.7 * j + 0.3 * k), c.v[c.n + p] = 0.5 * cos(0.9 * i), c.v[2 * c.n + p] = 0.0;
-                c.rho[p] = RHO0 * exp(-y * G / (RM * TBG));
+                c.v[p] = 20.0 + 5.0 * ((7 * j + 3 * k) % 11) / 11.0, c.v[c.n + p] = 0.5 * ((9 * i) % 7) / 7.0 - 0.25, c.v[2 * c.n + p] = 0.0;
+                c.rho[p] = RHO0 / (1.0 + y * G / (RM * TBG));
                 c.m[p] = c.rho[p] * dr * dr * dr;
                 c.h[p] = h0_();
             }

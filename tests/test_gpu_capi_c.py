@@ -24,8 +24,8 @@ def c_scenario():
     i, j, kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
     i, j, kk = i.ravel(), j.ravel(), kk.ravel()
     x = np.stack([(i + 0.5) * dr, (j + 0.5) * dr, (kk + 0.5) * dr], axis=1)
-    v = np.stack([20.0 + 5.0 * np.sin(0.7 * j + 0.3 * kk), 0.5 * np.cos(0.9 * i), np.zeros(len(i))], axis=1)
-    rho = k.rho0 * np.exp(-x[:, 1] * k.g / (k.R_mass * k.T_bg))
+    v = np.stack([20.0 + 5.0 * ((7 * j + 3 * kk) % 11) / 11.0, 0.5 * ((9 * i) % 7) / 7.0 - 0.25, np.zeros(len(i))], axis=1)
+    rho = k.rho0 / (1.0 + x[:, 1] * k.g / (k.R_mass * k.T_bg))
     fields = dict(x=x, v=v, m=rho * dr ** 3, h=np.full(len(i), k.h0), rho=rho, rho_p=np.zeros(len(i)),
                   type=np.zeros(len(i)))
     return cases.Case("c_scenario", "wcsph", 3, (0.0, 0.0, 0.0), (nx * dr, ny * dr, nz * dr), k.h0, k.params(),

@@ -275,3 +275,50 @@ def test_dambreak_validation_at_reference_resolution(gpu):
     assert deviation("H_Violeau", ts, H, t_max=2.6)[0] < 0.04   # measured 3.0 %
     assert deviation("H_Violeau", ts, H)[0] < 0.12          # the last digitised point (t* = 3): 9 %
     assert len(s) == case.n
+
+
+def test_async_frame_capture_and_upload_prefetch(gpu):
+    """sphmw_frame_capture/_wait and sphmw_upload_async/_commit (csrc/frame_async.cu): the captured
+    arrays are the downloaded fields (index order, components interleaved) at the moment of the
+    capture even though stepping continues, and a committed prefetch leaves the state an ordinary
+    upload leaves — save_frame! (IO.jl:53-75) off the critical path changes no value"""
+    import ctypes as C
+
+    from sph_mountain_waves_b200 import _capi
+    from sph_mountain_waves_b200.system import FIELD_NCOMP, canonical
+    lib = _capi.lib()
+    case = cases.mountain_wave_2d(n_y=20.0, dom_length=60e3, h_m=3000.0, a=10e3, U=20.0)
+    s = load_gpu(case)
+    s.create_cell_list()
+    s.step(3)
+    fields = ["x", "v", "rho", "T", "type"]
+    want = {f: s.field(f) for f in fields}
+    names = (C.c_char_p * len(fields))(*[canonical(f).encode() for f in fields])
+    slot = C.c_int32()
+    assert lib.sphmw_frame_capture(s.ctx, names, len(fields), C.byref(slot)) == 0
+    s.step(2)                                   # the state moves on while the copy is in flight
+    ptrs = (C.c_void_p * len(fields))()
+    n = C.c_int64()
+    assert lib.sphmw_frame_wait(s.ctx, slot.value, ptrs, len(fields), C.byref(n)) == 0
+    assert n.value == case.n
+    for k, f in enumerate(fields):
+        nc = FIELD_NCOMP[canonical(f)]
+        got = np.ctypeslib.as_array(C.cast(ptrs[k], C.POINTER(C.c_double)), shape=(case.n * nc,)).copy()
+        got = got.reshape(case.n, nc) if nc == 3 else got
+        assert np.array_equal(got, want[f]), f
+    assert not np.array_equal(s.field("x"), want["x"])
+    # prefetch: a second system fed through upload_async/commit equals one fed through upload
+    a, b = load_gpu(case), load_gpu(case)
+    a.create_cell_list()
+    keep = {}
+    for f in ("x", "v", "m", "h", "rho", "rho_p", "type"):
+        arr = case.fields[f]
+        nc = FIELD_NCOMP[canonical(f)]
+        keep[f] = np.ascontiguousarray(arr.T if nc == 3 else arr, dtype=np.float64)
+        assert lib.sphmw_upload_async(b.ctx, canonical(f).encode(), _capi.ptr(keep[f]), case.n, nc) == 0
+    assert lib.sphmw_upload_commit(b.ctx) == 0
+    b.create_cell_list()
+    a.step(4)
+    b.step(4)
+    for f in ("x", "v", "rho", "h"):
+        assert np.array_equal(a.field(f), b.field(f)), f
