@@ -768,6 +768,75 @@ struct B_pack_momentum : PairOpBase {
     }
 };
 
+// ---- fused passes of the Hopkins drivers (sphmw_step, schemes "hopkins", "hopkins_full") -------
+// hopkins_perturbed_witch.jl:324-349 runs three binary operators on one cell list; fused:
+//   pass 1 (records the pair list)  reset_density! + compute_density! + finalize_density! +
+//                                   update_smoothing!                                  (:331-334)
+//   pass 2 (replays it)             reset_pressure! + compute_pressure! + finalize_pressure!
+//                                                                                      (:337-339)
+//   pass 3 (replays it)             balance_of_momentum! + accelerate!                 (:346-347)
+// find_temperature! / find_pot_temp! (:342-343) are diagnostics, rebuilt on demand.  Each fused
+// operator performs its unfused parts' arithmetic in the same order: same bits.
+struct B_hopkins_density_fused : PairOpBase {
+    double rho, hp;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &, int64_t p) {
+        rho = 0.0;  // reset_density!
+        hp = PF(S_H);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &, int64_t, int64_t q, double, double, double, double r) {
+        rho += QF(S_M) * sph_W<DIM>(hp, r);
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &c, int64_t p) {
+        double rbg = background_density(c, PF(S_X1));  // finalize_density!
+        PF(S_RHO) = rho;
+        PF(S_RHO_BG) = rbg;
+        PF(S_RHO_P) = rho - rbg;
+        double rfl = jl_max(rho, c.rho_floor);         // update_smoothing!
+        // (in place: the density closure reads only the particle's OWN h, never a neighbour's)
+        double m = PF(S_M);
+        PF(S_H) = DIM == 2 ? c.eta * sqrt(m / rfl) : c.eta * cbrt(m / rfl);
+    }
+};
+struct B_hopkins_pressure_fused : PairOpBase {
+    double P, hp;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &, int64_t p) {
+        P = 0.0;  // reset_pressure!
+        hp = PF(S_H);
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double, double, double, double r) {
+        double ker = sph_W<DIM>(0.5 * (hp + QF(S_H)), r);
+        P += QF(S_M) * pow(QF(S_A), 1 / c.gamma) * ker;
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &c, int64_t p) {
+        double Pf = pow(P, c.gamma);  // finalize_pressure!
+        double pbg = background_pressure(c, PF(S_X1));
+        PF(S_P) = Pf;
+        PF(S_P_BG) = pbg;
+        PF(S_P_P) = Pf - pbg;
+    }
+};
+// a force operator + the trailing accelerate! of the step: Dv starts at 0 and is never stored, the
+// new velocity goes to `out` (neighbours still read the old one)
+template <class Force>
+struct B_force_kick_fused : Force {
+    template <int DIM>
+    static __device__ void skip(const Fields &f, const Fields &out, int64_t p) {
+        out.s[S_V0][p] = f.s[S_V0][p];
+        out.s[S_V1][p] = f.s[S_V1][p];
+        if (DIM == 3) out.s[S_V2][p] = f.s[S_V2][p];
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &out, const Params &c, int64_t p) {
+        wcsph_force_finish<DIM>(f, out, c, p, this->s.v0, this->s.v1, this->s.v2, this->s.dv0, this->s.dv1, this->s.dv2);
+    }
+};
+
 #undef PF
 #undef QF
 

@@ -822,6 +822,31 @@ static int step_wcsph_fused_post(sphmw_ctx *c) {
     return SPHMW_OK;
 }
 
+// hopkins_perturbed_witch.jl:324-349 / full_hopkins_perturbed_witch.jl:350-374 with the unary
+// sweeps folded into the three pair passes (ops_menu.cuh): the density pass records the pair
+// list, the pressure and force passes replay it.  Whole-domain contexts only: the pressure sum
+// needs the NEW smoothing length of a particle's neighbours, i.e. complete density sums two cell
+// columns beyond the owned ones — one ghost column more than a slab context keeps.
+template <class Force>
+static int step_hopkins_fused(sphmw_ctx *c) {
+    TRY(step_wcsph_fused_pre(c));           // accelerate! + move! (:325-326)
+    TRY(sphmw_build_cell_list(c, nullptr));  // :329
+    TRY(need_slots(c, SL(S_X0, S_V0, S_M, S_H, S_A, S_TYPE), SL()));
+    TRY(need_slots(c, SL(S_DV0), SL()));     // all zero after accelerate!; the force operator starts from it
+    for (int s : {S_RHO_BG, S_RHO_P, S_RHO, S_P_BG, S_P_P, S_P}) {
+        TRY(sphmw_ensure_slot(c, s));
+        c->stale[s] = false;
+    }
+    c->want_list = true;
+    TRY((run_binary<B_hopkins_density_fused>(c, "hopkins.density_fused", 0, c->cur)));
+    TRY((run_binary<B_hopkins_pressure_fused>(c, "hopkins.pressure_fused", 0, c->cur)));
+    TRY((run_binary<B_force_kick_fused<Force>>(c, "hopkins.momentum_fused", 0, c->alt)));
+    std::swap(c->cur.s[S_V0], c->alt.s[S_V0]);
+    std::swap(c->cur.s[S_V1], c->alt.s[S_V1]);
+    if (c->grid.dim == 3) std::swap(c->cur.s[S_V2], c->alt.s[S_V2]);
+    return SPHMW_OK;
+}
+
 static int step_wcsph_fused(sphmw_ctx *c) {
     TRY(step_wcsph_fused_pre(c));
     return step_wcsph_fused_post(c);
@@ -999,7 +1024,11 @@ int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps) {
                               "create_cell_list", "wcsph.compute_pressure",
                               "wcsph.find_temperature", "wcsph.find_pot_temp",
                               "wcsph.balance_of_momentum", "wcsph.accelerate"}));
-        } else if (!strcmp(scheme, "hopkins")) {
+        } else if (!strcmp(scheme, "hopkins") && c->slab_lo < 0 && !getenv("SPHMW_HOPKINS_UNFUSED")) {
+            TRY(step_hopkins_fused<B_wcsph_momentum>(c));
+        } else if (!strcmp(scheme, "hopkins_full") && c->slab_lo < 0 && !getenv("SPHMW_HOPKINS_UNFUSED")) {
+            TRY(step_hopkins_fused<B_hf_momentum>(c));
+        } else if (!strcmp(scheme, "hopkins") || !strcmp(scheme, "hopkins_unfused")) {
             // hopkins_perturbed_witch.jl:325-349
             TRY(apply_seq(c, {"wcsph.accelerate", "wcsph.move", "create_cell_list",
                               "wcsph.reset_density", "wcsph.compute_density",
@@ -1008,7 +1037,7 @@ int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps) {
                               "hopkins.finalize_pressure", "wcsph.find_temperature",
                               "wcsph.find_pot_temp", "wcsph.balance_of_momentum",
                               "wcsph.accelerate"}));
-        } else if (!strcmp(scheme, "hopkins_full")) {
+        } else if (!strcmp(scheme, "hopkins_full") || !strcmp(scheme, "hopkins_full_unfused")) {
             // full_hopkins_perturbed_witch.jl:350-374
             TRY(apply_seq(c, {"wcsph.accelerate", "wcsph.move", "create_cell_list",
                               "wcsph.reset_density", "wcsph.compute_density",

@@ -557,24 +557,32 @@ class SlabRun:
             check(lib.sphmw_frame_wait(sys.ctx, slot, ptrs, len(out_fields), C.byref(n)))
             return n.value
 
+        def run_cycles(count):
+            moved = 0
+            prefetch()
+            pending = None
+            for k in range(count):
+                check(lib.sphmw_upload_commit(sys.ctx))       # staged fields -> particle state (no host wait)
+                if slab:
+                    check(lib.sphmw_set_index(sys.ctx, _capi.ptr(self._gidx), n0))
+                if k + 1 < count:
+                    prefetch()
+                self.create_cell_list()
+                self.step(every)
+                slot = C.c_int32()
+                check(lib.sphmw_frame_capture(sys.ctx, names, len(out_fields), C.byref(slot)))   # D2H beside the next cycle
+                if pending is not None:
+                    moved += comps * wait(pending) * 8
+                pending = slot.value
+            moved += comps * wait(pending) * 8
+            return moved
+
+        if not getattr(self, "_e2e_warm", False):
+            run_cycles(2)          # untimed: the library allocates its pinned snapshot and staging buffers
+            self._e2e_warm = True
         barrier()
         t0 = time.perf_counter()
-        prefetch()
-        pending = None
-        for k in range(cycles):
-            check(lib.sphmw_upload_commit(sys.ctx))       # staged fields -> particle state (no host wait)
-            if slab:
-                check(lib.sphmw_set_index(sys.ctx, _capi.ptr(self._gidx), n0))
-            if k + 1 < cycles:
-                prefetch()
-            self.create_cell_list()
-            self.step(every)
-            slot = C.c_int32()
-            check(lib.sphmw_frame_capture(sys.ctx, names, len(out_fields), C.byref(slot)))   # D2H beside the next cycle
-            if pending is not None:
-                d2h += comps * wait(pending) * 8
-            pending = slot.value
-        d2h += comps * wait(pending) * 8
+        d2h = run_cycles(cycles)
         barrier()
         dt = time.perf_counter() - t0
         return {"seconds": dt, "steps": cycles * every, "h2d_bytes": h2d * cycles, "d2h_bytes": d2h,

@@ -26,7 +26,7 @@ def c_scenario():
     x = np.stack([(i + 0.5) * dr, (j + 0.5) * dr, (kk + 0.5) * dr], axis=1)
     v = np.stack([20.0 + 5.0 * ((7 * j + 3 * kk) % 11) / 11.0, 0.5 * ((9 * i) % 7) / 7.0 - 0.25, np.zeros(len(i))], axis=1)
     rho = k.rho0 / (1.0 + x[:, 1] * k.g / (k.R_mass * k.T_bg))
-    fields = dict(x=x, v=v, m=rho * dr ** 3, h=np.full(len(i), k.h0), rho=rho, rho_p=np.zeros(len(i)),
+    fields = dict(x=x, v=v, m=rho * dr * dr * dr, h=np.full(len(i), k.h0), rho=rho, rho_p=np.zeros(len(i)),
                   type=np.zeros(len(i)))
     return cases.Case("c_scenario", "wcsph", 3, (0.0, 0.0, 0.0), (nx * dr, ny * dr, nz * dr), k.h0, k.params(),
                       fields, {})

@@ -322,3 +322,21 @@ def test_async_frame_capture_and_upload_prefetch(gpu):
     b.step(4)
     for f in ("x", "v", "rho", "h"):
         assert np.array_equal(a.field(f), b.field(f)), f
+
+
+@pytest.mark.parametrize("variant", ["hopkins", "hopkins_full"])
+def test_fused_hopkins_step_equals_operator_sequence(gpu, variant):
+    """sphmw_step("hopkins"/"hopkins_full") — three fused pair passes, the first recording the
+    pair list, the other two replaying it — leaves the state of the literal operator sequence
+    (hopkins_perturbed_witch.jl:324-349, full_hopkins_perturbed_witch.jl:350-374), bit for bit"""
+    case = cases.hopkins_2d(variant)
+    a, b = load_gpu(case), load_gpu(case)
+    a.create_cell_list()
+    b.create_cell_list()
+    a.timing(True)
+    a.step(5, variant)
+    b.step(5, variant + "_unfused")
+    names = a.timing_report()
+    assert "hopkins.pressure_fused" in names and "hopkins.momentum_fused" in names, names
+    for f in ("x", "v", "rho", "rho_p", "h", "P", "P_p", "P_bg", "T", "theta", "A", "Dv"):
+        assert np.array_equal(a.field(f), b.field(f), equal_nan=True), f
