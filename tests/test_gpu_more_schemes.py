@@ -310,6 +310,8 @@ def test_async_frame_capture_and_upload_prefetch(gpu):
     # prefetch: a second system fed through upload_async/commit equals one fed through upload
     a, b = load_gpu(case), load_gpu(case)
     a.create_cell_list()
+    b.create_cell_list()
+    b.step(2)                                   # b's state is about to be replaced wholesale
     keep = {}
     for f in ("x", "v", "m", "h", "rho", "rho_p", "type"):
         arr = case.fields[f]
