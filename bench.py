@@ -38,7 +38,10 @@ WORKLOADS = {
     "bell_hill_3d_256M": (3100, 240, 320),
     # BASELINE config 3: 2D Witch of Agnesi, dr = 26 km / 510 (one GPU only)
     "witch_2d_4M": None,
+    # BASELINE config 2: 2D isothermal atmosphere at rest (hydrostatic well-balance test), ~244 k particles
+    "static_2d_250k": None,
 }
+CASES_2D = {"witch_2d_4M": "witch_2d", "static_2d_250k": "static_atmosphere_2d"}
 
 
 def parse():
@@ -223,8 +226,9 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         if is2d:
-            assert world == 1, "the 2D workload is a single-GPU configuration (BASELINE config 3)"
-            run = SlabRun.whole(cases.witch_2d(), device=local, stream=stream.cuda_stream, flags=args.flags)
+            assert world == 1, "the 2D workloads are single-GPU configurations (BASELINE configs 2 and 3)"
+            run = SlabRun.whole(getattr(cases, CASES_2D[args.workload])(), device=local, stream=stream.cuda_stream,
+                                flags=args.flags)
         else:
             run = SlabRun.bell_hill_3d(nx, ny, nz, rank=rank, world=world, device=local,
                                        stream=stream.cuda_stream, flags=args.flags,
@@ -302,8 +306,19 @@ def run_ours(args):
                 traffic = (rec["dram_bytes_read"] + rec["dram_bytes_write"]) / 1e9
         except Exception:
             pass
+        # the second bound SURVEY.md §8d asks for: the FP64 pipe, against the MEASURED DFMA peak
+        # (profiles/microbench/fp64_peak.cu) and with the pipe utilisation ncu saw for this kernel
+        fp64 = None
+        try:
+            pk = json.loads((ROOT / "profiles" / "r02_final_fp64_peak.json").read_text())
+            fp64 = {"peak_tflops_measured": pk["fp64_peak_tflops"], "dfma_per_clk_per_sm": pk["dfma_per_clk_per_sm"],
+                    "pipe_busy_frac_ncu": 0.454 if not (args.flags & 1) else 0.350,
+                    "source": "profiles/r02_final_fp64_peak.json, profiles/r02_ncu_shipped_64M_strict.txt "
+                              "(sm__inst_executed_pipe_fp64, 64 M particles strict; fast: 9 M particles)"}
+        except Exception:
+            pass
         roofline = {
-            "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "bound": "hbm", "kernel": kname, "fp64": fp64, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
             "frac": achieved / peak_gbs, "traffic": traffic, "traffic_unit": "GB per launch (ncu)",
             "alg_gbytes_per_launch": alg_bytes / 1e9, "peak_source": peak_src,
             "alg_bytes_per_particle": BYTES["K_C"], "ms_per_launch": per_launch_s * 1e3,
@@ -364,7 +379,10 @@ def run_ours(args):
                                       1: "fast (FMA + reciprocals in the closure bodies; exact neighbour set; "
                                          "<=1e-13 rel. of strict per step)",
                                       2: "strict, cell-centric pair-parallel kernel"}.get(args.flags & 3, str(args.flags)),
-                       "l2": "inputs (>= 80 B x particles) far exceed the 126 MB L2; no flush needed",
+                       "l2": ("inputs (>= 80 B x particles) far exceed the 126 MB L2; no flush needed"
+                              if n_total * 80 > 4 * 126e6 else
+                              "SMALL workload: the state (%.0f MB) fits the 126 MB L2, no flush between steps — "
+                              "a parity/latency case, not a bandwidth figure" % (n_total * 485 / 1e6)),
                        "pair_interactions_per_s": pairs_force * 2 / (ms_max * 1e-3 / args.steps)
                        if pairs_force else None,
                        "pairs_per_binary_pass": pairs_force,
