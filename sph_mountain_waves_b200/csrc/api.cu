@@ -433,6 +433,13 @@ __global__ void k_permute_out(double *__restrict__ stg, const double *__restrict
     if (pos < n) stg[idx[pos]] = src[pos];
 }
 
+__global__ void k_count_nonzero(const double *__restrict__ a, int64_t n, unsigned long long *__restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool nz = i < n && !(a[i] == 0.0);  // NaN counts as non-zero
+    const int cnt = __syncthreads_count(nz);
+    if (threadIdx.x == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
+}
+
 extern "C" int sphmw_upload(sphmw_ctx *c, const char *field, const double *buf, int64_t n,
                             int32_t ncomp) {
     if (!c || !field || !buf) { sphmw_set_error("null argument"); return SPHMW_E_INVALID; }
@@ -450,8 +457,20 @@ extern "C" int sphmw_upload(sphmw_ctx *c, const char *field, const double *buf, 
     for (int k = 0; k < ncomp; ++k) {
         int slot = d->slot + k;
         if (c->grid.dim == 2 && ncomp == 3 && k == 2) {
-            // 2D systems keep no third component: it must be exactly zero or the
-            // particle would leave the box 0 <= x[3] <= 0 (geometry.jl:24-30).
+            // 2D systems keep no third component.  In the reference a particle with x[3] != 0 leaves
+            // the box 0 <= x[3] <= 0 (geometry.jl:24-30) and is removed, and one with v[3] != 0 does so
+            // after its first move!; silently dropping the component would diverge from that, so a
+            // non-zero third component is refused.
+            CUDA_TRY(cudaMemsetAsync(c->d_counters + 7, 0, sizeof(unsigned long long), c->stream));
+            k_count_nonzero<<<grid_for(n, 256), 256, 0, c->stream>>>(c->staging + (int64_t)k * n, n, c->d_counters + 7);
+            CUDA_TRY(cudaMemcpyAsync(c->h_counters + 7, c->d_counters + 7, sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            if (c->h_counters[7] != 0) {
+                sphmw_set_error("upload(%s): %llu particles have a non-zero third component in a 2D system "
+                                "(the reference would remove them: box 0 <= x[3] <= 0)", field, c->h_counters[7]);
+                return SPHMW_E_INVALID;
+            }
             continue;
         }
         TRY(sphmw_ensure_slot(c, slot));
@@ -511,6 +530,11 @@ extern "C" int sphmw_download(sphmw_ctx *c, const char *field, double *buf, int6
 // reductions — avg_velocity/max_velocity (wcsph_perturbed_witch.jl:338-350)
 // ---------------------------------------------------------------------------
 // mode 0: sum of a, 1: max of a, 2: sum |v|, 3: max |v|
+// Julia's max propagates NaN (wcsph_perturbed_witch.jl:345-350 uses it for max_velocity); fmax drops it
+__device__ __forceinline__ double nanmax(double a, double b) {
+    if (a != a || b != b) return a + b;
+    return a < b ? b : a;
+}
 __global__ void k_reduce(const double *a, const double *b, const double *cc, int64_t n, int mode,
                          double *out) {
     __shared__ double sh[32];
@@ -524,11 +548,11 @@ __global__ void k_reduce(const double *a, const double *b, const double *cc, int
         } else {
             v = a[i];
         }
-        acc = (mode & 1) ? fmax(acc, v) : acc + v;
+        acc = (mode & 1) ? nanmax(acc, v) : acc + v;
     }
     for (int o = 16; o > 0; o >>= 1) {
         double t = __shfl_down_sync(0xffffffffu, acc, o);
-        acc = (mode & 1) ? fmax(acc, t) : acc + t;
+        acc = (mode & 1) ? nanmax(acc, t) : acc + t;
     }
     int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (l == 0) sh[w] = acc;
@@ -538,7 +562,7 @@ __global__ void k_reduce(const double *a, const double *b, const double *cc, int
         acc = l < nw ? sh[l] : ((mode & 1) ? -INFINITY : 0.0);
         for (int o = 16; o > 0; o >>= 1) {
             double t = __shfl_down_sync(0xffffffffu, acc, o);
-            acc = (mode & 1) ? fmax(acc, t) : acc + t;
+            acc = (mode & 1) ? nanmax(acc, t) : acc + t;
         }
         if (l == 0) out[blockIdx.x] = acc;
     }

@@ -361,9 +361,26 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     c->slab_dead_known = false;
     if (k > 0 && c->slab_lo < 0) {
         if (k > c->removed_cap) {
-            sphmw_set_error("more than %lld particles left the domain in one step",
-                            (long long)c->removed_cap);
-            return SPHMW_E_CAPACITY;
+            // the list of removed indices did not fit (the reference removes any number of
+            // particles, core.jl:60-81): grow it and run the key kernel again — it rewrites the same
+            // keys and fills the list; histogram and scatter did not depend on the list
+            cudaFree(c->removed);
+            cudaFreeHost(c->h_removed);
+            c->removed = nullptr;
+            c->h_removed = nullptr;
+            c->removed_cap = k + k / 4 + 1024;
+            CUDA_TRY(cudaMalloc(&c->removed, sizeof(uint32_t) * (c->removed_cap + 1)));
+            CUDA_TRY(cudaMallocHost(&c->h_removed, sizeof(uint32_t) * (c->removed_cap + 1)));
+            CUDA_TRY(cudaMemsetAsync(c->removed, 0, sizeof(uint32_t) * 2, c->stream));
+            const unsigned gr = grid_for(n, 256);
+            if (g.dim == 2)
+                k_keys<2, false><<<gr, 256, 0, c->stream>>>(c->cur.s[S_X0], c->cur.s[S_X1], c->cur.s[S_X2], n, g, c->key,
+                                                            c->removed, (uint32_t)c->removed_cap, c->idx, c->tag, c->cellx);
+            else
+                k_keys<3, false><<<gr, 256, 0, c->stream>>>(c->cur.s[S_X0], c->cur.s[S_X1], c->cur.s[S_X2], n, g, c->key,
+                                                            c->removed, (uint32_t)c->removed_cap, c->idx, c->tag, c->cellx);
+            CUDA_TRY(cudaGetLastError());
+            c->launches += 1;
         }
         CUDA_TRY(cudaMemcpyAsync(c->h_removed + 1, c->removed + 1, sizeof(uint32_t) * k,
                                  cudaMemcpyDeviceToHost, c->stream));

@@ -18,6 +18,11 @@
 //                 have not changed since the recording pass, so the accepted set is the list
 //                 itself and no test is repeated.
 //
+// STATUS: opt-in (SPHMW_FLAG_TILES).  Correct — CPU emulation and GPU tests — but 2.5x slower than the
+// packed-record kernels of pair_list.cuh on B200: a 114 KB tile per 4 warps leaves 8 warps per SM, and a
+// thread's closure is one dependent chain that two warps per scheduler cannot hide
+// (profiles/r02_pair_kernels.md §3).
+//
 // Visiting order is that of k_binary (pair_ops.cu) — key_diff order, cell entries front to back —
 // so every FP64 sum keeps its bits.  Blocks whose tile does not fit (crowded cells) or that
 // straddle too many chunk rows (narrow or sparse grids), and particles whose candidates overflow
@@ -189,11 +194,11 @@ __host__ __device__ constexpr int tile_bytes_build(int stride) {
 // The block's record goes to shared memory, the global position of every slot is written out
 // (gidx: the copy loops and the non-staged fields address global memory through it), then the
 // field arrays follow — either
-//   TILE_STAGE_TMA 1  one bulk copy (cp.async.bulk, TMA engine) per (segment, array), completion
-//                     on an mbarrier.  Measured on B200: ~240 cycles of SM time per copy whatever
-//                     its size; with SoA fields a block issues 100-160 copies of ~1 KB and the
-//                     passes run 3x slower than without tiles (profiles/r02_tiles.md)
+//   TILE_STAGE_TMA 1  one bulk copy (cp.async.bulk, TMA engine; SASS UBLKCP.S.G) per (segment, array),
+//                     completion on an mbarrier (SYNCS.*): no LSU instructions, no registers
 //   TILE_STAGE_TMA 0  coalesced 16-byte loads and stores by all threads (default)
+// Both were measured on B200 and run the passes at the same speed (profiles/r02_pair_kernels.md):
+// the tiled kernels are not limited by the staging but by their 8 resident warps per SM.
 #ifndef TILE_STAGE_TMA
 #define TILE_STAGE_TMA 0
 #endif
