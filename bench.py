@@ -347,7 +347,7 @@ def run_ours(args):
         # ---- end to end through the public API with HOST buffers ------------------
         e2e = None
         if not args.no_e2e:
-            e2e = run.e2e_cycle(cycles=4, barrier=barrier)   # 4 frame intervals: the copies of one overlap the steps of the next
+            e2e = run.e2e_cycle(cycles=6, barrier=barrier)   # 6 frame intervals: the copies of one overlap the steps of the next
             te = torch.tensor([e2e["seconds"]], dtype=torch.float64, device="cuda")
             tb = torch.tensor([e2e["h2d_bytes"], e2e["d2h_bytes"]], dtype=torch.float64, device="cuda")
             if world > 1:

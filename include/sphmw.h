@@ -85,7 +85,8 @@ typedef struct sphmw_config {
  * by the density pass) with one 256-bit load each instead of eleven 8-byte gathers (+96 B per
  * particle; the records are bit copies of the SoA fields, so no sum changes).  Measured on B200,
  * 64 M particles: step 48.5 -> 42.1 ms (profiles/r02_pair_kernels.md).  NO_PACKED_RECORDS: gather
- * from the SoA arrays.  PACKED_RECORDS (the round-1 opt-in bit) is accepted and ignored.
+ * from the SoA arrays.  The records are the default in 3D; in 2D (9 neighbour fields instead of 11) the SoA
+ * gathers are 6 % faster and stay the default, PACKED_RECORDS switches the records on there.
  * Ignored together with NO_PAIR_LIST / CELL_PAIRS. */
 #define SPHMW_FLAG_PACKED_RECORDS 32
 #define SPHMW_FLAG_NO_PACKED_RECORDS 128

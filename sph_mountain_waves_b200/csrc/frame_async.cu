@@ -43,7 +43,8 @@ struct UploadItem {
 };
 
 struct FrameAsync {
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // device -> host (frames)
+    cudaStream_t up_stream = nullptr;    // host -> device (prefetch): its own stream, so that a commit never waits for a frame copy
     FrameSlot slot[2];
     int next = 0;
     // upload prefetch
@@ -72,6 +73,7 @@ static int fa_get(sphmw_ctx *c, FrameAsync **out) {
         FrameAsync *fa = new FrameAsync();
         c->frame_async = fa;
         CUDA_TRY(cudaStreamCreateWithFlags(&fa->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&fa->up_stream, cudaStreamNonBlocking));
         for (FrameSlot &s : fa->slot) {
             CUDA_TRY(cudaEventCreateWithFlags(&s.snapped, cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
@@ -105,10 +107,12 @@ void sphmw_frame_async_free(sphmw_ctx *c) {
         if (s.copied) cudaEventDestroy(s.copied);
     }
     if (fa->copy_stream) cudaStreamSynchronize(fa->copy_stream);
+    if (fa->up_stream) cudaStreamSynchronize(fa->up_stream);
     cudaFree(fa->up_dev);
     if (fa->up_copied) cudaEventDestroy(fa->up_copied);
     if (fa->up_consumed) cudaEventDestroy(fa->up_consumed);
     if (fa->copy_stream) cudaStreamDestroy(fa->copy_stream);
+    if (fa->up_stream) cudaStreamDestroy(fa->up_stream);
     delete fa;
     c->frame_async = nullptr;
 }
@@ -257,7 +261,7 @@ extern "C" int sphmw_upload_async(sphmw_ctx *c, const char *field, const double 
         fa->up_n = n;
         fa->up_used = 0;
         // the staging area may still be read by the permute kernels of the previous commit
-        if (fa->up_consumed_valid) CUDA_TRY(cudaStreamWaitEvent(fa->copy_stream, fa->up_consumed, 0));
+        if (fa->up_consumed_valid) CUDA_TRY(cudaStreamWaitEvent(fa->up_stream, fa->up_consumed, 0));
     } else if (n != fa->up_n) {
         sphmw_set_error("upload_async: all fields of one batch have the same length");
         return SPHMW_E_INVALID;
@@ -265,14 +269,14 @@ extern "C" int sphmw_upload_async(sphmw_ctx *c, const char *field, const double 
     const size_t need = fa->up_used + (size_t)ncomp * (size_t)n;
     if (need > fa->up_cap) {
         if (!fa->up_items.empty()) { sphmw_set_error("upload_async: staging area too small for this batch"); return SPHMW_E_CAPACITY; }
-        CUDA_TRY(cudaStreamSynchronize(fa->copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(fa->up_stream));
         cudaFree(fa->up_dev);
         fa->up_dev = nullptr;
         fa->up_cap = std::max<size_t>((size_t)16 * (size_t)c->cap, need);  // x, v, and ten scalars
         CUDA_TRY(cudaMalloc(&fa->up_dev, sizeof(double) * fa->up_cap));
     }
     if (n) CUDA_TRY(cudaMemcpyAsync(fa->up_dev + fa->up_used, buf, sizeof(double) * ncomp * n, cudaMemcpyHostToDevice,
-                                    fa->copy_stream));
+                                    fa->up_stream));
     fa->up_items.push_back(UploadItem{d->slot, ncomp, fa->up_used});
     fa->up_used = need;
     return SPHMW_OK;
@@ -292,7 +296,7 @@ extern "C" int sphmw_upload_commit(sphmw_ctx *c) {
     FrameAsync *fa = c->frame_async;
     TRY(sphmw_resize(c, 0));
     TRY(sphmw_resize(c, fa->up_n));
-    CUDA_TRY(cudaEventRecord(fa->up_copied, fa->copy_stream));
+    CUDA_TRY(cudaEventRecord(fa->up_copied, fa->up_stream));
     CUDA_TRY(cudaStreamWaitEvent(c->stream, fa->up_copied, 0));
     const int64_t n = fa->up_n;
     for (const UploadItem &it : fa->up_items)

@@ -310,10 +310,14 @@ struct sphmw_ctx {
     int64_t launches = 0;
 };
 
-// the fused pair passes read packed neighbour records unless told otherwise (sphmw.h)
+// The fused pair passes read packed neighbour records unless told otherwise (sphmw.h).  Default in 3D
+// only: in 2D a neighbour needs 9 fields, the records still move 96 bytes, and the SoA gathers are 6 %
+// faster (4.1 M particles: 1.19 vs 1.26 ms per step, profiles/r02_pair_kernels.md); PACKED_RECORDS forces them.
 static inline bool sphmw_use_records(const sphmw_ctx *c) {
-    return !(c->flags & (SPHMW_FLAG_NO_PACKED_RECORDS | SPHMW_FLAG_NO_PAIR_LIST | SPHMW_FLAG_CELL_PAIRS |
-                         SPHMW_FLAG_TILES | SPHMW_FLAG_NO_PRETEST));
+    if (c->flags & (SPHMW_FLAG_NO_PACKED_RECORDS | SPHMW_FLAG_NO_PAIR_LIST | SPHMW_FLAG_CELL_PAIRS | SPHMW_FLAG_TILES |
+                    SPHMW_FLAG_NO_PRETEST))
+        return false;
+    return c->grid.dim == 3 || (c->flags & SPHMW_FLAG_PACKED_RECORDS);
 }
 
 // error plumbing -----------------------------------------------------------

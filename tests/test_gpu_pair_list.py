@@ -218,6 +218,7 @@ def test_cutoff_boundary_in_3d_across_cell_faces(gpu):
 # shared memory (csrc/pair_tile.cuh).  All must give the same bits.
 # ---------------------------------------------------------------------------------------
 NO_RECORDS = 128
+PACKED = 32    # forces the records in 2D, where SoA gathers are the default
 TILES = 64
 
 
@@ -233,7 +234,7 @@ def long_2d():
 
 @pytest.mark.parametrize("make", [small_2d, small_3d, long_2d, long_3d])
 @pytest.mark.parametrize("arith", [0, FAST_MATH])
-@pytest.mark.parametrize("variant", [NO_RECORDS, TILES])
+@pytest.mark.parametrize("variant", [NO_RECORDS, PACKED, TILES])
 def test_pair_pass_variants_same_bits(gpu, make, arith, variant):
     """records (default) vs SoA gathers vs shared-memory tiles: the neighbour data are bit copies
     of the SoA fields and the visiting order is the same, so nothing may change"""
