@@ -105,6 +105,17 @@ extern "C" int sphmw_get_param(sphmw_ctx *c, const char *name, double *v) {
     return SPHMW_E_INVALID;
 }
 
+__global__ void k_publish_words(const uint32_t *__restrict__ src, volatile uint32_t *dst, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+int sphmw_publish_words(sphmw_ctx *c, const uint32_t *dev_src, uint32_t *pinned_dst, int nwords, cudaStream_t stream) {
+    k_publish_words<<<1, 32, 0, stream>>>(dev_src, pinned_dst, nwords);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
+    return SPHMW_OK;
+}
+
 // ---------------------------------------------------------------------------
 // timing
 // ---------------------------------------------------------------------------

@@ -309,8 +309,7 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
         else k_keys<3, true><<<gr, 256, 0, c->stream>>>(KEYS_ARGS);
 #undef KEYS_ARGS
     }
-    CUDA_TRY(cudaMemcpyAsync(c->h_removed, c->removed, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost,
-                             c->stream));
+    TRY(sphmw_publish_words(c, c->removed, c->h_removed, 2, c->stream));
     // overlap the host round trip with the histogram
     CUDA_TRY(cudaMemsetAsync(c->cell_start, 0, sizeof(uint32_t) * (ncells + 2), c->stream));
     {
@@ -345,8 +344,7 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
             }
         }
         const int cur = (int)(c->slab_checks & 3);
-        CUDA_TRY(cudaMemcpyAsync(c->h_slab_check + 2 * cur, c->removed, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost,
-                                 c->stream));
+        TRY(sphmw_publish_words(c, c->removed, c->h_slab_check + 2 * cur, 2, c->stream));
         CUDA_TRY(cudaEventRecord(c->slab_check_event[cur], c->stream));
         k = c->slab_dead_expected;
         owned_live = (uint32_t)c->n_owned;

@@ -170,8 +170,7 @@ static int pack_enqueue(sphmw_ctx *c, double *dev_buf_left, double *dev_buf_righ
         k_halo_header<<<1, 32, 0, c->stream>>>(c->halo_counters, msg_left, msg_right);
         c->launches += 1;
     }
-    CUDA_TRY(cudaMemcpyAsync(c->h_halo_counters, c->halo_counters, sizeof(uint32_t) * 8,
-                             cudaMemcpyDeviceToHost, c->stream));
+    TRY(sphmw_publish_words(c, c->halo_counters, c->h_halo_counters, 8, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->halo_counters + 5, 0, sizeof(uint32_t), c->stream));
     CUDA_TRY(cudaEventRecord(c->pack_event, c->stream));
     return SPHMW_OK;

@@ -197,9 +197,9 @@ static int comm_round(sphmw_ctx *c, const int64_t srows[2], const int64_t rrows[
     }
     NCCL_TRY(g_nccl.GroupEnd());
     for (int s = 0; s < 2; ++s)
-        if (m->has[s] && rrows[s] > 0)
-            CUDA_TRY(cudaMemcpyAsync(m->h_head + s * HALO_RECORD, m->recv[s], sizeof(double) * HALO_RECORD,
-                                     cudaMemcpyDeviceToHost, m->stream));
+        if (m->has[s] && rrows[s] > 0)  // (a kernel store, not a copy-engine transfer: see sphmw_publish_words)
+            TRY(sphmw_publish_words(c, (const uint32_t *)m->recv[s], (uint32_t *)(m->h_head + s * HALO_RECORD), 2 * HALO_RECORD,
+                                    m->stream));
     CUDA_TRY(cudaEventRecord(m->recv_event, m->stream));
     return SPHMW_OK;
 }

@@ -388,6 +388,12 @@ int sphmw_write_vtp(const char *path, int64_t n, const double *points3n, int nfi
                     const char *const *names, const int *ncomps, const double *const *data);
 int sphmw_write_pvd(const char *path, const std::vector<std::string> &files);
 
+// A few words from device memory to PINNED host memory, written by a one-thread kernel through the
+// unified address space instead of a cudaMemcpyAsync: the step's counters (removed particles, halo
+// record counts) must not queue on the device-to-host copy engine behind a multi-gigabyte frame copy
+// of another stream (measured: every step of a frame interval waited 15 ms for it; api.cu)
+int sphmw_publish_words(sphmw_ctx *c, const uint32_t *dev_src, uint32_t *pinned_dst, int nwords, cudaStream_t stream);
+
 // timing helpers (api.cu)
 struct KernelTimer {
     sphmw_ctx *c;
