@@ -213,12 +213,15 @@ int sphmw_tile_info(sphmw_ctx *ctx, int64_t out[6]);
 /* Host-only test hooks (no device, no context).
  * sphmw_pretest_pairs: the integer pre-test of the pair-list recording pass on n pairs
  * (xp, xq: n x 3 doubles): pass[i] = 1 passes, 0 rejected, 2 q is not in one of p's 27 cells.
- * Every pair with r <= h must pass.
+ * Every pair with r <= h must pass.  (10-bit mirror of the x-chunked cell order, SPHMW_FLAG_TILES.)
  * sphmw_slab_column_sets: the column sets of the overlapped slab step for a context `width`
  * local columns wide (ghosts included): out = {edge, interior, force_edge, force_interior} x
  * {a0, a1, b0, b1}, each set [a0,a1] U [b0,b1] (empty when first > last). */
 int sphmw_pretest_pairs(const double *xp, const double *xq, int64_t n, double h, int32_t dim,
                         uint8_t *pass);
+/* the same for the 6-bit pre-test of the default (zrun) cell order: one packed add + DP4A */
+int sphmw_pretest_pairs_q6(const double *xp, const double *xq, int64_t n, double h, int32_t dim,
+                           uint8_t *pass);
 int sphmw_slab_column_sets(int32_t width, int32_t has_left, int32_t has_right, int32_t out[16]);
 
 /* ≙ avg_velocity / max_velocity / length(sys.particles)

@@ -260,6 +260,17 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
             delete c;
             return rc;
         }
+        // physical cell order: zrun unless a shared-memory variant that stages x-rows is asked for;
+        // sphmw_set_flags may switch later, so the cell-start table is sized for either order
+        Grid xo = g;
+        sphmw_grid_set_order(xo, false);
+        c->cells_cap = std::max(g.pkey_max, xo.pkey_max);
+        if (c->cells_cap >= (long long)0x7FFFFFF0) {
+            sphmw_set_error("too many cells (%lld)", (long long)c->cells_cap);
+            delete c;
+            return SPHMW_E_INVALID;
+        }
+        if (!sphmw_want_zrun(c->flags)) g = xo;
     }
     memset(&c->prm, 0, sizeof(Params));
 
@@ -280,7 +291,7 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
         CUDA_TRY(cudaMalloc(&c->cellx_alt, sizeof(uint32_t) * c->cap));
         CUDA_TRY(cudaMalloc(&c->rank, sizeof(uint32_t) * c->cap));
         CUDA_TRY(cudaMalloc(&c->src, sizeof(uint32_t) * c->cap));
-        CUDA_TRY(cudaMalloc(&c->cell_start, sizeof(uint32_t) * (g.pkey_max + 2)));
+        CUDA_TRY(cudaMalloc(&c->cell_start, sizeof(uint32_t) * (c->cells_cap + 2)));
         c->removed_cap = 1 << 20;
         CUDA_TRY(cudaMalloc(&c->removed, sizeof(uint32_t) * (c->removed_cap + 1)));
         CUDA_TRY(cudaMallocHost(&c->h_removed, sizeof(uint32_t) * (c->removed_cap + 1)));
@@ -343,6 +354,18 @@ extern "C" int sphmw_set_stream(sphmw_ctx *c, void *s) {
 extern "C" int sphmw_set_flags(sphmw_ctx *c, int32_t flags) {
     if (!c) return SPHMW_E_INVALID;
     c->flags = flags;
+    if ((c->grid.zrun != 0) != sphmw_want_zrun(flags)) {
+        // the variant asked for needs the other physical cell order: same cells, same particles,
+        // stored differently — rebuild the cell list if one was valid (results do not change)
+        CUDA_TRY(cudaSetDevice(c->device));
+        sphmw_grid_set_order(c->grid, sphmw_want_zrun(flags));
+        c->pl_gen = ~0ull;
+        c->tile_gen = ~0ull;
+        if (c->cell_list_valid) {
+            c->cell_list_valid = false;
+            if (c->slab_lo < 0) TRY(sphmw_build_cell_list(c, nullptr));
+        }
+    }
     return SPHMW_OK;
 }
 extern "C" int sphmw_sync(sphmw_ctx *c) {
@@ -730,6 +753,27 @@ extern "C" int sphmw_pretest_pairs(const double *xp, const double *xq, int64_t n
             dc[a] = (int)d;
         }
         pass[i] = !neighbour ? 2 : (nl_q10_pass(wp, wq, dc[0], dc[1], dc[2], dim) ? 1 : 0);
+    }
+    return SPHMW_OK;
+}
+// the 6-bit pre-test of the zrun cell order (the default): words as the cell-list gather writes
+// them, the run constant as k_binary_build forms it
+extern "C" int sphmw_pretest_pairs_q6(const double *xp, const double *xq, int64_t n, double h, int32_t dim,
+                                      uint8_t *pass) {
+    if (!xp || !xq || !pass || !(h > 0.0) || (dim != 2 && dim != 3)) return SPHMW_E_INVALID;
+    for (int64_t i = 0; i < n; ++i) {
+        int dc[3] = {0, 0, 0};
+        bool neighbour = true;
+        for (int a = 0; a < dim; ++a) {
+            const double d = floor(xq[3 * i + a] / h) - floor(xp[3 * i + a] / h);
+            if (!(fabs(d) <= 1.0)) neighbour = false;
+            dc[a] = (int)d;
+        }
+        const long long phase = -7;  // any key_phase: the run-axis byte is taken modulo four cells
+        const uint32_t wp = nl_q6_word(xp[3 * i], xp[3 * i + 1], xp[3 * i + 2], h, phase, dim);
+        const uint32_t wq = nl_q6_word(xq[3 * i], xq[3 * i + 1], xq[3 * i + 2], h, phase, dim);
+        const uint32_t K = nl_q6_run_const(wp, dc[0], dim == 3 ? dc[1] : 0);
+        pass[i] = !neighbour ? 2 : (nl_q6_dist2(K, wq) > NL_Q6_R2MAX ? 0 : 1);
     }
     return SPHMW_OK;
 }

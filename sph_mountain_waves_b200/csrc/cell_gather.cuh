@@ -1,6 +1,6 @@
 // The last kernel of the cell-list build (cell_list.cu): one launch permutes every live field
 // into the new physical order — (cell ascending, reference index descending), core.jl:32-37 —
-// and writes the per-particle data the pair passes derive from the sorted positions (the 10-bit
+// and writes the per-particle data the pair passes derive from the sorted positions (the quantised
 // pre-test mirror and, when enabled, neighbour record A).  In a header so that the CPU emulation
 // harness (tests/emu/) runs the same code.
 #pragma once
@@ -11,10 +11,12 @@ struct GatherList {
     double *to[NSLOT];
     int count;
     // quantised mirror of the sorted positions (pair_list.cuh): where the particle sits inside
-    // its own cell, 10 bits per axis (h/1024)
+    // its own cell — the 6-bit word of the zrun cell order (q6), else 10 bits per axis (h/1024)
     int xpos[3];  // entry of x0/x1/x2 in the lists above (-1: no such component)
     double h;
     uint32_t *xq;
+    int q6, dim;
+    long long run_phase;  // key_phase of the run axis (z in 3D, y in 2D)
     // packed neighbour record A {x, y, z, m} (SPHMW_FLAG_PACKED_RECORDS; null otherwise)
     int mpos;
     NbRec *recA;
@@ -48,6 +50,7 @@ __global__ void k_gather(GatherList gl, const uint32_t *__restrict__ src,
                 qm |= nl_q10_axis(v, gl.h) << (10 * a);
             }
     }
+    if (gl.q6) qm = nl_q6_word(ra[0], ra[1], ra[2], gl.h, gl.run_phase, gl.dim);
     gl.xq[slot] = qm;
     if (gl.recA) nb_store(gl.recA + slot, ra[0], ra[1], ra[2], ra[3]);
 }

@@ -47,7 +47,7 @@ __global__ void k_keys(const double *__restrict__ x0, const double *__restrict__
                 long long kk = DIM == 3 ? (long long)floor(z / g.h) - g.phase[2] : 0;
                 if (i < 0 || i >= g.lim[0]) inside = false;
                 else {
-                    k = pkey_of(g, (int)i, (int)(j + g.lim[1] * kk));
+                    k = pkey_ijk(g, (int)i, (int)j, (int)kk);
                     ci = (uint32_t)i;
                 }
             }
@@ -81,7 +81,7 @@ __global__ void k_keys(const double *__restrict__ x0, const double *__restrict__
         long long j = (long long)floor(y / g.h) - g.phase[1];
         long long kk = DIM == 3 ? (long long)floor(z / g.h) - g.phase[2] : 0;
         // structs.jl:102 gives the reference key i + Lx*(j + Ly*k); stored is its physical image
-        k = pkey_of(g, (int)i, (int)(j + g.lim[1] * kk));
+        k = pkey_ijk(g, (int)i, (int)j, (int)kk);
         ci = (uint32_t)i;
     }
     if (!inside) {
@@ -416,6 +416,9 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     int gathered[NSLOT];
     gl.xq = c->xq;
     gl.h = g.h;
+    gl.q6 = g.zrun;  // mirror format follows the physical cell order (sphmw_internal.h)
+    gl.dim = g.dim;
+    gl.run_phase = g.phase[g.dim == 3 ? 2 : 1];
     for (int a = 0; a < 3; ++a) gl.xpos[a] = -1;
     gl.mpos = -1;
     gl.recA = nullptr;

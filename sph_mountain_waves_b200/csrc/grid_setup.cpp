@@ -5,6 +5,7 @@
 // emulation harness of the CPU test suite (tests/emu/).
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -21,6 +22,35 @@ void sphmw_derive_params(Params &p) {
     } else {
         p.sponge_y = 0.0;
     }
+}
+
+// Physical cell order (sphmw_internal.h, Grid::zrun).  zrun: x outermost, the innermost axis of the
+// reference's key_diff loops fastest — the default.  Otherwise x-chunked rows: a pass needs three
+// x-y planes of cells at a time; chunks are sized so that three chunk-planes (~6 particles x ~100 B
+// per cell) stay near 40 MB, well inside the 126 MB L2: about 22000 / Ly columns (measured on the
+// 64 M case, profiles/r01_tuning.md: 256 columns best of 32..2048).  Grids up to 1.5x that wide, and
+// 2D grids, stay one chunk (plain x-fastest rows); wider ones are cut into equal-looking
+// power-of-two chunks.
+void sphmw_grid_set_order(Grid &g, bool zrun) {
+    g.zrun = zrun ? 1 : 0;
+    g.rows = g.lim[1] * g.lim[2];
+    g.cx_shift = 0;
+    if (zrun) {
+        g.pkey_max = g.lim[0] * g.rows;
+        return;
+    }
+    const long long lx = g.lim[0];
+    const long long want = g.dim == 3 ? std::max<long long>(32, 22000 / std::max<long long>(1, g.lim[1])) : lx;
+    long long cols = lx;
+    if (2 * lx > 3 * want) {
+        const long long nchunks = (lx + want - 1) / want;
+        cols = (lx + nchunks - 1) / nchunks;
+    }
+    while ((1LL << g.cx_shift) < cols) ++g.cx_shift;
+    if (getenv("SPHMW_CX_SHIFT")) g.cx_shift = atoi(getenv("SPHMW_CX_SHIFT"));
+    const long long cx = 1LL << g.cx_shift;
+    const long long nchunks = (g.lim[0] + cx - 1) / cx;
+    g.pkey_max = nchunks * cx * g.rows;
 }
 
 int sphmw_grid_setup(Grid &g, const double box_min[3], const double box_max[3], double h, int64_t slab_lo,
@@ -87,29 +117,7 @@ int sphmw_grid_setup(Grid &g, const double box_min[3], const double box_max[3], 
                     g.key_diff[g.ndiff++] = (int)(di + g.lim[0] * (dj + g.lim[1] * dk));
                 }
     }
-    // physical x-chunking.  A pass needs three x-y planes of cells at a time; chunks are sized
-    // so that three chunk-planes (~6 particles x ~100 B per cell) stay near 40 MB, well inside
-    // the 126 MB L2: about 22000 / Ly columns (measured on the 64 M case, profiles/r01_tuning.md:
-    // 256 columns best of 32..2048).  Grids up to 1.5x that wide, and 2D grids, stay one chunk
-    // (plain x-fastest rows); wider ones are cut into equal-looking power-of-two chunks.
-    {
-        const long long lx = g.lim[0];
-        const long long want = g.dim == 3 ? std::max<long long>(32, 22000 / std::max<long long>(1, g.lim[1])) : lx;
-        long long cols = lx;
-        if (2 * lx > 3 * want) {
-            const long long nchunks = (lx + want - 1) / want;
-            cols = (lx + nchunks - 1) / nchunks;
-        }
-        g.cx_shift = 0;
-        while ((1LL << g.cx_shift) < cols) ++g.cx_shift;
-    }
-    if (getenv("SPHMW_CX_SHIFT")) g.cx_shift = atoi(getenv("SPHMW_CX_SHIFT"));
-    g.rows = g.lim[1] * g.lim[2];
-    {
-        long long cx = 1LL << g.cx_shift;
-        long long nchunks = (g.lim[0] + cx - 1) / cx;
-        g.pkey_max = nchunks * cx * g.rows;
-    }
+    sphmw_grid_set_order(g, !(getenv("SPHMW_CELL_ORDER") && !strcmp(getenv("SPHMW_CELL_ORDER"), "xchunk")));
     if (g.pkey_max >= (long long)0x7FFFFFF0) {
         sphmw_set_error("too many cells (%lld)", g.pkey_max);
         return SPHMW_E_INVALID;

@@ -1,12 +1,13 @@
 // Pair-list kernels: _apply_binary! (src/core.jl:94-112) split into a recording pass and
 // replaying passes.  See PairList in sphmw_internal.h for the layout and the invariants.
 //
-//   k_binary_build  walks the 9/27 neighbour cells in key_diff order (structs.jl:73-81) with a
-//                   cheap cut-off test (integers on a 10-bit mirror, or the exact FP64 one), queues
+//   k_binary_build  walks the 9/27 neighbour cells in key_diff order (structs.jl:73-81) — as 3/9
+//                   contiguous runs of three cells in the zrun cell order — with a cheap cut-off
+//                   test (one packed add + DP4A on the 6-bit mirror, or the exact FP64 one), queues
 //                   the survivors per thread in shared memory, then — with the lanes of a warp
-//                   compacted onto ~26 survivors instead of ~157 candidates — runs the exact test
-//                   `r > sys.h` (core.jl:104-105) and the closure body, and streams the queue
-//                   to the list.
+//                   compacted onto ~28 survivors instead of ~157 candidates — runs the exact test
+//                   `r > sys.h` (core.jl:104-105) and the closure body, and writes the ACCEPTED
+//                   neighbours (the particle itself left out, core.jl:105 `p == q`) to the list.
 //   k_binary_list   replays a recorded list: exact test + closure body per entry.
 //
 // Both visit accepted neighbours in exactly the order of k_binary (pair_ops.cu), so every FP64
@@ -44,11 +45,29 @@ __device__ __forceinline__ void nl_walk(Op &op, const Fields &f, const Params &p
     }
 }
 
-// exact test + closure body for one recorded candidate (the particle itself is among them)
-template <int DIM, class Op>
+// what the recording pass does with an accepted neighbour before the closure body runs: append it
+// to the particle's list column (entries beyond the stride are dropped; the caller then marks the
+// particle NL_NONE).  The replaying pass records nothing.
+struct NlNoSink {
+    __device__ __forceinline__ void operator()(uint32_t) const {}
+};
+struct NlListSink {
+    uint32_t *row;
+    uint32_t left;
+    __device__ __forceinline__ void operator()(uint32_t q) {
+        if (left) {
+            __stcs(row, q);
+            row += 32;
+            --left;
+        }
+    }
+};
+
+// exact test + closure body for one recorded candidate
+template <int DIM, class Op, class Sink = NlNoSink>
 __device__ __forceinline__ void nl_entry(Op &op, const Fields &f, const Params &prm, const Grid &g,
                                          int64_t p, uint32_t q, double px, double py, double pz,
-                                         unsigned &accepted) {
+                                         unsigned &accepted, Sink &&sink = Sink()) {
     // dist(p,q) — core.jl:8-10, algebra.jl:49-60: left-to-right, no FMA
     double dx = px - f.s[S_X0][q];
     double dy = py - f.s[S_X1][q];
@@ -59,6 +78,7 @@ __device__ __forceinline__ void nl_entry(Op &op, const Fields &f, const Params &
         r2 = r2 + dz * dz;
     }
     if ((r2 > g.r2_max) || (q == (uint32_t)p)) return;  // core.jl:105, decided on r2 (Grid::r2_max)
+    sink(q);
     double r = sqrt(r2);
     op.template pair<DIM>(f, prm, p, q, dx, dy, dz, r);
     ++accepted;
@@ -66,10 +86,11 @@ __device__ __forceinline__ void nl_entry(Op &op, const Fields &f, const Params &
 
 // ---- packed-record variants (SPHMW_FLAG_PACKED_RECORDS; NbRec in sphmw_internal.h) ----------
 // density closure: position and mass of q from record A
-template <int DIM, class Op>
+template <int DIM, class Op, class Sink = NlNoSink>
 __device__ __forceinline__ void nl_entry_rec_density(Op &op, const Params &prm, const Grid &g, int64_t p,
                                                      uint32_t q, double px, double py, double pz,
-                                                     const NbRec *__restrict__ recA, unsigned &accepted) {
+                                                     const NbRec *__restrict__ recA, unsigned &accepted,
+                                                     Sink &&sink = Sink()) {
     const NbRec A = nb_load(recA + q);
     double dx = px - A.a;
     double dy = py - A.b;
@@ -80,6 +101,7 @@ __device__ __forceinline__ void nl_entry_rec_density(Op &op, const Params &prm, 
         r2 = r2 + dz * dz;
     }
     if ((r2 > g.r2_max) || (q == (uint32_t)p)) return;
+    sink(q);
     double r = sqrt(r2);
     op.template pair_q<DIM>(prm, RecAQ{A.d}, dx, dy, dz, r);
     ++accepted;
@@ -150,11 +172,33 @@ __device__ __forceinline__ void nl_count_pairs(unsigned long long *pair_counter,
 }
 
 // FILTER: how phase 1 tests a candidate — the exact FP64 test (three 8-byte loads), or integers
-// on the 10-bit cell-relative mirror (one 4-byte load; survivors get the exact test in phase 2).
-// An FP32 mirror of the absolute positions (float4, 16-byte loads) was measured slower:
-// profiles/r01b_pair_list.md.
+// on the 6-bit mirror of the zrun cell order (one 4-byte load, one add, one xor, one DP4A;
+// survivors get the exact test in phase 2).  Measured alternatives: a 10-bit-per-axis mirror tested
+// cell by cell (19.5 SASS instructions per candidate slot, 216 slots per particle: round 2 until the
+// zrun order) and an FP32 mirror of the absolute positions (slower still, profiles/r01b_pair_list.md).
 #define NL_FILTER_F64 0
-#define NL_FILTER_Q10 2
+#define NL_FILTER_Q6 3
+#define NL_QUEUE_SLACK 4  // queue rows beyond the list stride: room is checked once per four slots
+// one candidate run [b, e) of the 6-bit pre-test; false: the queue is full
+__device__ __forceinline__ bool nl_q6_run(const uint32_t *__restrict__ xq, uint32_t b, uint32_t e, uint32_t K,
+                                          unsigned &qtop, unsigned qlimit) {
+    if (b >= e) return true;
+    const uint32_t last = e - 1;
+    for (uint32_t q = b; q < e; q += 4) {
+        if (qtop > qlimit) return false;
+        const uint32_t *__restrict__ cp = xq + q;  // padded: slots past the run are masked
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = cp[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int s2 = nl_q6_dist2(K, w[i]);
+            const uint32_t qi = q + i;
+            nl_push(qtop, qi, !((s2 > NL_Q6_R2MAX) || (i > 0 && qi > last)));
+        }
+    }
+    return true;
+}
 // REC (fused density pass only): phase 2 reads q from record A, and the particle's own records B
 // and C are written once its density, smoothing length and pressure are final
 template <int DIM, class Op, int FILTER, bool REC = false>
@@ -162,7 +206,7 @@ __global__ void __launch_bounds__(NL_BLOCK)
 k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
                const uint32_t *__restrict__ cellx, const uint32_t *__restrict__ cell_start, int64_t n,
                int self, unsigned long long *pair_counter, ColFilter cf, PairList pl) {
-    extern __shared__ uint32_t nl_queue[];  // [stride][NL_BLOCK]: a private column per thread
+    extern __shared__ uint32_t nl_queue[];  // [stride + NL_QUEUE_SLACK][NL_BLOCK]: a private column per thread
     const int64_t p = blockIdx.x * (int64_t)NL_BLOCK + threadIdx.x;
     if (p >= n) return;
     const CellCoord home = cell_of(g, key[p], cellx[p]);
@@ -173,64 +217,42 @@ k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restr
     }
     const uint32_t stride = (uint32_t)pl.stride;
     const unsigned qbase = (unsigned)__cvta_generic_to_shared(nl_queue + threadIdx.x);
-    const unsigned qend = qbase + stride * (NL_BLOCK * 4u);
+    const unsigned qend = qbase + (stride + NL_QUEUE_SLACK) * (NL_BLOCK * 4u);
     unsigned qtop = qbase;
     const double px = f.s[S_X0][p], py = f.s[S_X1][p], pz = DIM == 3 ? f.s[S_X2][p] : 0.0;
     bool fits = true;
     // ---- phase 1: candidates -> queue -------------------------------------------------
-    if (FILTER == NL_FILTER_Q10) {
-        // own position in h/1024 inside the home cell, and the home cell's row coordinates: a
-        // neighbour cell reached without any wrap of the linear key arithmetic (core.jl:98 has no
-        // per-axis check) lies exactly (di, dj, dk) cells away; the few wrapped ones (cells on
-        // the faces of the grid) take the exact FP64 test instead
+    // A home cell that touches no face of the grid reaches its 9/27 neighbour cells without any
+    // wrap of the linear key arithmetic (core.jl:98 has no per-axis check), and in the zrun order
+    // the cells (di, dj, -1..1) are one contiguous run visited in exactly the reference's order:
+    // 3/9 runs, one constant per run.  Cells on a face (and FILTER_F64) go cell by cell with the
+    // exact FP64 test.
+    bool by_runs = false;
+    if (FILTER == NL_FILTER_Q6) {
+        const int lx = (int)g.lim[0], ly = (int)g.lim[1], lz = (int)g.lim[2];
+        by_runs = home.i >= 1 && home.i <= lx - 2 && home.j >= 1 && home.j <= ly - 2 &&
+                  (DIM == 2 || (home.k >= 1 && home.k <= lz - 2));
+    }
+    if (by_runs) {
         const uint32_t ow = pl.xq[p];
-        const int qx = (int)(ow & 1023u), qy = (int)((ow >> 10) & 1023u), qz = (int)(ow >> 20);
-        const int ly = (int)g.lim[1];
-        const int hj = home.rest % ly, hk = home.rest / ly;
-        for (int d = 0; d < g.ndiff; ++d) {
-            unsigned nk;
-            if (!neighbour_pkey(g, home, d, nk)) continue;
-            const uint32_t b = cell_start[nk], e = cell_start[nk + 1];
-            if (!nl_room(qtop, qend, e - b)) {
-                fits = false;
-                break;
-            }
-            const int di = g.nb_di[d], dj = g.nb_dj[d], dk = g.nb_dk[d];
-            const bool regular = (unsigned)(home.i + di) < (unsigned)g.lim[0] && (unsigned)(hj + dj) < (unsigned)ly &&
-                                 (unsigned)(hk + dk) < (unsigned)g.lim[2];
-            if (regular) {
-                int ox = qx - NL_Q10_ONE * di, oy = qy - NL_Q10_ONE * dj, oz = qz - NL_Q10_ONE * dk;
-                asm volatile("" : "+r"(ox), "+r"(oy), "+r"(oz));  // keep them out of the inner loop
-                const uint32_t last = e - 1;
-                for (uint32_t q = b; q < e; q += 4) {
-                    const uint32_t *__restrict__ cp = pl.xq + q;  // padded: slots past the run are masked
-                    uint32_t w[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) w[i] = cp[i];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int dx = ox - (int)(w[i] & 1023u);
-                        const int dy = oy - (int)((w[i] >> 10) & 1023u);
-                        int s2 = dx * dx + dy * dy;
-                        if (DIM == 3) {
-                            const int dz = oz - (int)(w[i] >> 20);
-                            s2 += dz * dz;
-                        }
-                        const uint32_t qi = q + i;
-                        nl_push(qtop, qi, !((s2 > NL_Q10_R2MAX) || (i > 0 && qi > last)));
+        const unsigned rows = (unsigned)g.rows, lz = (unsigned)g.lim[2];
+        const unsigned qlimit = qend - 4u * (NL_BLOCK * 4u);
+        // first cell of the run (-1, -1): one step back along the run axis (z in 3D, y in 2D)
+        const unsigned pk0 = pkey_ijk(g, home.i - 1, home.j - 1, DIM == 3 ? home.k - 1 : 0);
+        for (int di = -1; di <= 1 && fits; ++di) {
+            if (DIM == 3) {
+#pragma unroll 1
+                for (int dj = -1; dj <= 1; ++dj) {
+                    const unsigned rk = pk0 + (unsigned)(di + 1) * rows + (unsigned)(dj + 1) * lz;
+                    if (!nl_q6_run(pl.xq, cell_start[rk], cell_start[rk + 3], nl_q6_run_const(ow, di, dj), qtop, qlimit)) {
+                        fits = false;
+                        break;
                     }
                 }
             } else {
-                for (uint32_t q = b; q < e; ++q) {
-                    double dx = px - f.s[S_X0][q];
-                    double dy = py - f.s[S_X1][q];
-                    double r2 = dx * dx + dy * dy;
-                    if (DIM == 3) {
-                        double dz = pz - f.s[S_X2][q];
-                        r2 = r2 + dz * dz;
-                    }
-                    nl_push(qtop, q, !(r2 > g.r2_max));
-                }
+                const unsigned rk = pk0 + (unsigned)(di + 1) * rows;
+                if (!nl_q6_run(pl.xq, cell_start[rk], cell_start[rk + 3], nl_q6_run_const(ow, di, 0), qtop, qlimit))
+                    fits = false;
             }
         }
     } else {
@@ -254,20 +276,22 @@ k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restr
             }
         }
     }
-    // ---- phase 2: exact test + closure over the queue; queue -> list --------------------
+    // ---- phase 2: exact test + closure over the queue; accepted neighbours -> list -------
     Op op;
     op.template init<DIM>(f, prm, p);
     unsigned accepted = 0;
     if (fits) {
-        uint32_t *row = pl.list + ((size_t)(p >> 5) * stride) * 32 + (size_t)(p & 31);
-        for (unsigned a = qbase; a < qtop; a += NL_BLOCK * 4u, row += 32) {
+        NlListSink sink{pl.list + ((size_t)(p >> 5) * stride) * 32 + (size_t)(p & 31), stride};
+        for (unsigned a = qbase; a < qtop; a += NL_BLOCK * 4u) {
             const uint32_t q = nl_peek(a);
-            __stcs(row, q);
             if constexpr (REC && Op::REC_KIND == 1)
-                nl_entry_rec_density<DIM>(op, prm, g, p, q, px, py, pz, pl.recA, accepted);
-            else nl_entry<DIM>(op, f, prm, g, p, q, px, py, pz, accepted);
+                nl_entry_rec_density<DIM>(op, prm, g, p, q, px, py, pz, pl.recA, accepted, sink);
+            else nl_entry<DIM>(op, f, prm, g, p, q, px, py, pz, accepted, sink);
         }
-        pl.cnt[p] = (qtop - qbase) / (NL_BLOCK * 4u);
+        // more accepted neighbours than the list holds: this pass is complete (the closure saw
+        // them all), later passes walk the cells for this particle
+        if (accepted > stride) atomicAdd(pl.overflow, 1ull);
+        pl.cnt[p] = accepted > stride ? NL_NONE : accepted;
     } else {
         pl.cnt[p] = NL_NONE;
         atomicAdd(pl.overflow, 1ull);

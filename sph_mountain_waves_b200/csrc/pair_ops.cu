@@ -273,7 +273,7 @@ static int ensure_pair_list(sphmw_ctx *c) {
     int stride = c->grid.dim == 3 ? 40 : 32;
     if (const char *e = getenv("SPHMW_PAIR_LIST_STRIDE")) stride = atoi(e);
     if (stride < 4) stride = 4;
-    if (stride > 96) stride = 96;  // 48 KB of queue per block
+    if (stride > 92) stride = 92;  // (stride + NL_QUEUE_SLACK) rows: 48 KB of queue per block
     const size_t warps = (size_t)((c->cap + 31) / 32);
     uint32_t *list = nullptr, *cnt = nullptr;
     if (cudaMalloc(&list, sizeof(uint32_t) * warps * (size_t)stride * 32) != cudaSuccess ||
@@ -348,30 +348,30 @@ static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Field
             k_binary_list<3, Op><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
     } else if (record) {
         c->pl.xq = c->xq;
-        // pre-test of the recording pass: integers on the 10-bit cell-relative mirror, or
-        // (SPHMW_FLAG_NO_PRETEST) the exact FP64 test only
-        const bool q10 = !(c->flags & SPHMW_FLAG_NO_PRETEST);
-        const size_t smem = sizeof(uint32_t) * (size_t)c->pl.stride * NL_BLOCK;
+        // pre-test of the recording pass: integers on the 6-bit mirror of the zrun cell order, or
+        // (SPHMW_FLAG_NO_PRETEST, x-chunked cell order) the exact FP64 test only
+        const bool q6 = c->grid.zrun && !(c->flags & SPHMW_FLAG_NO_PRETEST);
+        const size_t smem = sizeof(uint32_t) * (size_t)(c->pl.stride + NL_QUEUE_SLACK) * NL_BLOCK;
         TIMED(c, name);
         c->pl_gen = c->cell_gen;
         c->pl_format = 0;
         c->pl_builds += 1;
         if constexpr (REC) {
-            if (rec) {
+            if (rec && q6) {
                 if (c->grid.dim == 2)
-                    k_binary_build<2, Op, NL_FILTER_Q10, true><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+                    k_binary_build<2, Op, NL_FILTER_Q6, true><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
                 else
-                    k_binary_build<3, Op, NL_FILTER_Q10, true><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+                    k_binary_build<3, Op, NL_FILTER_Q6, true><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
                 if (Op::REC_KIND == 1) c->rec_bc_gen = c->cell_gen;
                 CUDA_TRY(cudaGetLastError());
                 return SPHMW_OK;
             }
         }
         if (c->grid.dim == 2) {
-            if (q10) k_binary_build<2, Op, NL_FILTER_Q10><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+            if (q6) k_binary_build<2, Op, NL_FILTER_Q6><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
             else k_binary_build<2, Op, NL_FILTER_F64><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
         } else {
-            if (q10) k_binary_build<3, Op, NL_FILTER_Q10><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
+            if (q6) k_binary_build<3, Op, NL_FILTER_Q6><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
             else k_binary_build<3, Op, NL_FILTER_F64><<<blocks, NL_BLOCK, smem, c->stream>>>(NL_ARGS, c->pl);
         }
     } else {

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <string>
 #include <vector>
@@ -76,39 +78,72 @@ struct Grid {
     int nb_drest[27];
     int nb_dj[27];  // the row part split into its y and z offsets (nb_drest = dj + Ly*dk)
     int nb_dk[27];
+    // zrun (the default): cells stored x-outermost with the INNERMOST axis of the
+    // reference's key_diff loops fastest — z in 3D, y in 2D (structs.jl:73-81: `for di, dj, dk`,
+    // the last one runs fastest): pkey = i*rows + j*Lz + k.  The three cells (di, dj, -1..1) are
+    // then one contiguous run of memory whose order IS the reference's visiting order, so a pair
+    // pass walks 9 (3 in 2D) runs instead of 27 (9) cells, and a y-z plane of cells (a few MB)
+    // stays in L2.  zrun == 0: the x-chunked order above, kept for the shared-memory variants
+    // (SPHMW_FLAG_TILES, SPHMW_FLAG_CELL_PAIRS) that stage x-rows.
+    int zrun;
 };
 
 #if defined(__CUDACC__) || defined(SPHMW_EMU)
 // 32-bit cell arithmetic (all quantities < 2^31: sphmw_create checks pkey_max)
 struct CellCoord {
-    int i, rest;
+    int i, rest;  // column, and the row part j + Ly*k of the reference key (structs.jl:102)
+    int j, k;
 };
-__host__ __device__ __forceinline__ unsigned pkey_of(const Grid &g, int i, int rest) {
-    return ((((unsigned)(i >> g.cx_shift) * (unsigned)g.rows) + (unsigned)rest) << g.cx_shift) +
+__host__ __device__ __forceinline__ unsigned pkey_ijk(const Grid &g, int i, int j, int k) {
+    if (g.zrun) return (unsigned)i * (unsigned)g.rows + (unsigned)j * (unsigned)g.lim[2] + (unsigned)k;
+    const unsigned rest = (unsigned)j + (unsigned)g.lim[1] * (unsigned)k;
+    return ((((unsigned)(i >> g.cx_shift) * (unsigned)g.rows) + rest) << g.cx_shift) +
            ((unsigned)i & ((1u << g.cx_shift) - 1u));
+}
+__host__ __device__ __forceinline__ unsigned pkey_of(const Grid &g, int i, int rest) {
+    const int ly = (int)g.lim[1];
+    return pkey_ijk(g, i, rest % ly, rest / ly);
 }
 // column i is stored per particle (cellx), the row part follows from the physical key
 __host__ __device__ __forceinline__ CellCoord cell_of(const Grid &g, unsigned pk, unsigned i) {
     CellCoord c;
     c.i = (int)i;
-    c.rest = (int)((pk >> g.cx_shift) - (i >> g.cx_shift) * (unsigned)g.rows);
+    if (g.zrun) {
+        const unsigned pr = pk - i * (unsigned)g.rows;
+        c.j = (int)(pr / (unsigned)g.lim[2]);
+        c.k = (int)(pr - (unsigned)c.j * (unsigned)g.lim[2]);
+        c.rest = c.j + (int)g.lim[1] * c.k;
+    } else {
+        c.rest = (int)((pk >> g.cx_shift) - (i >> g.cx_shift) * (unsigned)g.rows);
+        c.k = c.rest / (int)g.lim[1];
+        c.j = c.rest - c.k * (int)g.lim[1];
+    }
     return c;
 }
 // neighbour cell number d of the reference's key_diff table (structs.jl:73-81).  The
 // reference only checks 1 <= key + dkey <= key_max (core.jl:98), so a column overflow wraps
-// into the adjacent row exactly as the linear key arithmetic does.
+// into the adjacent row (and a row overflow into the adjacent plane) exactly as the linear key
+// arithmetic does.
 __device__ __forceinline__ bool neighbour_pkey(const Grid &g, const CellCoord &c, int d, unsigned &pk) {
-    int i = c.i + g.nb_di[d], rest = c.rest + g.nb_drest[d];
-    const int lx = (int)g.lim[0];
+    int i = c.i + g.nb_di[d], j = c.j + g.nb_dj[d], k = c.k + g.nb_dk[d];
+    const int lx = (int)g.lim[0], ly = (int)g.lim[1];
     if (i < 0) {
         i += lx;
-        rest -= 1;
+        j -= 1;
     } else if (i >= lx) {
         i -= lx;
-        rest += 1;
+        j += 1;
     }
-    if (rest < 0 || rest >= (int)g.rows) return false;
-    pk = pkey_of(g, i, rest);
+    while (j < 0) {
+        j += ly;
+        k -= 1;
+    }
+    while (j >= ly) {
+        j -= ly;
+        k += 1;
+    }
+    if (k < 0 || k >= (int)g.lim[2]) return false;  // <=> key + dkey outside 1..key_max
+    pk = pkey_ijk(g, i, j, k);
     return true;
 }
 #endif
@@ -173,6 +208,54 @@ NL_HD bool nl_q10_pass(uint32_t own, uint32_t other, int di, int dj, int dk, int
         s2 += dz * dz;
     }
     return !(s2 > NL_Q10_R2MAX);
+}
+// ---- 6-bit mirror of the zrun cell order: one packed subtract and one DP4A per candidate --------
+// Word of a particle: byte 0 = x inside its cell in h/64 (0..63), byte 1 = y likewise (3D only),
+// byte 2 = 0, byte 3 = the run axis (z in 3D, y in 2D) ABSOLUTE modulo four cells:
+// (cell & 3) << 6 | fraction.  For a candidate q in the run (di, dj, -1..1) of p's cell:
+//     t = word(q) + K,   K = 0x80808080 + 64*di + (64*dj << 8) - word(p)      (one 32-bit add)
+// has in bytes 0/1 the x/y difference in h/64 biased by 128 — never a carry: 0x80 + 64*d - p_b is in
+// [1, 192] and q_b < 64 — in byte 2 the bias alone, and in byte 3 the run-axis difference modulo
+// 256, exact as a signed byte because two cells are 128 units (carries out of byte 3 leave the
+// word).  t ^ 0x80808080 turns the biased bytes into signed ones and DP4A of that word with itself
+// is the squared distance in (h/64)^2.  Conservative for the same reason as above: positions are
+// cell + (q + e)/64 with e in [0,1), so |d_a| < |t_a| + 1 and sum d_a^2 < (64 + sqrt(3))^2 whenever
+// r <= h.  All |d_a| <= 127 fit a signed byte.
+#define NL_Q6_ONE 64
+#define NL_Q6_R2MAX 4321  // floor((64 + 1.74)^2)
+#define NL_Q6_BIAS 0x80808080u
+NL_HD uint32_t nl_q6_axis(double x, double h) {
+    const double t = x / h;
+    const double fr = t - floor(t);
+    int q = (int)(fr * (double)NL_Q6_ONE);
+    q = q < 0 ? 0 : (q > NL_Q6_ONE - 1 ? NL_Q6_ONE - 1 : q);
+    return (uint32_t)q;
+}
+// run-axis byte: cell index (floor(x/h) - phase, as k_keys computes it) modulo 4, and the fraction
+NL_HD uint32_t nl_q6_run_axis(double x, double h, long long phase) {
+    const long long cell = (long long)floor(x / h) - phase;
+    return ((uint32_t)(cell & 3) << 6) | nl_q6_axis(x, h);
+}
+NL_HD uint32_t nl_q6_word(double x, double y, double z, double h, long long run_phase, int dim) {
+    if (dim == 3) return nl_q6_axis(x, h) | (nl_q6_axis(y, h) << 8) | (nl_q6_run_axis(z, h, run_phase) << 24);
+    return nl_q6_axis(x, h) | (nl_q6_run_axis(y, h, run_phase) << 24);
+}
+// K of a run: (di, dj) = the run's cell column minus p's (dj = 0 in 2D, where y is the run axis)
+NL_HD uint32_t nl_q6_run_const(uint32_t own, int di, int dj) {
+    return NL_Q6_BIAS + (uint32_t)(NL_Q6_ONE * di) + (uint32_t)(NL_Q6_ONE * dj * 256) - own;
+}
+NL_HD int nl_q6_dist2(uint32_t K, uint32_t other) {
+    const uint32_t s = (other + K) ^ NL_Q6_BIAS;
+#if defined(__CUDA_ARCH__)
+    return __dp4a((int)s, (int)s, 0);
+#else
+    int acc = 0;
+    for (int b = 0; b < 4; ++b) {
+        const int v = (int)(int8_t)(s >> (8 * b));
+        acc += v * v;
+    }
+    return acc;
+#endif
 }
 // Packed neighbour records (SPHMW_FLAG_PACKED_RECORDS): what a replayed list entry needs from its
 // neighbour, as three 32-byte records read with one 256-bit load each instead of eleven 8-byte
@@ -260,7 +343,8 @@ struct sphmw_ctx {
     uint32_t *cellx = nullptr, *cellx_alt = nullptr;  // cell column i of each position
     uint32_t *rank = nullptr;        // arrival rank inside the cell
     uint32_t *src = nullptr;         // new position -> old position
-    uint32_t *cell_start = nullptr;  // key_max + 2 entries
+    uint32_t *cell_start = nullptr;  // cells_cap + 2 entries
+    int64_t cells_cap = 0;           // pkey_max of the larger of the two physical cell orders
     uint32_t *scan_tmp = nullptr;
     int64_t scan_tmp_len = 0;
     uint32_t *removed = nullptr;     // [0] = count, [1..] = removed reference indices
@@ -320,6 +404,14 @@ static inline bool sphmw_use_records(const sphmw_ctx *c) {
     return c->grid.dim == 3 || (c->flags & SPHMW_FLAG_PACKED_RECORDS);
 }
 
+// which physical cell order a set of flags runs on (Grid::zrun): the shared-memory variants stage
+// x-rows of cells and keep the x-chunked order; SPHMW_CELL_ORDER=xchunk forces it (A/B runs)
+static inline bool sphmw_want_zrun(int flags) {
+    if (flags & (SPHMW_FLAG_CELL_PAIRS | SPHMW_FLAG_TILES)) return false;
+    const char *e = getenv("SPHMW_CELL_ORDER");
+    return !(e && !strcmp(e, "xchunk"));
+}
+
 // error plumbing -----------------------------------------------------------
 void sphmw_set_error(const char *fmt, ...);
 #define CUDA_TRY(expr)                                                              \
@@ -348,6 +440,7 @@ const FieldDesc *sphmw_find_field(const char *name);
 void sphmw_derive_params(Params &p);
 int sphmw_grid_setup(Grid &g, const double box_min[3], const double box_max[3], double h, int64_t slab_lo,
                      int64_t slab_hi, int64_t *global_cols);
+void sphmw_grid_set_order(Grid &g, bool zrun);  // physical cell order (Grid::zrun)
 // implemented in cell_list.cu
 int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive);
 int sphmw_ensure_slot(sphmw_ctx *c, int slot);

@@ -25,7 +25,7 @@
 #include "sphmw_internal.h"
 
 uint3 threadIdx, blockIdx, blockDim;
-uint32_t nl_queue[96 * NL_BLOCK];
+uint32_t nl_queue[(96 + NL_QUEUE_SLACK) * NL_BLOCK];
 
 void sphmw_set_error(const char *fmt, ...) {
     va_list ap;
@@ -86,7 +86,7 @@ struct System {
                 fprintf(stderr, "emu_ops: particle %lld is outside the box (removal is not emulated)\n", (long long)i);
                 return 3;
             }
-            pkey[i] = pkey_of(g, (int)ci, (int)(cj + g.lim[1] * ck));
+            pkey[i] = pkey_ijk(g, (int)ci, (int)cj, (int)ck);
             col[i] = (uint32_t)ci;
         }
         std::iota(order.begin(), order.end(), 0u);
@@ -115,6 +115,9 @@ struct System {
             ++gl.count;
         }
         gl.h = g.h;
+        gl.q6 = g.zrun;
+        gl.dim = dim;
+        gl.run_phase = g.phase[dim == 3 ? 2 : 1];
         gl.xq = xq.data();
         gl.recA = recA.data();
         launch(n, [&] {
@@ -154,8 +157,8 @@ struct System {
         if (list_built) {  // replay
             launch(n, [&] { k_binary_list<DIM, Op>(f, f, prm, g, k, cx, cs, n, self, &counters[0], cf, pl); });
         } else if (generation % 3 != 0) {  // record (integer or FP64 pre-test)
-            if (generation % 3 == 1)
-                launch(n, [&] { k_binary_build<DIM, Op, NL_FILTER_Q10>(f, f, prm, g, k, cx, cs, n, self, &counters[0], cf, pl); });
+            if (generation % 3 == 1 && g.zrun)  // the 6-bit pre-test needs the zrun cell order
+                launch(n, [&] { k_binary_build<DIM, Op, NL_FILTER_Q6>(f, f, prm, g, k, cx, cs, n, self, &counters[0], cf, pl); });
             else
                 launch(n, [&] { k_binary_build<DIM, Op, NL_FILTER_F64>(f, f, prm, g, k, cx, cs, n, self, &counters[0], cf, pl); });
             list_built = true;
@@ -221,7 +224,10 @@ int main(int argc, char **argv) {
     System sys;
     sys.n = n;
     sys.stride = head[0];
-    if (head[1] >= 0) setenv("SPHMW_CX_SHIFT", std::to_string(head[1]).c_str(), 1);
+    if (head[1] >= 0) {  // x-chunked cell order with this chunk width; default: the zrun order
+        setenv("SPHMW_CX_SHIFT", std::to_string(head[1]).c_str(), 1);
+        setenv("SPHMW_CELL_ORDER", "xchunk", 1);
+    }
     memset(&sys.prm, 0, sizeof(Params));
     struct Named {
         const char *name;

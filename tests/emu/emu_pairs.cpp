@@ -33,7 +33,7 @@
 #include "wcsph_ops.cuh"
 
 uint3 threadIdx, blockIdx, blockDim;
-uint32_t nl_queue[96 * NL_BLOCK];
+uint32_t nl_queue[(96 + NL_QUEUE_SLACK) * NL_BLOCK];
 // the tiled kernels' shared window (pair_tile.cuh) and the sync-point bookkeeping of their emulation
 alignas(16) unsigned char emu_tile_smem[256 * 1024];
 int emu_phase = 0, emu_sync_seen = 0;
@@ -116,6 +116,8 @@ struct Result {
     std::vector<uint32_t> column;  // cell column of every particle (reference index order)
     unsigned long long pairs_density = 0, pairs_force = 0, overflow = 0;
     long long tiled_blocks = 0, blocks = 0;  // tiles variants: blocks with a staged tile
+    unsigned long long list_entries = 0;     // list variants: entries recorded (particles with a list)
+    unsigned long long listed_pairs = 0;     // ... and the accepted pairs of those particles
     bool same_as(const Result &o) const {
         for (int k = 0; k < 9; ++k)
             if (memcmp(fields[k].data(), o.fields[k].data(), sizeof(double) * fields[k].size())) return false;
@@ -125,7 +127,10 @@ struct Result {
     }
 };
 
-enum Variant { WALK, LIST_Q10, LIST_F64, RECORDS, TILES, SLAB_LIST, SLAB_RECORDS, SLAB_TILES };
+enum Variant { WALK, LIST_Q6, LIST_F64, RECORDS, TILES, SLAB_LIST, SLAB_RECORDS, SLAB_TILES };
+// the shared-memory tiles stage x-rows of cells and run on the x-chunked cell order (with its 10-bit
+// mirror); everything else runs on the zrun order (6-bit mirror)
+static bool needs_xchunk(Variant v) { return v == TILES || v == SLAB_TILES; }
 
 template <int DIM, class DensityOp, class ForceOp>
 static Result run_variant(State st, const Grid &g, const Params &prm, Variant v, int stride) {
@@ -150,14 +155,14 @@ static Result run_variant(State st, const Grid &g, const Params &prm, Variant v,
     if (v == WALK) {
         launch(n, [&] { walk_thread<DIM, DensityOp>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, &counters[0]); });
         launch(n, [&] { walk_thread<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, &counters[1]); });
-    } else if (v == LIST_Q10) {
-        launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q10>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cf, pl); });
+    } else if (v == LIST_Q6) {
+        launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q6>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cf, pl); });
         launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cf, pl); });
     } else if (v == LIST_F64) {
         launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_F64>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cf, pl); });
         launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cf, pl); });
     } else if (v == RECORDS) {
-        launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q10, true>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cf, pl); });
+        launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q6, true>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cf, pl); });
         launch(n, [&] { k_binary_list<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cf, pl); });
     } else if (v == TILES) {
         for (size_t b = 0; b * TM_WORDS < st.tile_tab.size(); ++b) {
@@ -176,7 +181,7 @@ static Result run_variant(State st, const Grid &g, const Params &prm, Variant v,
         const ColFilter cd{1, 1, W - 2, 1, 0, 1};
         const ColFilter cedge{1, 2, 3, W - 4, W - 3, 1}, cint{1, 4, W - 5, 1, 0, 0};
         if (v == SLAB_LIST) {
-            launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q10>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cd, pl); });
+            launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q6>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cd, pl); });
             launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge, pl); });
             launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[3], cint, pl); });
         } else if (v == SLAB_TILES) {
@@ -184,13 +189,16 @@ static Result run_variant(State st, const Grid &g, const Params &prm, Variant v,
             launch_tiled(n, [&] { k_tile_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge, pl, tab); });
             launch_tiled(n, [&] { k_tile_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[3], cint, pl, tab); });
         } else {
-            launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q10, true>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cd, pl); });
+            launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q6, true>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cd, pl); });
             launch(n, [&] { k_binary_list<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge, pl); });
             launch(n, [&] { k_binary_list<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[3], cint, pl); });
         }
     }
     r.pairs_density = counters[0];
     r.pairs_force = counters[1];
+    if (v == LIST_Q6 || v == LIST_F64 || v == RECORDS)
+        for (int64_t p = 0; p < n; ++p)
+            if (st.cnt[p] != NL_NONE) r.list_entries += st.cnt[p];
     r.overflow = counters[2];
     // back to reference index order
     for (int k = 0; k < 9; ++k) {
@@ -235,7 +243,7 @@ int main(int argc, char **argv) {
     read_exact(fp, &n, sizeof(n));
     read_exact(fp, box, sizeof(box));
     const int fast = head[0], stride = head[1], nparams = head[3], nsteps = head[4];
-    if (head[2] >= 0) setenv("SPHMW_CX_SHIFT", std::to_string(head[2]).c_str(), 1);
+    if (head[2] >= 0) setenv("SPHMW_CX_SHIFT", std::to_string(head[2]).c_str(), 1);  // chunk width of the x-chunked order
     Params prm;
     memset(&prm, 0, sizeof(prm));
     struct Named {
@@ -258,10 +266,13 @@ int main(int argc, char **argv) {
             if (!strcmp(t.name, name)) prm.*(t.field) = value;
     }
     sphmw_derive_params(prm);
-    Grid g;
+    Grid g;  // zrun cell order (the library default); gx: the same grid in the x-chunked order
     memset(&g, 0, sizeof(g));
     int64_t global_cols = 0;
     if (sphmw_grid_setup(g, box, box + 3, box[6], -1, -1, &global_cols) != SPHMW_OK) return 3;
+    sphmw_grid_set_order(g, true);
+    Grid gx = g;
+    sphmw_grid_set_order(gx, false);
     const int dim = g.dim;
 
     // fields in reference index order, component-major
@@ -274,7 +285,7 @@ int main(int argc, char **argv) {
     fclose(fp);
 
     // ---- cell list: keys (structs.jl:97-106), order (cell ascending, index descending) --------
-    auto build_state = [&](State &st) -> int {
+    auto build_state = [&](State &st, const Grid &g) -> int {
     std::vector<uint32_t> pkey(n), col(n), order(n);
     for (int64_t i = 0; i < n; ++i) {
         const long long ci = (long long)floor(in[0][i] / g.h) - g.phase[0];
@@ -284,7 +295,7 @@ int main(int argc, char **argv) {
             fprintf(stderr, "emu_pairs: particle %lld is outside the box (not supported here)\n", (long long)i);
             return 3;
         }
-        pkey[i] = pkey_of(g, (int)ci, (int)(cj + g.lim[1] * ck));
+        pkey[i] = pkey_ijk(g, (int)ci, (int)cj, (int)ck);
         col[i] = (uint32_t)ci;
     }
     std::iota(order.begin(), order.end(), 0u);
@@ -322,6 +333,9 @@ int main(int argc, char **argv) {
             ++gl.count;
         }
         gl.h = g.h;
+        gl.q6 = g.zrun;
+        gl.dim = dim;
+        gl.run_phase = g.phase[dim == 3 ? 2 : 1];
         gl.xq = st.xq.data();
         gl.recA = st.rec[0].data();
         launch(n, [&] {
@@ -342,21 +356,22 @@ int main(int argc, char **argv) {
     // the tile map of this cell list (csrc/tile_map.cuh), one record per block
     const int64_t nblocks = (n + TM_BLOCK - 1) / TM_BLOCK;
     st.tile_tab.assign((size_t)nblocks * TM_WORDS, 0u);
-    for (int64_t b = 0; b < nblocks; ++b)
+    for (int64_t b = 0; b < nblocks && !g.zrun; ++b)  // tiles: x-chunked order only
         tm_build_record(g, st.key.data(), st.cellx.data(), st.cell_start.data(), n, b, st.tile_tab.data() + (size_t)b * TM_WORDS);
     return 0;
     };
-    State st;
-    if (build_state(st)) return 3;
+    State st, stx;
+    if (build_state(st, g) || build_state(stx, gx)) return 3;
 
     // ---- the variants --------------------------------------------------------------------------
-    auto run = [&](Variant v) -> Result {
+    auto run_on = [&](Variant v, const State &s, const Grid &gg) -> Result {
         if (dim == 2)
-            return fast ? run_variant<2, B_wcsph_density_fast, B_wcsph_momentum_fast>(st, g, prm, v, stride)
-                        : run_variant<2, B_wcsph_density_fused, B_wcsph_momentum_fused>(st, g, prm, v, stride);
-        return fast ? run_variant<3, B_wcsph_density_fast, B_wcsph_momentum_fast>(st, g, prm, v, stride)
-                    : run_variant<3, B_wcsph_density_fused, B_wcsph_momentum_fused>(st, g, prm, v, stride);
+            return fast ? run_variant<2, B_wcsph_density_fast, B_wcsph_momentum_fast>(s, gg, prm, v, stride)
+                        : run_variant<2, B_wcsph_density_fused, B_wcsph_momentum_fused>(s, gg, prm, v, stride);
+        return fast ? run_variant<3, B_wcsph_density_fast, B_wcsph_momentum_fast>(s, gg, prm, v, stride)
+                    : run_variant<3, B_wcsph_density_fused, B_wcsph_momentum_fused>(s, gg, prm, v, stride);
     };
+    auto run = [&](Variant v) -> Result { return needs_xchunk(v) ? run_on(v, stx, gx) : run_on(v, st, g); };
     if (nsteps > 0) {
         // master copy stays in reference index order; kick and drift are per-particle
         Fields master{};
@@ -375,7 +390,8 @@ int main(int argc, char **argv) {
                 }
             });
             st = State();
-            if (build_state(st)) return 3;
+            stx = State();
+            if (build_state(st, g) || build_state(stx, gx)) return 3;
             const Result r = run((Variant)(step % 5));
             pairs = r.pairs_force;
             for (int64_t i = 0; i < n; ++i) {
@@ -390,7 +406,7 @@ int main(int argc, char **argv) {
             perror(argv[2]);
             return 2;
         }
-        const int64_t meta[6] = {n, dim, (int64_t)pairs, (int64_t)pairs, 0, g.cx_shift};
+        const int64_t meta[6] = {n, dim, (int64_t)pairs, (int64_t)pairs, 0, gx.cx_shift};
         fwrite(meta, sizeof(meta), 1, out);
         for (int k : {8, 9, 9, 7, 9, 9, 9}) fwrite(in[k].data(), sizeof(double), n, out);  // rho, -, -, h, -, -, -
         for (int k = 0; k < 3; ++k) fwrite(in[3 + k].data(), sizeof(double), n, out);       // v
@@ -400,10 +416,22 @@ int main(int argc, char **argv) {
         return 0;
     }
     const Result base = run(WALK);
+    if (!run_on(WALK, stx, gx).same_as(base)) {
+        fprintf(stderr, "emu_pairs: the cell walk depends on the physical cell order\n");
+        return 1;
+    }
+    {
+        // the x-chunked order records with the FP64 test (no 6-bit mirror there)
+        const Result r = run_on(LIST_F64, stx, gx);
+        if (!r.same_as(base)) {
+            fprintf(stderr, "emu_pairs: list_f64 on the x-chunked order differs from the cell walk\n");
+            return 1;
+        }
+    }
     static const char *NAMES[] = {"walk", "list", "list_f64", "records", "tiles", "slab_list", "slab_records", "slab_tiles"};
     unsigned long long overflow = 0;
     long long tiled_blocks = 0, blocks = 0;
-    for (Variant v : {LIST_Q10, LIST_F64, RECORDS, TILES}) {
+    for (Variant v : {LIST_Q6, LIST_F64, RECORDS, TILES}) {
         const Result r = run(v);
         if (v == TILES) tiled_blocks = r.tiled_blocks, blocks = r.blocks;
         if (!r.same_as(base)) {
@@ -412,6 +440,12 @@ int main(int argc, char **argv) {
             return 1;
         }
         overflow = std::max(overflow, r.overflow);
+        // the list holds the accepted neighbours and nothing else (no self entry, no false accepts)
+        if (v != TILES && r.overflow == 0 && r.list_entries != base.pairs_density) {
+            fprintf(stderr, "emu_pairs: variant '%s' recorded %llu list entries for %llu accepted pairs\n", NAMES[v],
+                    r.list_entries, base.pairs_density);
+            return 1;
+        }
     }
     if (g.lim[0] >= 10) {
         const int W = (int)g.lim[0];
@@ -441,13 +475,13 @@ int main(int argc, char **argv) {
         return 2;
     }
     const int64_t meta[6] = {n, dim, (int64_t)base.pairs_density, (int64_t)base.pairs_force, (int64_t)overflow,
-                             g.cx_shift};
+                             gx.cx_shift};
     fwrite(meta, sizeof(meta), 1, out);
     for (int k = 0; k < 7; ++k) fwrite(base.fields[k].data(), sizeof(double), n, out);  // rho .. P
     for (int k = 0; k < 3; ++k) fwrite(base.vnew[k].data(), sizeof(double), n, out);
     fclose(out);
     printf("emu_pairs: n=%lld dim=%d pairs=%llu overflow=%llu cx_shift=%d tiled=%lld/%lld: walk == list == list_f64 =="
            " records == tiles (== slab-filtered launches on their columns)\n",
-           (long long)n, dim, base.pairs_force, overflow, g.cx_shift, tiled_blocks, blocks);
+           (long long)n, dim, base.pairs_force, overflow, gx.cx_shift, tiled_blocks, blocks);
     return 0;
 }

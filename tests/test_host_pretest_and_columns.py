@@ -1,7 +1,8 @@
 """Host-only checks (no GPU) of two pieces of logic the device kernels rely on:
 
-* the integer pre-test of the pair-list recording pass (csrc/sphmw_internal.h nl_q10_*): it may
-  let false candidates through — the exact FP64 test `r > sys.h` (src/core.jl:104-105) follows —
+* the integer pre-tests of the pair-list recording pass (csrc/sphmw_internal.h: nl_q6_*, one packed
+  add + DP4A on the 6-bit mirror of the default cell order; nl_q10_*, the 10-bit mirror of the
+  shared-memory tile variant): they may let false candidates through — the exact FP64 test `r > sys.h` (src/core.jl:104-105) follows —
   but it must never reject a pair the reference accepts;
 * the column sets of the overlapped slab step (csrc/pair_ops.cu sphmw_slab_cols_of): edge and
   interior columns partition the local grid, the force sets are their owned parts.
@@ -19,11 +20,12 @@ from sph_mountain_waves_b200 import _capi
 GHOST = 2
 
 
-def pretest(xp, xq, h, dim):
+def pretest(xp, xq, h, dim, bits=10):
     xp = np.ascontiguousarray(xp, dtype=np.float64)
     xq = np.ascontiguousarray(xq, dtype=np.float64)
     out = np.empty(len(xp), dtype=np.uint8)
-    rc = _capi.lib().sphmw_pretest_pairs(_capi.ptr(xp), _capi.ptr(xq), len(xp), float(h), dim, _capi.ptr(out))
+    fn = _capi.lib().sphmw_pretest_pairs_q6 if bits == 6 else _capi.lib().sphmw_pretest_pairs
+    rc = fn(_capi.ptr(xp), _capi.ptr(xq), len(xp), float(h), dim, _capi.ptr(out))
     assert rc == 0
     return out
 
@@ -47,9 +49,10 @@ def r2_max(h):
     return t
 
 
+@pytest.mark.parametrize("bits", [6, 10])
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("h,origin", [(1.0, 0.0), (390.0, -2.0e5), (0.0317, 11.0), (2925.0, 3.9e5), (1e-3, -7.0)])
-def test_pretest_never_rejects_an_accepted_pair(dim, h, origin):
+def test_pretest_never_rejects_an_accepted_pair(dim, h, origin, bits):
     rng = np.random.default_rng(int(abs(origin)) + dim)
     n = 400_000
     xp = np.zeros((n, 3))
@@ -67,14 +70,16 @@ def test_pretest_never_rejects_an_accepted_pair(dim, h, origin):
     xq[np.arange(n // 4), axis] += h * np.where(rng.random(n // 4) < 0.5, 1.0, -1.0)
     accepted = ~(r2_left_to_right(xp, xq, dim) > r2_max(h))
     assert accepted.sum() > n // 3
-    got = pretest(xp, xq, h, dim)
+    got = pretest(xp, xq, h, dim, bits)
     # an accepted partner is always in one of the 27 cells, and always passes
     assert not np.any(got[accepted] == 2)
     assert np.all(got[accepted] == 1), f"{int(np.sum(got[accepted] == 0))} accepted pairs rejected by the pre-test"
 
 
-def test_pretest_is_tight():
-    """false candidates are confined to a thin shell: beyond (1 + 4/1024) h everything is rejected"""
+@pytest.mark.parametrize("bits,unit", [(6, 64.0), (10, 1024.0)])
+def test_pretest_is_tight(bits, unit):
+    """false candidates are confined to a thin shell: beyond (1 + 4/unit) h everything is rejected
+    (unit = quantisation steps per cell: h/64 or h/1024)"""
     rng = np.random.default_rng(5)
     n, h = 300_000, 2.5
     xp = rng.uniform(-100.0, 100.0, (n, 3))
@@ -82,11 +87,11 @@ def test_pretest_is_tight():
     u /= np.linalg.norm(u, axis=1)[:, None]
     r = rng.uniform(1.0, 1.5, n) * h
     xq = xp + u * r[:, None]
-    got = pretest(xp, xq, h, 3)
-    far = r > (1.0 + 4.0 / 1024.0) * h
+    got = pretest(xp, xq, h, 3, bits)
+    far = r > (1.0 + 4.0 / unit) * h
     assert not np.any(got[far] == 1)
     shell = (got == 1) & (r > h)
-    assert shell.sum() > 0 and np.max(r[shell]) < (1.0 + 4.0 / 1024.0) * h
+    assert shell.sum() > 0 and np.max(r[shell]) < (1.0 + 4.0 / unit) * h
 
 
 def column_sets(width, has_left, has_right):
