@@ -243,6 +243,22 @@ __global__ void k_renumber(uint32_t *__restrict__ idx, const uint32_t *__restric
     if (t < m) idx[pos_of_idx[mv_old[t]]] = mv_new[t];
 }
 
+// reference index -> physical position.  Only the removal renumbering, the inflow spawn and the pair
+// dump need it, so the cell-list build no longer writes it (a scattered 4-byte store per particle
+// per step): it is rebuilt from idx on demand.
+__global__ void k_inverse_map(const uint32_t *__restrict__ idx, uint32_t *__restrict__ pos_of_idx, int64_t n) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p < n) pos_of_idx[idx[p]] = (uint32_t)p;
+}
+int sphmw_ensure_pos_of_idx(sphmw_ctx *c) {
+    if (!c->pos_of_idx || c->pos_valid || c->n == 0) return SPHMW_OK;
+    TIMED(c, "inverse_map");
+    k_inverse_map<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->idx, c->pos_of_idx, c->n);
+    CUDA_TRY(cudaGetLastError());
+    c->pos_valid = true;
+    return SPHMW_OK;
+}
+
 // core.jl:72-81 on index space.  `removed` holds the reference indices (0-based)
 // of the particles outside the box.  The serial loop
 //     particles[removal[i]] = particles[end+1-i]   (removal sorted DESCENDING)
@@ -398,6 +414,7 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
                                      cudaMemcpyHostToDevice, c->stream));
             CUDA_TRY(cudaMemcpyAsync(c->mv_new, mn.data(), sizeof(uint32_t) * m,
                                      cudaMemcpyHostToDevice, c->stream));
+            TRY(sphmw_ensure_pos_of_idx(c));
             TIMED(c, "cell_renumber");
             k_renumber<<<grid_for(m, 256), 256, 0, c->stream>>>(c->idx, c->pos_of_idx, c->mv_old,
                                                                 c->mv_new, m);
@@ -439,9 +456,10 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     if (n_new > 0) {
         TIMED(c, "cell_gather");
         k_gather<<<grid_for(n_new, 256), 256, 0, c->stream>>>(gl, c->src, c->idx, c->idx_alt,
-                                                              c->pos_of_idx, c->key, c->rank, c->tag,
+                                                              nullptr, c->key, c->rank, c->tag,
                                                               c->tag_alt, c->cellx, c->cellx_alt, n_new);
     }
+    c->pos_valid = false;  // rebuilt on demand (sphmw_ensure_pos_of_idx)
     CUDA_TRY(cudaGetLastError());
     for (int f = 0; f < gl.count; ++f) std::swap(c->cur.s[gathered[f]], c->alt.s[gathered[f]]);
     std::swap(c->idx, c->idx_alt);

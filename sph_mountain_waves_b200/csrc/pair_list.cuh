@@ -179,7 +179,10 @@ __device__ __forceinline__ void nl_count_pairs(unsigned long long *pair_counter,
 #define NL_FILTER_F64 0
 #define NL_FILTER_Q6 3
 #define NL_QUEUE_SLACK 4  // queue rows beyond the list stride: room is checked once per four slots
-// one candidate run [b, e) of the 6-bit pre-test; false: the queue is full
+// one candidate run [b, e) of the 6-bit pre-test; false: the queue is full.  Measured and set aside
+// (profiles/r02b_zrun.md): requesting the next four words ahead, aligned 16-byte loads of four
+// words, and two queue entries per iteration in phase 2 — the plain loop with the fewest registers
+// (56: nine resident blocks) was the fastest of all.
 __device__ __forceinline__ bool nl_q6_run(const uint32_t *__restrict__ xq, uint32_t b, uint32_t e, uint32_t K,
                                           unsigned &qtop, unsigned qlimit) {
     if (b >= e) return true;
@@ -241,14 +244,17 @@ k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restr
         const unsigned pk0 = pkey_ijk(g, home.i - 1, home.j - 1, DIM == 3 ? home.k - 1 : 0);
         for (int di = -1; di <= 1 && fits; ++di) {
             if (DIM == 3) {
-#pragma unroll 1
-                for (int dj = -1; dj <= 1; ++dj) {
-                    const unsigned rk = pk0 + (unsigned)(di + 1) * rows + (unsigned)(dj + 1) * lz;
-                    if (!nl_q6_run(pl.xq, cell_start[rk], cell_start[rk + 3], nl_q6_run_const(ow, di, dj), qtop, qlimit)) {
-                        fits = false;
-                        break;
-                    }
+                // the bounds of the plane's three runs in one go (six independent loads)
+                const unsigned rk = pk0 + (unsigned)(di + 1) * rows;
+                uint32_t rb[3], re[3];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    rb[t] = cell_start[rk + (unsigned)t * lz];
+                    re[t] = cell_start[rk + (unsigned)t * lz + 3];
                 }
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+                    if (fits && !nl_q6_run(pl.xq, rb[t], re[t], nl_q6_run_const(ow, di, t - 1), qtop, qlimit)) fits = false;
             } else {
                 const unsigned rk = pk0 + (unsigned)(di + 1) * rows;
                 if (!nl_q6_run(pl.xq, cell_start[rk], cell_start[rk + 3], nl_q6_run_const(ow, di, 0), qtop, qlimit))

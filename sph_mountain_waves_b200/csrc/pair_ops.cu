@@ -142,6 +142,7 @@ int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_
     const int64_t n = c->n;
     *nout = 0;
     if (n == 0) return SPHMW_OK;
+    TRY(sphmw_ensure_pos_of_idx(c));
     unsigned long long *counts = nullptr;
     long long *dpi = nullptr, *dpj = nullptr;
     CUDA_TRY(cudaMalloc(&counts, sizeof(unsigned long long) * (n + 1)));
@@ -743,6 +744,17 @@ static int apply_seq(sphmw_ctx *c, std::initializer_list<const char *> ops) {
 // wcsph_perturbed_witch.jl:309-332 with the unary sweeps fused into the two pair
 // passes; the redundant second create_cell_list! (:320, positions unchanged —
 // SURVEY quirk 4) is skipped.
+// bookkeeping after accelerate! + move!: positions changed, derived fields are void
+static void wcsph_after_drift(sphmw_ctx *c) {
+    // Dv is identically zero from here on and is not carried through the sort
+    for (int s = S_DV0; s <= S_DV2; ++s)
+        if (c->allocated[s]) c->stale[s] = true;
+    c->cell_list_valid = false;
+    // diagnostics and per-step derived fields need not travel through the reorder
+    for (int s : {S_RHO_BG, S_P_BG, S_P_P, S_P, S_T_P, S_T, S_TH_BG, S_TH_P, S_TH, S_PR2, S_CS})
+        if (c->allocated[s]) c->stale[s] = true;
+}
+
 static int step_wcsph_fused_pre(sphmw_ctx *c) {
     // accelerate! + move!  (:311-312)
     TRY(need_slots(c, SL(S_TYPE, S_RHO_P, S_RHO, S_X0, S_V0, S_M, S_H), SL(S_V0, S_X0)));
@@ -753,14 +765,8 @@ static int step_wcsph_fused_pre(sphmw_ctx *c) {
     } else {
         TRY(run_unary<U_wcsph_accelerate<false>>(c, "wcsph.accelerate"));
     }
-    // Dv is identically zero from here on and is not carried through the sort
-    for (int s = S_DV0; s <= S_DV2; ++s)
-        if (c->allocated[s]) c->stale[s] = true;
     TRY(run_unary<U_wcsph_move>(c, "wcsph.move"));
-    c->cell_list_valid = false;
-    // diagnostics and per-step derived fields need not travel through the reorder
-    for (int s : {S_RHO_BG, S_P_BG, S_P_P, S_P, S_T_P, S_T, S_TH_BG, S_TH_P, S_TH, S_PR2, S_CS})
-        if (c->allocated[s]) c->stale[s] = true;
+    wcsph_after_drift(c);
     return SPHMW_OK;
 }
 
@@ -781,8 +787,16 @@ static int run_fused_density(sphmw_ctx *c) {
     return rec ? run_binary<B_wcsph_density_fused, true>(c, name, 0, c->cur, 1)
                : run_binary<B_wcsph_density_fused>(c, name, 0, c->cur, 1);
 }
-static int run_fused_force(sphmw_ctx *c, const char *name, const ColFilter &cf) {
+static int run_fused_force(sphmw_ctx *c, const char *name, const ColFilter &cf, bool advance = false) {
     const bool rec = sphmw_use_records(c);
+    if (advance) {
+        // + the next step's accelerate! and move! in finish() (B_force_advance); x and v go to alt
+        if (c->flags & SPHMW_FLAG_FAST_MATH)
+            return rec ? run_binary_cols<B_force_advance<B_wcsph_momentum_fast>, true>(c, name, 0, c->alt, cf)
+                       : run_binary_cols<B_force_advance<B_wcsph_momentum_fast>>(c, name, 0, c->alt, cf);
+        return rec ? run_binary_cols<B_force_advance<B_wcsph_momentum_fused>, true>(c, name, 0, c->alt, cf)
+                   : run_binary_cols<B_force_advance<B_wcsph_momentum_fused>>(c, name, 0, c->alt, cf);
+    }
     if (tiles_enabled(c)) {
         if (c->flags & SPHMW_FLAG_FAST_MATH) return run_tiled<B_wcsph_momentum_fast>(c, name, 0, c->alt, cf);
         return run_tiled<B_wcsph_momentum_fused>(c, name, 0, c->alt, cf);
@@ -795,7 +809,15 @@ static int run_fused_force(sphmw_ctx *c, const char *name, const ColFilter &cf) 
 }
 
 // slab mode: the halo exchange sits between the two halves (after the drift, before the sort)
-static int step_wcsph_fused_post(sphmw_ctx *c) {
+// advance: the force pass also opens the next step (accelerate! + move!, B_force_advance); the
+// context is then in the state step_wcsph_fused_pre leaves behind
+static int step_wcsph_fused_post(sphmw_ctx *c, bool advance = false) {
+    // rho and rho' were last read by the kick that opened this step and are rewritten by the density
+    // pass below: on a whole-domain context they need not travel through the sort (a slab context
+    // packs them into its halo records after the drift)
+    if (c->slab_lo < 0)
+        for (int s : {S_RHO, S_RHO_P})
+            if (c->allocated[s]) c->stale[s] = true;
     TRY(sphmw_build_cell_list(c, nullptr));  // :313
     // :316-323
     for (int s : {S_RHO_BG, S_RHO_P, S_RHO, S_P_BG, S_P_P, S_P, S_PR2, S_CS}) {
@@ -815,10 +837,16 @@ static int step_wcsph_fused_post(sphmw_ctx *c) {
     if (c->flags & SPHMW_FLAG_CELL_PAIRS)
         TRY((run_cell_pairs<CP_Momentum>(c, "wcsph.momentum_fused", c->alt, 0)));
     else
-        TRY(run_fused_force(c, "wcsph.momentum_fused", filter_for_depth(c, 0)));
+        TRY(run_fused_force(c, "wcsph.momentum_fused", filter_for_depth(c, 0), advance));
     std::swap(c->cur.s[S_V0], c->alt.s[S_V0]);
     std::swap(c->cur.s[S_V1], c->alt.s[S_V1]);
     if (c->grid.dim == 3) std::swap(c->cur.s[S_V2], c->alt.s[S_V2]);
+    if (advance) {
+        std::swap(c->cur.s[S_X0], c->alt.s[S_X0]);
+        std::swap(c->cur.s[S_X1], c->alt.s[S_X1]);
+        if (c->grid.dim == 3) std::swap(c->cur.s[S_X2], c->alt.s[S_X2]);
+        wcsph_after_drift(c);
+    }
     return SPHMW_OK;
 }
 
@@ -847,9 +875,11 @@ static int step_hopkins_fused(sphmw_ctx *c) {
     return SPHMW_OK;
 }
 
-static int step_wcsph_fused(sphmw_ctx *c) {
-    TRY(step_wcsph_fused_pre(c));
-    return step_wcsph_fused_post(c);
+// one step of a whole-domain multi-step call.  opened: the previous step's force pass already ran
+// this step's accelerate! + move!; advance: do the same for the next one
+static int step_wcsph_fused(sphmw_ctx *c, bool opened = false, bool advance = false) {
+    if (!opened) TRY(step_wcsph_fused_pre(c));
+    return step_wcsph_fused_post(c, advance);
 }
 
 // ===========================================================================
@@ -1013,9 +1043,15 @@ int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps) {
                         "step_phase around the caller's halo exchange");
         return SPHMW_E_STATE;
     }
+    // the fused step folds the next step's accelerate! + move! into its force pass (all steps of a
+    // call but the last); not with the shared-memory variants, whose kernels have no such finish()
+    const bool fold = !(c->flags & (SPHMW_FLAG_CELL_PAIRS | SPHMW_FLAG_TILES)) && !getenv("SPHMW_NO_FUSED_ADVANCE");
+    bool opened = false;
     for (int k = 0; k < nsteps; ++k) {
         if (!strcmp(scheme, "wcsph")) {
-            TRY(step_wcsph_fused(c));
+            const bool advance = fold && k + 1 < nsteps;
+            TRY(step_wcsph_fused(c, opened, advance));
+            opened = advance;
         } else if (!strcmp(scheme, "wcsph_unfused")) {
             // the literal operator sequence of wcsph_perturbed_witch.jl:309-332
             TRY(apply_seq(c, {"wcsph.accelerate", "wcsph.move", "create_cell_list",

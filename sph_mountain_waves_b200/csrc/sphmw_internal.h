@@ -323,7 +323,8 @@ struct sphmw_ctx {
     bool dv_zero = true;     // Dv is known to be all-zero (never written since accelerate!)
 
     uint32_t *idx = nullptr, *idx_alt = nullptr;  // reference particle index of each position
-    uint32_t *pos_of_idx = nullptr;               // inverse map (whole-domain contexts only)
+    uint32_t *pos_of_idx = nullptr;               // inverse map (whole-domain contexts only), valid iff pos_valid
+    bool pos_valid = false;
     uint32_t *tag = nullptr, *tag_alt = nullptr;  // TAG_OWNED / TAG_GHOST / TAG_DEAD per position
     int64_t n_owned = 0;                          // slab mode: resident particles this rank owns
     // dead particles the next cell-list build will meet (halo.cu: ghosts and migrants of the last
@@ -444,6 +445,7 @@ void sphmw_grid_set_order(Grid &g, bool zrun);  // physical cell order (Grid::zr
 // implemented in cell_list.cu
 int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive);
 int sphmw_ensure_slot(sphmw_ctx *c, int slot);
+int sphmw_ensure_pos_of_idx(sphmw_ctx *c);  // rebuild the inverse index map if a cell-list build voided it
 // implemented in pair_ops.cu
 int sphmw_apply_named(sphmw_ctx *c, const char *op, int self);
 int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps);

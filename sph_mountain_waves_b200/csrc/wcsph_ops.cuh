@@ -250,6 +250,34 @@ struct B_wcsph_momentum_fused : PairOpBase {
         wcsph_force_finish<DIM>(f, out, c, p, v0, v1, v2, dv0, dv1, dv2);
     }
 };
+// Force pass of every step of a multi-step call but the last: after the kick that ends step n, the
+// same thread applies the accelerate! and move! that open step n+1 (wcsph_perturbed_witch.jl:311-312)
+// — the very closures the unary kernels run, on a view whose x and v live in the `out` buffers,
+// because neighbours still read the old positions and velocities.  Saves two sweeps over the
+// particles per step; per-particle operations, so no bit changes.
+template <class Base>
+struct B_force_advance : Base {
+    template <int DIM>
+    static __device__ void skip(const Fields &f, const Fields &out, int64_t p) {
+        Base::template skip<DIM>(f, out, p);
+        out.s[S_X0][p] = f.s[S_X0][p];
+        out.s[S_X1][p] = f.s[S_X1][p];
+        if (DIM == 3) out.s[S_X2][p] = f.s[S_X2][p];
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &out, const Params &c, int64_t p) {
+        Base::template finish<DIM>(f, out, c, p);  // new velocity -> out
+        Fields mix = f;
+        for (int s = S_X0; s <= S_X2; ++s) mix.s[s] = out.s[s];
+        for (int s = S_V0; s <= S_V2; ++s) mix.s[s] = out.s[s];
+        mix.s[S_X0][p] = f.s[S_X0][p];
+        mix.s[S_X1][p] = f.s[S_X1][p];
+        if (DIM == 3) mix.s[S_X2][p] = f.s[S_X2][p];
+        U_wcsph_accelerate<false>::template apply<DIM>(mix, c, p);
+        U_wcsph_move::template apply<DIM>(mix, c, p);
+    }
+};
+
 // ---- fast-arithmetic variants of the two fused passes (SPHMW_FLAG_FAST_MATH) ----------
 // Same neighbour set (the cut-off test stays exact) and the same summation ORDER, but the
 // closure bodies use fused multiply-adds, reciprocals instead of divisions and one rsqrt,

@@ -153,6 +153,27 @@ def test_fused_step_equals_operator_sequence(gpu, name):
         assert bits_equal(a.field(f), b.field(f)), f
 
 
+@pytest.mark.parametrize("flags", [0, 1, 128])
+@pytest.mark.parametrize("name", ["witch2d", "hill3d"])
+def test_multi_step_call_equals_single_steps(gpu, name, flags):
+    """one call of n steps folds each next step's accelerate! + move! into the force pass
+    (B_force_advance, csrc/wcsph_ops.cuh); n calls of one step run them as unary sweeps —
+    wcsph_perturbed_witch.jl:311-312 either way, so the bits must agree (strict, fast, SoA gathers)"""
+    case = CASES[name]()
+    a, b = load_gpu(case, flags=flags), load_gpu(case, flags=flags)
+    a.create_cell_list()
+    b.create_cell_list()
+    a.step(7)
+    for _ in range(7):
+        b.step(1)
+    for f in WCSPH_FIELDS:
+        assert bits_equal(a.field(f), b.field(f)), f
+    a.step(2)  # and a call after an advanced one starts from a clean state
+    b.step(2)
+    for f in ("x", "v", "rho"):
+        assert bits_equal(a.field(f), b.field(f)), f
+
+
 @pytest.mark.parametrize("name", ["static2d", "witch2d", "hill3d"])
 def test_step_parity_vs_oracle(gpu, name):
     case = CASES[name]()
