@@ -258,6 +258,9 @@ int sphmw_frame_capture(sphmw_ctx *ctx, const char *const *fields, int32_t nfiel
 int sphmw_frame_wait(sphmw_ctx *ctx, int32_t slot, const double **host, int32_t nfields, int64_t *n);
 int sphmw_upload_async(sphmw_ctx *ctx, const char *field, const double *buf, int64_t n, int32_t ncomp);
 int sphmw_upload_commit(sphmw_ctx *ctx);
+/* slab contexts: the global particle indices of the staged batch (≙ sphmw_set_index after the
+ * commit, without its host wait) — staged like a field, applied by sphmw_upload_commit */
+int sphmw_upload_index_async(sphmw_ctx *ctx, const int64_t *global_idx, int64_t n);
 
 /* ≙ the file half of import_particles!(sys, path, ctor) — src/IO.jl:83-122 (ReadVTK.jl): a
  * host-only reader of the PolyData files WriteVTK (and sphmw_pvd_save_frame) writes.  Array 0

@@ -92,6 +92,7 @@ _SIGS = {
     "sphmw_frame_wait": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_int64)]),
     "sphmw_upload_async": (C.c_int, [_P, C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
     "sphmw_upload_commit": (C.c_int, [_P]),
+    "sphmw_upload_index_async": (C.c_int, [_P, C.c_void_p, C.c_int64]),
     "sphmw_comm_unique_id": (C.c_int, [C.c_void_p]),
     "sphmw_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_char_p, C.c_int64]),
     "sphmw_comm_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),

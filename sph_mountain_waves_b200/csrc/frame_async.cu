@@ -249,12 +249,28 @@ int sphmw_frame_async_drain(sphmw_ctx *c) {
 // ---- host -> device prefetch ---------------------------------------------------------------------
 // Stages one field on the copy stream; `buf` must stay valid until sphmw_upload_commit.  n is the
 // particle count the commit will set (every field of one batch has the same n).
+// slot < 0: the batch's global particle indices (slab contexts), n int64 values
+static int upload_stage(sphmw_ctx *c, int slot, int ncomp, const void *buf, int64_t n, const char *what);
+
 extern "C" int sphmw_upload_async(sphmw_ctx *c, const char *field, const double *buf, int64_t n, int32_t ncomp) {
     if (!c || !field || !buf || n < 0) { sphmw_set_error("null argument"); return SPHMW_E_INVALID; }
     CUDA_TRY(cudaSetDevice(c->device));
     const FieldDesc *d = sphmw_find_field(field);
     if (!d) { sphmw_set_error("Variable %s does not exist!", field); return SPHMW_E_UNKNOWN_FIELD; }
     if (ncomp != d->ncomp || n > c->cap) { sphmw_set_error("upload_async(%s): shape mismatch", field); return SPHMW_E_INVALID; }
+    return upload_stage(c, d->slot, ncomp, buf, n, field);
+}
+// the global indices of the batch (slab contexts; ≙ sphmw_set_index after the commit, without its
+// host wait): staged like a field, applied by the commit
+extern "C" int sphmw_upload_index_async(sphmw_ctx *c, const int64_t *global_idx, int64_t n) {
+    if (!c || !global_idx || n < 0) { sphmw_set_error("null argument"); return SPHMW_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->slab_lo < 0) { sphmw_set_error("upload_index_async: context has no slab"); return SPHMW_E_STATE; }
+    if (n > c->cap) { sphmw_set_error("upload_index_async: n exceeds the capacity"); return SPHMW_E_INVALID; }
+    return upload_stage(c, -1, 1, global_idx, n, "index");
+}
+
+static int upload_stage(sphmw_ctx *c, int slot, int ncomp, const void *buf, int64_t n, const char *field) {
     FrameAsync *fa;
     TRY(fa_get(c, &fa));
     if (fa->up_items.empty()) {
@@ -277,7 +293,7 @@ extern "C" int sphmw_upload_async(sphmw_ctx *c, const char *field, const double 
     }
     if (n) CUDA_TRY(cudaMemcpyAsync(fa->up_dev + fa->up_used, buf, sizeof(double) * ncomp * n, cudaMemcpyHostToDevice,
                                     fa->up_stream));
-    fa->up_items.push_back(UploadItem{d->slot, ncomp, fa->up_used});
+    fa->up_items.push_back(UploadItem{slot, ncomp, fa->up_used});
     fa->up_used = need;
     return SPHMW_OK;
 }
@@ -285,6 +301,10 @@ extern "C" int sphmw_upload_async(sphmw_ctx *c, const char *field, const double 
 __global__ void k_permute_in_async(double *__restrict__ dst, const double *__restrict__ stg, int64_t n) {
     const int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (pos < n) dst[pos] = stg[pos];
+}
+__global__ void k_index_in_async(uint32_t *__restrict__ idx, const long long *__restrict__ stg, int64_t n) {
+    const int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (pos < n) idx[pos] = (uint32_t)stg[pos];
 }
 
 // The staged fields become the particle state: the context is resized to the batch's n (indices
@@ -301,6 +321,10 @@ extern "C" int sphmw_upload_commit(sphmw_ctx *c) {
     const int64_t n = fa->up_n;
     for (const UploadItem &it : fa->up_items)
         for (int k = 0; k < it.ncomp; ++k) {
+            if (it.slot < 0) {  // global indices (sphmw_upload_index_async)
+                if (n) k_index_in_async<<<grid_for(n, 256), 256, 0, c->stream>>>(c->idx, (const long long *)(fa->up_dev + it.off), n);
+                continue;
+            }
             if (c->grid.dim == 2 && it.ncomp == 3 && k == 2) continue;
             const int slot = it.slot + k;
             TRY(sphmw_ensure_slot(c, slot));

@@ -14,6 +14,7 @@
 // wherever no transcendental (exp, pow, cbrt) is involved.
 #include <math.h>
 #include <stdlib.h>
+#include <limits.h>
 #include <string.h>
 
 #include <string>
@@ -335,15 +336,27 @@ static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Field
 #define NL_ARGS c->cur, out, c->prm, c->grid, c->key, c->cellx, c->cell_start, c->n, self, pc, cf
     if (replay) {
         TIMED(c, name);
+        // a few columns only (edge columns of the overlapped slab step): a small grid strides over
+        // their particle ranges, which are contiguous in the zrun cell order
+        const bool cols = cf.on && cf.sparse && !cf.copy && c->grid.zrun && !getenv("SPHMW_NO_COLUMN_RANGES");
+        const unsigned cblocks = std::min<unsigned>(blocks, (unsigned)c->sm_count * 8u);
         if constexpr (REC) {
             if (rec && c->rec_bc_gen == c->cell_gen) {
-                if (c->grid.dim == 2) k_binary_list<2, Op, true><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
-                else k_binary_list<3, Op, true><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
+                if (cols) {
+                    if (c->grid.dim == 2) k_binary_list_cols<2, Op, true><<<cblocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
+                    else k_binary_list_cols<3, Op, true><<<cblocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
+                } else {
+                    if (c->grid.dim == 2) k_binary_list<2, Op, true><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
+                    else k_binary_list<3, Op, true><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
+                }
                 CUDA_TRY(cudaGetLastError());
                 return SPHMW_OK;
             }
         }
-        if (c->grid.dim == 2)
+        if (cols) {
+            if (c->grid.dim == 2) k_binary_list_cols<2, Op><<<cblocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
+            else k_binary_list_cols<3, Op><<<cblocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
+        } else if (c->grid.dim == 2)
             k_binary_list<2, Op><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
         else
             k_binary_list<3, Op><<<blocks, NL_BLOCK, 0, c->stream>>>(NL_ARGS, c->pl);
@@ -755,6 +768,15 @@ static void wcsph_after_drift(sphmw_ctx *c) {
         if (c->allocated[s]) c->stale[s] = true;
 }
 
+// rho and rho' were last read by the kick that opened this step (and, on a slab context, by the halo
+// pack that followed the drift) and are rewritten by the density pass for every particle a later
+// pass reads them from: they need not travel through the sort.  (The outermost ghost column keeps
+// no density at all: nothing reads it — the force pass stops one column short of it.)
+static void wcsph_before_sort(sphmw_ctx *c) {
+    for (int s : {S_RHO, S_RHO_P})
+        if (c->allocated[s]) c->stale[s] = true;
+}
+
 static int step_wcsph_fused_pre(sphmw_ctx *c) {
     // accelerate! + move!  (:311-312)
     TRY(need_slots(c, SL(S_TYPE, S_RHO_P, S_RHO, S_X0, S_V0, S_M, S_H), SL(S_V0, S_X0)));
@@ -812,12 +834,7 @@ static int run_fused_force(sphmw_ctx *c, const char *name, const ColFilter &cf, 
 // advance: the force pass also opens the next step (accelerate! + move!, B_force_advance); the
 // context is then in the state step_wcsph_fused_pre leaves behind
 static int step_wcsph_fused_post(sphmw_ctx *c, bool advance = false) {
-    // rho and rho' were last read by the kick that opened this step and are rewritten by the density
-    // pass below: on a whole-domain context they need not travel through the sort (a slab context
-    // packs them into its halo records after the drift)
-    if (c->slab_lo < 0)
-        for (int s : {S_RHO, S_RHO_P})
-            if (c->allocated[s]) c->stale[s] = true;
+    wcsph_before_sort(c);
     TRY(sphmw_build_cell_list(c, nullptr));  // :313
     // :316-323
     for (int s : {S_RHO_BG, S_RHO_P, S_RHO, S_P_BG, S_P_P, S_P, S_PR2, S_CS}) {
@@ -901,8 +918,8 @@ static int step_wcsph_fused(sphmw_ctx *c, bool opened = false, bool advance = fa
 // dt = 0.01 h/c in the drivers); the interior kernel counts violations and
 // sphmw_halo_pack_finish fails loudly on them.
 // ===========================================================================
-static ColFilter cols_range(int a0, int a1, int b0, int b1) {
-    ColFilter cf{1, a0, a1, b0, b1, 0};
+static ColFilter cols_range(int a0, int a1, int b0, int b1, int sparse = 0) {
+    ColFilter cf{1, a0, a1, b0, b1, 0, sparse};
     return cf;
 }
 
@@ -917,9 +934,9 @@ SlabCols sphmw_slab_cols_of(int W, bool hl, bool hr) {
     const int ir = hr ? W - G - 4 : W - 1;             // last interior column
     const int er = hr ? (ir + 1 > il ? ir + 1 : il) : W;  // first column of the right edge set
     SlabCols sc;
-    sc.edge = cols_range(hl ? 0 : 1, hl ? il - 1 : 0, hr ? er : 1, hr ? W - 1 : 0);
+    sc.edge = cols_range(hl ? 0 : 1, hl ? il - 1 : 0, hr ? er : 1, hr ? W - 1 : 0, 1);
     sc.interior = cols_range(il, ir, 1, 0);
-    sc.force_edge = cols_range(hl ? G : 1, hl ? il - 1 : 0, hr ? er : 1, hr ? W - G - 1 : 0);
+    sc.force_edge = cols_range(hl ? G : 1, hl ? il - 1 : 0, hr ? er : 1, hr ? W - G - 1 : 0, 1);
     sc.force_interior = cols_range(il > G ? il : G, ir < W - G - 1 ? ir : W - G - 1, 1, 0);
     return sc;
 }
@@ -930,12 +947,11 @@ SlabCols sphmw_slab_cols_of(int W, bool hl, bool hr) {
 // the next pack).  check_escape: count particles that end up in a column whose records were
 // already packed.
 template <int DIM>
-__global__ void __launch_bounds__(256)
-k_advance_cols(Fields cur, Fields mix, Params prm, Grid g, const uint32_t *__restrict__ cellx,
-               const uint32_t *__restrict__ tag, int64_t n, ColFilter cf, int check_escape, int has_left,
-               int has_right, uint32_t *__restrict__ counters) {
-    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= n) return;
+__device__ __forceinline__ void advance_particle(int64_t p, const Fields &cur, const Fields &mix, const Params &prm,
+                                                 const Grid &g, const uint32_t *__restrict__ cellx,
+                                                 const uint32_t *__restrict__ tag, const ColFilter &cf,
+                                                 int check_escape, int has_left, int has_right,
+                                                 uint32_t *__restrict__ counters) {
     if (!col_selected(cf, (int)cellx[p])) return;
     mix.s[S_X0][p] = cur.s[S_X0][p];
     mix.s[S_X1][p] = cur.s[S_X1][p];
@@ -955,6 +971,28 @@ k_advance_cols(Fields cur, Fields mix, Params prm, Grid g, const uint32_t *__res
             atomicAdd(&counters[5], 1u);
     }
 }
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_advance_cols(Fields cur, Fields mix, Params prm, Grid g, const uint32_t *__restrict__ cellx,
+               const uint32_t *__restrict__ tag, int64_t n, ColFilter cf, int check_escape, int has_left,
+               int has_right, uint32_t *__restrict__ counters) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    advance_particle<DIM>(p, cur, mix, prm, g, cellx, tag, cf, check_escape, has_left, has_right, counters);
+}
+// the same over the particle ranges of a few columns (zrun cell order; pair_list.cuh col_ranges)
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_advance_cols_ranges(Fields cur, Fields mix, Params prm, Grid g, const uint32_t *__restrict__ cellx,
+                      const uint32_t *__restrict__ tag, const uint32_t *__restrict__ cell_start, int64_t n,
+                      ColFilter cf, int check_escape, int has_left, int has_right, uint32_t *__restrict__ counters) {
+    const ColRanges r = col_ranges(g, cf, cell_start);
+    const uint32_t total = r.n0 + r.n1;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int64_t p = t < r.n0 ? (int64_t)r.b0 + t : (int64_t)r.b1 + (t - r.n0);
+        if (p < n) advance_particle<DIM>(p, cur, mix, prm, g, cellx, tag, cf, check_escape, has_left, has_right, counters);
+    }
+}
 
 static Fields mixed_view(sphmw_ctx *c) {
     Fields m = c->cur;
@@ -966,6 +1004,17 @@ static int run_advance_cols(sphmw_ctx *c, const char *name, const ColFilter &cf,
     if (c->n == 0) return SPHMW_OK;
     const int hl = c->slab_lo > 0, hr = c->slab_hi < c->global_cols;
     TIMED(c, name);
+    if (cf.sparse && c->grid.zrun && !getenv("SPHMW_NO_COLUMN_RANGES")) {
+        const unsigned gb = std::min<unsigned>(grid_for(c->n, 256), (unsigned)c->sm_count * 4u);
+        if (c->grid.dim == 2)
+            k_advance_cols_ranges<2><<<gb, 256, 0, c->stream>>>(c->cur, mixed_view(c), c->prm, c->grid, c->cellx, c->tag,
+                                                                c->cell_start, c->n, cf, check_escape, hl, hr, c->halo_counters);
+        else
+            k_advance_cols_ranges<3><<<gb, 256, 0, c->stream>>>(c->cur, mixed_view(c), c->prm, c->grid, c->cellx, c->tag,
+                                                                c->cell_start, c->n, cf, check_escape, hl, hr, c->halo_counters);
+        CUDA_TRY(cudaGetLastError());
+        return SPHMW_OK;
+    }
     if (c->grid.dim == 2)
         k_advance_cols<2><<<grid_for(c->n, 256), 256, 0, c->stream>>>(
             c->cur, mixed_view(c), c->prm, c->grid, c->cellx, c->tag, c->n, cf, check_escape, hl, hr, c->halo_counters);
@@ -983,6 +1032,7 @@ static int step_wcsph_overlap_a(sphmw_ctx *c) {
     }
     if (c->overlap_stage != 0) { sphmw_set_error("step_phase 2: an overlapped step is already in flight"); return SPHMW_E_STATE; }
     if (!c->dv_zero) { sphmw_set_error("step_phase 2: Dv must be zero (run step_phase 0 first)"); return SPHMW_E_STATE; }
+    wcsph_before_sort(c);
     TRY(sphmw_build_cell_list(c, nullptr));
     for (int s : {S_RHO_BG, S_RHO_P, S_RHO, S_P_BG, S_P_P, S_P, S_PR2, S_CS}) {
         TRY(sphmw_ensure_slot(c, s));
@@ -1004,8 +1054,27 @@ static int step_wcsph_overlap_b(sphmw_ctx *c) {
         return SPHMW_E_STATE;
     }
     const SlabCols sc = sphmw_slab_cols(c);
-    TRY(run_fused_force(c, "wcsph.momentum_fused", sc.force_interior));
-    TRY(run_advance_cols(c, "wcsph.advance_interior", sc.interior, 1));
+    const bool fold = !(c->flags & SPHMW_FLAG_TILES) && !getenv("SPHMW_NO_FUSED_ADVANCE");
+    if (fold) {
+        // the interior force pass also runs the next step's accelerate! + move! (B_force_advance)
+        // and counts particles that drift into a column whose records were already packed; the
+        // interior columns outside the force set (ghost columns of a rank on the global boundary:
+        // empty, or nearly) get the plain advance kernel over their particle ranges
+        const int W = (int)c->grid.lim[0], G = GHOST_COLS;
+        c->prm.esc_counter = c->halo_counters + 5;
+        c->prm.esc_h = c->grid.h;
+        c->prm.esc_phase = c->grid.phase[0];
+        c->prm.esc_lo = c->slab_lo > 0 ? 2 * G : INT_MIN;
+        c->prm.esc_hi = c->slab_hi < c->global_cols ? W - 2 * G : INT_MAX;
+        const int rc = run_fused_force(c, "wcsph.momentum_fused", sc.force_interior, true);
+        c->prm.esc_counter = nullptr;
+        TRY(rc);
+        ColFilter rest = cols_range(sc.interior.a0, sc.force_interior.a0 - 1, sc.force_interior.a1 + 1, sc.interior.a1, 1);
+        if (rest.a0 <= rest.a1 || rest.b0 <= rest.b1) TRY(run_advance_cols(c, "wcsph.advance_interior", rest, 1));
+    } else {
+        TRY(run_fused_force(c, "wcsph.momentum_fused", sc.force_interior));
+        TRY(run_advance_cols(c, "wcsph.advance_interior", sc.interior, 1));
+    }
     for (int s : {S_X0, S_X1, S_X2, S_V0, S_V1, S_V2})
         if ((s != S_X2 && s != S_V2) || c->grid.dim == 3) std::swap(c->cur.s[s], c->alt.s[s]);
     // as after step_wcsph_fused_pre: positions changed, per-step derived fields are stale

@@ -49,6 +49,13 @@ struct Params {
     // derived on the host when a parameter changes
     double sponge_y;  // -gamma_r*sin(pi/2*(1-(z_t-z_b)/z_b))^2  (:245-251)
     double sponge_z0; // z_t - z_b
+    // overlapped slab step: the interior force pass also runs the next step's accelerate!/move!
+    // (B_force_advance) and counts particles that drift into a column whose halo records were
+    // already packed (pair_ops.cu); null otherwise
+    uint32_t *esc_counter;
+    double esc_h;
+    long long esc_phase;
+    int esc_lo, esc_hi;  // legal local columns after the drift: [esc_lo, esc_hi)
 };
 
 // neighbour-grid description passed to kernels by value (structs.jl:63-82)
@@ -161,6 +168,7 @@ __device__ __forceinline__ bool neighbour_pkey(const Grid &g, const CellCoord &c
 // the set carry double-buffered outputs over (B_*::skip)
 struct ColFilter {
     int on, a0, a1, b0, b1, copy;
+    int sparse;  // the set is a small part of the grid: launch over the columns' particle ranges
 };
 __host__ __device__ __forceinline__ bool col_selected(const ColFilter &cf, int i) {
     return (i >= cf.a0 && i <= cf.a1) || (i >= cf.b0 && i <= cf.b1);

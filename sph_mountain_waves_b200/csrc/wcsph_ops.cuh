@@ -275,6 +275,10 @@ struct B_force_advance : Base {
         if (DIM == 3) mix.s[S_X2][p] = f.s[S_X2][p];
         U_wcsph_accelerate<false>::template apply<DIM>(mix, c, p);
         U_wcsph_move::template apply<DIM>(mix, c, p);
+        if (c.esc_counter) {
+            const long long i = (long long)floor(mix.s[S_X0][p] / c.esc_h) - c.esc_phase;
+            if (i < c.esc_lo || i >= c.esc_hi) atomicAdd(c.esc_counter, 1u);
+        }
     }
 };
 

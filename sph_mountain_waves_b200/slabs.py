@@ -526,7 +526,9 @@ class SlabRun:
                     t = torch.empty(a.T.shape if a.ndim == 2 else a.shape, dtype=torch.float64, pin_memory=True)
                     t.copy_(torch.from_numpy(np.ascontiguousarray(a.T if a.ndim == 2 else a)))
                     self._pinned[f] = t
-                self._gidx = np.ascontiguousarray(gidx)
+                # global indices travel with every batch: pinned, staged by sphmw_upload_index_async
+                self._gidx = torch.empty((n0,), dtype=torch.int64, pin_memory=True)
+                self._gidx.copy_(torch.from_numpy(np.ascontiguousarray(gidx, dtype=np.int64)))
             else:
                 n0 = sys.n_device
                 for f in carried:
@@ -540,7 +542,7 @@ class SlabRun:
                 nc = FIELD_NCOMP[canonical(f)]
                 self._pinned["out:" + f] = torch.empty((nc * cap,), dtype=torch.float64, pin_memory=True)
         n0 = self._n0
-        h2d = sum(self._pinned[f].numel() * 8 for f in carried)
+        h2d = sum(self._pinned[f].numel() * 8 for f in carried) + (n0 * 8 if slab else 0)
         d2h = 0
         names = (C.c_char_p * len(out_fields))(*[canonical(f).encode() for f in out_fields])
         comps = sum(FIELD_NCOMP[canonical(f)] for f in out_fields)
@@ -550,6 +552,8 @@ class SlabRun:
             for f in carried:
                 check(lib.sphmw_upload_async(sys.ctx, canonical(f).encode(), C.c_void_p(self._pinned[f].data_ptr()),
                                              n0, FIELD_NCOMP[canonical(f)]))
+            if slab:
+                check(lib.sphmw_upload_index_async(sys.ctx, C.c_void_p(self._gidx.data_ptr()), n0))
 
         def wait(slot):
             ptrs = (C.c_void_p * len(out_fields))()
@@ -562,9 +566,7 @@ class SlabRun:
             prefetch()
             pending = None
             for k in range(count):
-                check(lib.sphmw_upload_commit(sys.ctx))       # staged fields -> particle state (no host wait)
-                if slab:
-                    check(lib.sphmw_set_index(sys.ctx, _capi.ptr(self._gidx), n0))
+                check(lib.sphmw_upload_commit(sys.ctx))       # staged fields (+ indices) -> particle state, no host wait
                 if k + 1 < count:
                     prefetch()
                 self.create_cell_list()

@@ -27,7 +27,7 @@ struct float4 {
 struct double2 {
     double x, y;
 };
-extern uint3 threadIdx, blockIdx, blockDim;  // set by the harness before every "thread"
+extern uint3 threadIdx, blockIdx, blockDim, gridDim;  // set by the harness before every "thread"
 
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;

@@ -24,7 +24,7 @@
 #include "pair_list.cuh"
 #include "sphmw_internal.h"
 
-uint3 threadIdx, blockIdx, blockDim;
+uint3 threadIdx, blockIdx, blockDim, gridDim;
 uint32_t nl_queue[(96 + NL_QUEUE_SLACK) * NL_BLOCK];
 
 void sphmw_set_error(const char *fmt, ...) {

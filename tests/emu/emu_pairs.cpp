@@ -32,7 +32,7 @@
 #include "sphmw_internal.h"
 #include "wcsph_ops.cuh"
 
-uint3 threadIdx, blockIdx, blockDim;
+uint3 threadIdx, blockIdx, blockDim, gridDim;
 uint32_t nl_queue[(96 + NL_QUEUE_SLACK) * NL_BLOCK];
 // the tiled kernels' shared window (pair_tile.cuh) and the sync-point bookkeeping of their emulation
 alignas(16) unsigned char emu_tile_smem[256 * 1024];
@@ -52,6 +52,20 @@ static void launch(int64_t n, F &&thread_body) {
     blockDim = uint3{NL_BLOCK, 1, 1};
     for (int64_t b = 0; b * NL_BLOCK < n; ++b) {
         blockIdx = uint3{(unsigned)b, 0, 0};
+        for (unsigned t = 0; t < NL_BLOCK; ++t) {
+            threadIdx = uint3{t, 0, 0};
+            thread_body();
+        }
+    }
+}
+
+// a fixed grid whose threads stride over their work themselves (k_binary_list_cols)
+template <class F>
+static void launch_grid(unsigned nblocks, F &&thread_body) {
+    blockDim = uint3{NL_BLOCK, 1, 1};
+    gridDim = uint3{nblocks, 1, 1};
+    for (unsigned b = 0; b < nblocks; ++b) {
+        blockIdx = uint3{b, 0, 0};
         for (unsigned t = 0; t < NL_BLOCK; ++t) {
             threadIdx = uint3{t, 0, 0};
             thread_body();
@@ -180,18 +194,22 @@ static Result run_variant(State st, const Grid &g, const Params &prm, Variant v,
         const int W = (int)g.lim[0];
         const ColFilter cd{1, 1, W - 2, 1, 0, 1};
         const ColFilter cedge{1, 2, 3, W - 4, W - 3, 1}, cint{1, 4, W - 5, 1, 0, 0};
+        // list variants on the zrun order: the interior launch goes first and carries the velocity of
+        // everything it skips, then the edge columns run over their particle ranges (three blocks
+        // striding, as k_binary_list_cols is launched by the overlapped slab step)
+        const ColFilter cint_copy{1, 4, W - 5, 1, 0, 1}, cedge_sparse{1, 2, 3, W - 4, W - 3, 0, 1};
         if (v == SLAB_LIST) {
             launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q6>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cd, pl); });
-            launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge, pl); });
-            launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[3], cint, pl); });
+            launch(n, [&] { k_binary_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[3], cint_copy, pl); });
+            launch_grid(3, [&] { k_binary_list_cols<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge_sparse, pl); });
         } else if (v == SLAB_TILES) {
             launch_tiled(n, [&] { k_tile_build<DIM, DensityOp>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cd, pl, tab); });
             launch_tiled(n, [&] { k_tile_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge, pl, tab); });
             launch_tiled(n, [&] { k_tile_list<DIM, ForceOp>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[3], cint, pl, tab); });
         } else {
             launch(n, [&] { k_binary_build<DIM, DensityOp, NL_FILTER_Q6, true>(st.fcur, st.fcur, prm, g, key, cellx, cs, n, 0, &counters[0], cd, pl); });
-            launch(n, [&] { k_binary_list<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge, pl); });
-            launch(n, [&] { k_binary_list<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[3], cint, pl); });
+            launch(n, [&] { k_binary_list<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[3], cint_copy, pl); });
+            launch_grid(3, [&] { k_binary_list_cols<DIM, ForceOp, true>(st.fcur, st.falt, prm, g, key, cellx, cs, n, 0, &counters[1], cedge_sparse, pl); });
         }
     }
     r.pairs_density = counters[0];
