@@ -187,6 +187,12 @@ int sphmw_generate_mountain_wave(sphmw_ctx *ctx, const sphmw_lattice_setup *setu
  * the next indices in the order the reference's loop would create them.  Parameters used:
  * inflow, fluid, x_inflow, bc_width, U_max, dr, rho0, g, R_mass, R_gas, cp, T_bg. */
 int sphmw_flow_add_new_particles(sphmw_ctx *ctx, int64_t *n_added);
+/* the same for the adiabatic variant of the driver — src/legacy/adiabatic_flow_witch.jl:197-208,
+ * Particle constructor :82-91: T = T0 (parameter T_bg), hydrostatic rho, m = rho dr^2, P = R_mass T rho,
+ * theta, and the entropy S = m cv log(cv T (gamma - 1) / (gamma rho^(gamma - 1))), cv = cp - R_mass.
+ * Its closures are the operators "aflow.*" (+ "flow.accelerate", "flow.internal_force", which the two
+ * drivers share character for character); sphmw_step(ctx, "aflow", n) is its verlet_step! (:231-243). */
+int sphmw_aflow_add_new_particles(sphmw_ctx *ctx, int64_t *n_added);
 
 /* Test hooks for bit-exact cell assignment / neighbour-pair parity. */
 /* 0-based cell key of every particle, reference index order (structs.jl:97-106) */
@@ -336,6 +342,15 @@ int sphmw_slab_counts(sphmw_ctx *ctx, int64_t *n_resident, int64_t *n_owned);
 int sphmw_comm_unique_id(void *id128);
 int sphmw_comm_init(sphmw_ctx *ctx, int32_t rank, int32_t world, const void *id128, int64_t halo_capacity);
 int sphmw_comm_info(sphmw_ctx *ctx, int64_t out[6]);
+/* Open box (collective, after sphmw_comm_init): particles may leave the GLOBAL bounding box.
+ * create_cell_list! removes them by moving the particles at the end of sys.particles into the
+ * vacated slots (src/core.jl:72-81), which renumbers survivors that may live on any rank; since
+ * neighbours are visited in index order the renumbering decides the bits of later sums.  With the
+ * open box every halo exchange gathers the indices all ranks dropped (one small all-gather) and
+ * replays that loop on each rank, and sphmw_step uses the plain (non-overlapped) schedule.  Without
+ * it (the default: walled configurations) a particle leaving the global box of a slab context is
+ * dropped and counted (sphmw_comm_info out[4]), and an interior one fails the step loudly. */
+int sphmw_comm_open_box(sphmw_ctx *ctx, int32_t on);
 /* global particle index of every resident particle (physical order) */
 int sphmw_set_index(sphmw_ctx *ctx, const int64_t *global_idx, int64_t n);
 /* physical-order read-back: indices + tags (0 owned, 1 ghost), and raw fields */

@@ -20,7 +20,7 @@ LIB_PATH = HERE / "libsph_oracle.so"
 FIELD_NCOMP = {
     "h": 1, "x": 3, "m": 1, "v": 3, "Dv": 3, "rho_bg": 1, "rho_p": 1, "rho": 1, "P_bg": 1,
     "P_p": 1, "P": 1, "theta_bg": 1, "theta_p": 1, "theta": 1, "T_bg": 1, "T_p": 1, "T": 1,
-    "type": 1, "A": 1, "A_bg": 1, "Drho": 1, "rho0": 1,
+    "type": 1, "A": 1, "A_bg": 1, "Drho": 1, "rho0": 1, "S": 1, "s": 1,
 }
 
 _lib = None
@@ -65,6 +65,10 @@ def lib() -> C.CDLL:
         l.orc_step.argtypes = [P, C.c_char_p, C.c_int]
         l.orc_flow_add_new_particles.restype = C.c_int64
         l.orc_flow_add_new_particles.argtypes = [P]
+        l.orc_aflow_add_new_particles.restype = C.c_int64
+        l.orc_aflow_add_new_particles.argtypes = [P]
+        l.orc_aflow_construct_all.restype = None
+        l.orc_aflow_construct_all.argtypes = [P]
         for k in ("wendland1", "Dwendland1", "rDwendland1", "wendland2", "Dwendland2", "rDwendland2",
                   "wendland3", "Dwendland3", "rDwendland3", "DDwendland3", "spline23", "Dspline23",
                   "rDspline23", "spline24", "Dspline24", "rDspline24"):
@@ -174,6 +178,14 @@ class OracleSystem:
 
     def flow_add_new_particles(self) -> int:
         return int(lib().orc_flow_add_new_particles(self._h))
+
+    def aflow_add_new_particles(self) -> int:
+        """add_new_particles! of src/legacy/adiabatic_flow_witch.jl:197-208"""
+        return int(lib().orc_aflow_add_new_particles(self._h))
+
+    def aflow_construct_all(self):
+        """the adiabatic driver's Particle constructor (:82-91) on every particle: T, rho, m, P, theta, S from x"""
+        lib().orc_aflow_construct_all(self._h)
 
     def cell_keys(self) -> np.ndarray:
         k = np.empty(self.n, dtype=np.int64)

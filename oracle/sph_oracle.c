@@ -56,6 +56,7 @@ typedef struct particle {
     double type;
     double A, A_bg;
     double Drho, rho0;
+    double S, s; /* entropy, entropy density: src/legacy/adiabatic_flow_witch.jl:75-76 */
 } particle;
 
 typedef struct {
@@ -73,7 +74,8 @@ static const field_desc FIELDS[] = {
     {"theta_p", OFF(th_p), 1},{"theta", OFF(th), 1},  {"T_bg", OFF(T_bg), 1},
     {"T_p", OFF(T_p), 1},     {"T", OFF(T), 1},       {"type", OFF(type), 1},
     {"A", OFF(A), 1},         {"A_bg", OFF(A_bg), 1}, {"Drho", OFF(Drho), 1},
-    {"rho0", OFF(rho0), 1},   {NULL, 0, 0}};
+    {"rho0", OFF(rho0), 1},   {"S", OFF(S), 1},       {"s", OFF(s), 1},
+    {NULL, 0, 0}};
 
 /* driver constants: wcsph_perturbed_witch.jl:25-75, collapse_dry.jl:30-66,
  * test_collision_2d.jl:14-35 */
@@ -1003,6 +1005,99 @@ int64_t orc_flow_add_new_particles(orc_system *s) {
 }
 
 /* ------------------------------------------------------------------------- */
+/* src/legacy/adiabatic_flow_witch.jl — the same flow with adiabatic           */
+/* thermodynamics: entropy S is carried per particle, T and P follow from rho  */
+/* and the entropy density s.  u is stored in v, Du in Dv, T0 = params.T_bg,   */
+/* h = params.kh, cv = cp - R_mass (:50), gamma = cp/cv (:51).                 */
+/* accelerate! (:225-229) and internal_force! (:146-153) are the isothermal    */
+/* driver's, character for character: f_accelerate, f_internal_force.          */
+/* ------------------------------------------------------------------------- */
+/* :159-163 (applied with self = true, :238) */
+static void af_find_density(particle *p, const particle *q, double r, const orc_system *s) {
+    const params *c = &s->prm;
+    if (p->type == c->fluid && q->type == c->fluid) p->rho += q->m * orc_wendland2(c->kh, r);
+}
+/* :165-169 */
+static void af_find_s(particle *p, const orc_system *s) {
+    if (p->type == s->prm.fluid) p->s = p->S * p->rho / p->m;
+}
+/* :171-176 */
+static void af_find_pressure(particle *p, const orc_system *s) {
+    const params *c = &s->prm;
+    if (p->type == c->fluid) {
+        const double cv = c->cp - c->R_mass;
+        p->T = (pow(p->rho, c->gamma - 1.0)) * exp(p->s / (p->rho * cv)) / (cv * (c->gamma - 1.0));
+        p->P = c->R_mass * p->rho * p->T;
+    }
+}
+/* :178-182 */
+static void af_find_pot_temp(particle *p, const orc_system *s) {
+    const params *c = &s->prm;
+    if (p->type == c->fluid) {
+        double b = (c->T_bg * c->R_gas * c->rho0) / p->P;
+        p->th = p->T * pow(b * b, 1.0 / 7.0);
+    }
+}
+/* :184-191 */
+static void af_entropy_production(particle *p, const particle *q, double r, const orc_system *s) {
+    const params *c = &s->prm;
+    if (p->type == c->fluid && q->type == c->fluid) {
+        double ker = orc_rDwendland2(c->kh, r);
+        double x_pq[3], u_pq[3];
+        for (int a = 0; a < 3; ++a) { x_pq[a] = p->x[a] - q->x[a]; u_pq[a] = p->v[a] - q->v[a]; }
+        double d = dot3(u_pq, x_pq);
+        p->S += -4.0 * p->m * q->m * ker * c->mu / (p->T * p->rho * q->rho) * (d * d) /
+                (r * r + 0.01 * c->kh * c->kh) * c->dt;
+    }
+}
+/* :217-223 */
+static void af_move(particle *p, const orc_system *s) {
+    const params *c = &s->prm;
+    p->Dv[0] = p->Dv[1] = p->Dv[2] = 0.0;
+    if (p->type == c->fluid) {
+        for (int a = 0; a < 3; ++a) p->x[a] += c->dt * p->v[a];
+        p->rho = 0.0;
+    }
+}
+/* the Particle constructor :82-91 */
+static void af_construct(particle *q, const params *c) {
+    const double cv = c->cp - c->R_mass;
+    q->T = c->T_bg;
+    q->rho = c->rho0 * exp(-q->x[1] * c->g / (c->R_mass * q->T));
+    q->m = q->rho * pow2(c->dr);
+    q->P = c->R_mass * q->T * q->rho;
+    double b = (c->T_bg * c->R_gas * c->rho0) / q->P;
+    q->th = q->T * pow(b * b, 1.0 / 7.0);
+    q->S = q->m * cv * log((cv * q->T * (c->gamma - 1.0)) / (c->gamma * pow(q->rho, c->gamma - 1.0)));
+}
+/* :197-208 add_new_particles! */
+int64_t orc_aflow_add_new_particles(orc_system *s) {
+    const params *c = &s->prm;
+    int64_t n0 = s->n, added = 0;
+    for (int64_t i = 0; i < n0; ++i) {
+        particle *p = s->p[i];
+        if (p->type == c->inflow && p->x[0] >= c->x_inflow) {
+            p->type = c->fluid;
+            orc_append(s, 1);
+            particle *q = s->p[s->n - 1];
+            static const double ex[3] = {1.0, 0.0, 0.0};
+            for (int a = 0; a < 3; ++a) {
+                q->x[a] = p->x[a] - c->bc_width * ex[a];
+                q->v[a] = c->U_max * ex[a];
+            }
+            q->type = c->inflow;
+            af_construct(q, c);
+            ++added;
+        }
+    }
+    return added;
+}
+/* the constructor applied to every particle of a freshly generated system (make_system, :106-110) */
+void orc_aflow_construct_all(orc_system *s) {
+    for (int64_t i = 0; i < s->n; ++i) af_construct(s->p[i], &s->prm);
+}
+
+/* ------------------------------------------------------------------------- */
 /* operator menu (names shared with the product's enum so tests read alike)   */
 /* ------------------------------------------------------------------------- */
 typedef struct {
@@ -1053,6 +1148,12 @@ static const op_desc OPS[] = {
     {"flow.find_pot_temp", f_find_pot_temp, NULL},
     {"flow.move", f_move, NULL},
     {"flow.accelerate", f_accelerate, NULL},
+    {"aflow.find_density", NULL, af_find_density},
+    {"aflow.find_s", af_find_s, NULL},
+    {"aflow.find_pressure", af_find_pressure, NULL},
+    {"aflow.find_pot_temp", af_find_pot_temp, NULL},
+    {"aflow.entropy_production", NULL, af_entropy_production},
+    {"aflow.move", af_move, NULL},
     {"packing.reset_rho", p_reset_rho, NULL},
     {"packing.accumulate_rho", NULL, p_accumulate_rho},
     {"packing.balance_of_momentum", NULL, p_balance_of_momentum},
@@ -1178,6 +1279,19 @@ static void step_flow(orc_system *s) {
     apply_binary(s, f_internal_force);
     apply_unary(s, f_accelerate);
 }
+/* adiabatic_flow_witch.jl:231-243 */
+static void step_aflow(orc_system *s) {
+    apply_unary(s, f_accelerate);
+    apply_unary(s, af_move);
+    orc_aflow_add_new_particles(s);
+    orc_create_cell_list(s);
+    orc_apply(s, "aflow.find_density", 1);
+    apply_unary(s, af_find_s);
+    apply_unary(s, af_find_pressure);
+    apply_binary(s, af_entropy_production);
+    apply_binary(s, f_internal_force);
+    apply_unary(s, f_accelerate);
+}
 /* test_collision_2d.jl:106-116 */
 static void step_collision(orc_system *s) {
     apply_unary(s, c_accelerate);
@@ -1200,6 +1314,7 @@ int orc_step(orc_system *s, const char *scheme, int nsteps) {
     else if (!strcmp(scheme, "dambreak")) f = step_dambreak;
     else if (!strcmp(scheme, "collision")) f = step_collision;
     else if (!strcmp(scheme, "flow")) f = step_flow;
+    else if (!strcmp(scheme, "aflow")) f = step_aflow;
     if (!f) return -1;
     for (int k = 0; k < nsteps; ++k) f(s);
     return 0;

@@ -77,6 +77,7 @@ _SIGS = {
     "sphmw_generate_mountain_wave": (C.c_int, [_P, C.POINTER(LatticeSetup), C.POINTER(C.c_int64),
                                                C.POINTER(C.c_int64)]),
     "sphmw_flow_add_new_particles": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "sphmw_aflow_add_new_particles": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "sphmw_cell_keys": (C.c_int, [_P, C.c_void_p, C.c_int64]),
     "sphmw_cell_entries": (C.c_int, [_P, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "sphmw_pairs_dump": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
@@ -96,6 +97,7 @@ _SIGS = {
     "sphmw_comm_unique_id": (C.c_int, [C.c_void_p]),
     "sphmw_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_char_p, C.c_int64]),
     "sphmw_comm_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "sphmw_comm_open_box": (C.c_int, [_P, C.c_int32]),
     "sphmw_reduce": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double)]),
     "sphmw_kernel_eval": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]),
     "sphmw_pvd_open": (C.c_int, [_P, C.c_char_p]),

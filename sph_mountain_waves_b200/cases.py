@@ -172,6 +172,68 @@ def flow_2d(n_y: float = 100.0, dom_length: float = 100e3, h_m: float = 13e3, a:
                 fields, dict(dr=dr, dt=dt))
 
 
+def aflow_2d(n_y: float = 100.0, dom_length: float = 100e3, h_m: float = 13e3, a: float = 10e3,
+             U_max: float = 20.0, x_inflow: Optional[float] = None) -> Case:
+    """The adiabatic variant of the flow driver — src/legacy/adiabatic_flow_witch.jl:24-128: the same
+    geometry and particle groups as `flow_2d`, cp = 7 R_mass / 2 (:49), entropy S carried per particle.
+    Fields are what the Particle constructor (:82-91) leaves plus initialize_system! (:134-140); the
+    operator calls that close make_system() (:121-126: find_density!, find_pressure!, find_pot_temp!,
+    find_s!, internal_force!) are the caller's, through the operator menu ("aflow.*").  The packing
+    pre-step (:118) is skipped as in `flow_2d`.  `x_inflow` moves the line behind which INFLOW particles
+    convert (the driver: -dom_length/2), so that a short test meets conversions."""
+    dom_height = 26e3
+    dr = dom_height / n_y
+    h = 1.8 * dr
+    bc_width = 6 * dr
+    rho0, mu = 1.393, 15.98e-6
+    c = math.sqrt(65e3 * (7 / 5) / rho0)
+    N = math.sqrt(0.0196)
+    g, R_mass, R_gas = 9.81, 287.05, 8.314
+    cp = 7 * R_mass / 2
+    cv = cp - R_mass
+    gamma = cp / cv
+    T0 = 250.0
+    dt = 0.01 * h / c
+    FLUID, INFLOW, OUTFLOW, WALL, MOUNTAIN = 0.0, 1.0, 2.0, 3.0, 4.0
+    grid = Grid(dr, "square")
+    L2 = dom_length / 2.0
+    domain = Rectangle(-L2, 0.0, L2, dom_height)
+    fence = BoundaryLayer(domain, grid, bc_width)
+    ground = Specification(fence, lambda x: x[:, 1] < 0)
+    sky = Specification(fence, lambda x: x[:, 1] > dom_height)
+    wind = Specification(fence, lambda x: (x[:, 0] <= -L2) & (x[:, 1] >= 0) & (x[:, 1] <= dom_height))
+    sink = Specification(fence, lambda x: (x[:, 0] >= L2) & (x[:, 1] >= 0) & (x[:, 1] <= dom_height))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mountain = Specification(domain, lambda x: x[:, 1] <= (h_m * a ** 2) / (x[:, 0] ** 2 + a ** 2))
+        groups = [(covering(grid, domain - mountain), FLUID), (covering(grid, mountain), MOUNTAIN),
+                  (covering(grid, wind), INFLOW), (covering(grid, sink), OUTFLOW),
+                  (covering(grid, ground + sky), WALL)]
+    x = np.concatenate([g_[0] for g_ in groups])
+    typ = np.concatenate([np.full(len(g_[0]), g_[1]) for g_ in groups])
+    keep = typ != OUTFLOW                       # :119 filter!
+    x, typ = x[keep], typ[keep]
+    n = len(x)
+    # Particle constructor :82-91 (numpy's exp/log/power stand in for libm's: the tests compare the
+    # device with the oracle on THESE inputs, and check the constructor itself through add_new_particles)
+    T = np.full(n, T0)
+    rho = rho0 * np.exp(-x[:, 1] * g / (R_mass * T))
+    m = rho * dr ** 2
+    P = R_mass * T * rho
+    b = (T0 * R_gas * rho0) / P
+    theta = T * (b * b) ** (1 / 7)
+    S = m * cv * np.log((cv * T * (gamma - 1)) / (gamma * rho ** (gamma - 1)))
+    u = np.zeros((n, 3))
+    u[(typ == FLUID) | (typ == INFLOW), 0] = U_max      # initialize_system! :134-140
+    fields = {"x": x, "v": u, "Dv": np.zeros((n, 3)), "rho": rho, "m": m, "P": P, "theta": theta, "T": T,
+              "S": S, "s": np.zeros(n), "type": typ}
+    params = dict(dt=dt, g=g, c=c, rho0=rho0, R_mass=R_mass, R_gas=R_gas, T_bg=T0, mu=mu, kh=h, gamma=gamma,
+                  z_t=dom_height, z_b=12e3, gamma_r=10 * N, fluid=FLUID, inflow=INFLOW, U_max=U_max, cp=cp,
+                  bc_width=bc_width, x_inflow=-L2 if x_inflow is None else x_inflow, dr=dr)
+    box = (domain + fence).boundarybox()
+    return Case("aflow_2d", "aflow", 2, (box.x1_min, box.x2_min, 0.0), (box.x1_max, box.x2_max, 0.0), h, params,
+                fields, dict(dr=dr, dt=dt))
+
+
 def collapse_dry(dr: float = 1.5e-2) -> Case:
     """BASELINE config 1 (C1) — sph_jl/examples/collapse_dry.jl:30-106."""
     # :42-62

@@ -56,6 +56,8 @@ static const FieldDesc FIELD_TABLE[] = {
     {"A_bg", S_A_BG, 1},
     {"Drho", S_DRHO, 1},
     {"rho0", S_RHO0, 1},
+    {"S", S_ENT, 1},   // adiabatic_flow_witch.jl:75-76
+    {"s", S_ENT_D, 1},
     {nullptr, 0, 0}};
 
 const FieldDesc *sphmw_find_field(const char *name) {
@@ -325,7 +327,7 @@ extern "C" int sphmw_destroy(sphmw_ctx *c) {
         cudaFree(c->cur.s[s]);
         cudaFree(c->alt.s[s]);
     }
-    cudaFree(c->idx); cudaFree(c->idx_alt); cudaFree(c->pos_of_idx);
+    cudaFree(c->idx); cudaFree(c->idx_alt); cudaFree(c->pos_of_idx); cudaFree(c->lost_list);
     cudaFree(c->tag); cudaFree(c->tag_alt); cudaFree(c->halo_counters);
     if (c->h_halo_counters) cudaFreeHost(c->h_halo_counters);
     cudaFree(c->key); cudaFree(c->rank); cudaFree(c->src); cudaFree(c->cellx); cudaFree(c->cellx_alt);
@@ -718,7 +720,12 @@ extern "C" int sphmw_step_phase(sphmw_ctx *c, const char *scheme, int32_t phase)
 extern "C" int sphmw_flow_add_new_particles(sphmw_ctx *c, int64_t *n_added) {
     if (!c) return SPHMW_E_INVALID;
     CUDA_TRY(cudaSetDevice(c->device));
-    return sphmw_flow_add_particles(c, n_added);
+    return sphmw_flow_add_particles(c, n_added, false);
+}
+extern "C" int sphmw_aflow_add_new_particles(sphmw_ctx *c, int64_t *n_added) {
+    if (!c) return SPHMW_E_INVALID;
+    CUDA_TRY(cudaSetDevice(c->device));
+    return sphmw_flow_add_particles(c, n_added, true);
 }
 extern "C" int sphmw_pairs_dump(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n) {
     if (!c || !n) return SPHMW_E_INVALID;

@@ -264,8 +264,8 @@ int sphmw_ensure_pos_of_idx(sphmw_ctx *c) {
 //     particles[removal[i]] = particles[end+1-i]   (removal sorted DESCENDING)
 // touches O(k) slots; we replay it on the host over a sparse map and return
 // the (old index -> new index) moves of the surviving particles.
-static void replay_swap_removal(int64_t N, std::vector<uint32_t> &removed,
-                                std::vector<uint32_t> &mv_old, std::vector<uint32_t> &mv_new) {
+void sphmw_replay_swap_removal(int64_t N, std::vector<uint32_t> &removed,
+                               std::vector<uint32_t> &mv_old, std::vector<uint32_t> &mv_new) {
     std::sort(removed.begin(), removed.end(), [](uint32_t a, uint32_t b) { return a > b; });
     std::unordered_map<uint32_t, uint32_t> occ;  // slot -> current occupant (original index)
     occ.reserve(removed.size() * 2);
@@ -400,7 +400,7 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
                                  cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         std::vector<uint32_t> rem(c->h_removed + 1, c->h_removed + 1 + k), mo, mn;
-        replay_swap_removal(n, rem, mo, mn);
+        sphmw_replay_swap_removal(n, rem, mo, mn);
         const int64_t m = (int64_t)mo.size();
         if (m > 0) {
             if (m > c->mv_cap) {

@@ -23,7 +23,8 @@ template <int DIM>
 __global__ void k_halo_pack(Fields f, const uint32_t *__restrict__ idx, uint32_t *__restrict__ tag,
                             int64_t n, Grid g, int has_left, int has_right, double *buf_l,
                             double *buf_r, uint32_t cap, uint32_t *counters,
-                            const uint32_t *__restrict__ cellx, ColFilter cf) {
+                            const uint32_t *__restrict__ cellx, ColFilter cf, uint32_t *__restrict__ lost_list,
+                            uint32_t lost_cap) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
     if (cf.on && !col_selected(cf, (int)cellx[p])) return;
@@ -36,8 +37,12 @@ __global__ void k_halo_pack(Fields f, const uint32_t *__restrict__ idx, uint32_t
     bool inside = g.box[0] <= x && x <= g.box[3] && g.box[1] <= y && y <= g.box[4] &&
                   g.box[2] <= z && z <= g.box[5];
     if (!inside) {
+        // left the GLOBAL box: removed, as create_cell_list! does (core.jl:60-66).  With an open box
+        // (slab_comm.cu) its global index is kept, because the reference then moves the particles at
+        // the end of sys.particles into the vacated slots (core.jl:72-81)
         tag[p] = TAG_DEAD;
-        atomicAdd(&counters[4], 1u);
+        const uint32_t slot = atomicAdd(&counters[4], 1u);
+        if (lost_list && slot < lost_cap) lost_list[1 + slot] = idx[p];
         return;
     }
     const long long W = g.lim[0];
@@ -159,13 +164,15 @@ static int pack_enqueue(sphmw_ctx *c, double *dev_buf_left, double *dev_buf_righ
         if (c->grid.dim == 2)
             k_halo_pack<2><<<grid_for(c->n, 256), 256, 0, c->stream>>>(
                 view, c->idx, c->tag, c->n, c->grid, has_left, has_right, dev_buf_left,
-                dev_buf_right, (uint32_t)cap_records, c->halo_counters, c->cellx, cf);
+                dev_buf_right, (uint32_t)cap_records, c->halo_counters, c->cellx, cf, c->lost_list, SLAB_LOST_CAP);
         else
             k_halo_pack<3><<<grid_for(c->n, 256), 256, 0, c->stream>>>(
                 view, c->idx, c->tag, c->n, c->grid, has_left, has_right, dev_buf_left,
-                dev_buf_right, (uint32_t)cap_records, c->halo_counters, c->cellx, cf);
+                dev_buf_right, (uint32_t)cap_records, c->halo_counters, c->cellx, cf, c->lost_list, SLAB_LOST_CAP);
         CUDA_TRY(cudaGetLastError());
     }
+    if (c->lost_list)  // word 0 of the list: how many particles this pack dropped
+        CUDA_TRY(cudaMemcpyAsync(c->lost_list, c->halo_counters + 4, sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
     if (msg_left || msg_right) {
         k_halo_header<<<1, 32, 0, c->stream>>>(c->halo_counters, msg_left, msg_right);
         c->launches += 1;

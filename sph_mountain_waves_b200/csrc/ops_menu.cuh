@@ -309,6 +309,53 @@ struct U_flow_accelerate {
         }
     }
 };
+// ---- src/legacy/adiabatic_flow_witch.jl (u in v, Du in Dv, T0 = T_bg, h = kh, cv = cp - R_mass) ----
+// accelerate! (:225-229) is U_flow_accelerate, internal_force! (:146-153) is B_flow_force.
+// move!  :217-223
+struct U_aflow_move {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        FLD(S_DV0) = 0.0;
+        FLD(S_DV1) = 0.0;
+        if (DIM == 3) FLD(S_DV2) = 0.0;
+        if (FLD(S_TYPE) == c.fluid) {
+            FLD(S_X0) += c.dt * FLD(S_V0);
+            FLD(S_X1) += c.dt * FLD(S_V1);
+            if (DIM == 3) FLD(S_X2) += c.dt * FLD(S_V2);
+            FLD(S_RHO) = 0.0;
+        }
+    }
+};
+// find_s!  :165-169
+struct U_aflow_find_s {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        if (FLD(S_TYPE) == c.fluid) FLD(S_ENT_D) = FLD(S_ENT) * FLD(S_RHO) / FLD(S_M);
+    }
+};
+// find_pressure!  :171-176
+struct U_aflow_find_pressure {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        if (FLD(S_TYPE) == c.fluid) {
+            const double cv = c.cp - c.R_mass;
+            const double rho = FLD(S_RHO);
+            const double T = (pow(rho, c.gamma - 1.0)) * exp(FLD(S_ENT_D) / (rho * cv)) / (cv * (c.gamma - 1.0));
+            FLD(S_T) = T;
+            FLD(S_P) = c.R_mass * rho * T;
+        }
+    }
+};
+// find_pot_temp!  :178-182
+struct U_aflow_find_pot_temp {
+    template <int DIM>
+    static __device__ void apply(const Fields &f, const Params &c, int64_t p) {
+        if (FLD(S_TYPE) == c.fluid) {
+            const double b = (c.T_bg * c.R_gas * c.rho0) / FLD(S_P);
+            FLD(S_TH) = FLD(S_T) * pow(b * b, 1.0 / 7.0);
+        }
+    }
+};
 #undef FLD
 
 // ===========================================================================
@@ -634,6 +681,54 @@ struct B_flow_mass : PairOpBase {
         PF(S_DRHO) = drho;
     }
 };
+// find_density!  adiabatic_flow_witch.jl:159-163 (the driver applies it with self = true)
+struct B_aflow_density : PairOpBase {
+    double rho;
+    bool fluid;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &c, int64_t p) {
+        rho = PF(S_RHO);
+        fluid = PF(S_TYPE) == c.fluid;
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double, double, double, double r) {
+        if (fluid && QF(S_TYPE) == c.fluid) rho += QF(S_M) * wendland2(c.kh, r);
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_RHO) = rho;
+    }
+};
+// entropy_production!  adiabatic_flow_witch.jl:184-191
+struct B_aflow_entropy : PairOpBase {
+    double S, v0, v1, v2, m, T, rho;
+    bool fluid;
+    template <int DIM>
+    __device__ void init(const Fields &f, const Params &c, int64_t p) {
+        S = PF(S_ENT);
+        v0 = PF(S_V0);
+        v1 = PF(S_V1);
+        v2 = DIM == 3 ? PF(S_V2) : 0.0;
+        m = PF(S_M);
+        T = PF(S_T);
+        rho = PF(S_RHO);
+        fluid = PF(S_TYPE) == c.fluid;
+    }
+    template <int DIM>
+    __device__ void pair(const Fields &f, const Params &c, int64_t, int64_t q, double dx, double dy, double dz,
+                         double r) {
+        if (fluid && QF(S_TYPE) == c.fluid) {
+            double ker = rDwendland2(c.kh, r);
+            double d = (v0 - QF(S_V0)) * dx + (v1 - QF(S_V1)) * dy;  // dot(u_pq, x_pq)
+            if (DIM == 3) d = d + (v2 - QF(S_V2)) * dz;
+            S += -4.0 * m * QF(S_M) * ker * c.mu / (T * rho * QF(S_RHO)) * (d * d) / (r * r + 0.01 * c.kh * c.kh) * c.dt;
+        }
+    }
+    template <int DIM>
+    __device__ void finish(const Fields &f, const Fields &, const Params &, int64_t p) {
+        PF(S_ENT) = S;
+    }
+};
 // internal_force!  isothermal_flow_witch.jl:145-150
 struct B_flow_force : PairOpBase {
     double dv0, dv1, dv2, v0, v1, v2, P, rho;
@@ -886,6 +981,12 @@ struct B_force_kick_fused : Force {
     U("flow.find_pot_temp", U_flow_find_pot_temp, SL(S_P), SL(S_TH),) \
     U("flow.move", U_flow_move, SL(S_TYPE, S_V0), SL(S_X0, S_DV0), (c->cell_list_valid = false, c->dv_zero = true)) \
     U("flow.accelerate", U_flow_accelerate, SL(S_TYPE, S_X0, S_DV0), SL(S_V0),) \
+    B("aflow.find_density", B_aflow_density, SL(S_X0, S_M, S_TYPE, S_RHO), SL(S_RHO),) \
+    B("aflow.entropy_production", B_aflow_entropy, SL(S_X0, S_V0, S_M, S_TYPE, S_T, S_RHO, S_ENT), SL(S_ENT),) \
+    U("aflow.find_s", U_aflow_find_s, SL(S_TYPE, S_ENT, S_RHO, S_M), SL(S_ENT_D),) \
+    U("aflow.find_pressure", U_aflow_find_pressure, SL(S_TYPE, S_RHO, S_ENT_D), SL(S_T, S_P),) \
+    U("aflow.find_pot_temp", U_aflow_find_pot_temp, SL(S_TYPE, S_P, S_T), SL(S_TH),) \
+    U("aflow.move", U_aflow_move, SL(S_TYPE, S_V0), SL(S_X0, S_DV0, S_RHO), (c->cell_list_valid = false, c->dv_zero = true)) \
     U("packing.reset_rho", U_pack_reset_rho, SL(S_TYPE), SL(S_RHO),) \
     B("packing.accumulate_rho", B_pack_rho, SL(S_X0, S_M, S_H, S_TYPE), SL(S_RHO),) \
     B("packing.balance_of_momentum", B_pack_momentum, SL(S_X0, S_M, S_H, S_TYPE, S_RHO), SL(S_DV0), c->dv_zero = false) \

@@ -670,7 +670,8 @@ __global__ void k_flow_flag(Fields f, Params c, const uint32_t *__restrict__ idx
 
 // One thread per old particle; a converting particle creates its successor at index
 // n + (number of converting particles with a smaller index): the order of the reference's loop.
-template <int DIM>
+// ADIABATIC: the constructor of src/legacy/adiabatic_flow_witch.jl:82-91 (T = T0, entropy from T and rho)
+template <int DIM, bool ADIABATIC>
 __global__ void k_flow_spawn(Fields f, Params c, uint32_t *__restrict__ idx,
                              uint32_t *__restrict__ pos_of_idx, uint32_t *__restrict__ tag, int64_t n,
                              const uint32_t *__restrict__ rank_by_idx) {
@@ -688,23 +689,35 @@ __global__ void k_flow_spawn(Fields f, Params c, uint32_t *__restrict__ idx,
     f.s[S_V1][s] = c.U_max * 0.0;
     if (DIM == 3) f.s[S_V2][s] = c.U_max * 0.0;
     const double rho = c.rho0 * exp(-y * c.g / (c.R_mass * c.T_bg));
-    const double P = rho * c.T_bg * c.R_mass;
     f.s[S_RHO][s] = rho;
-    f.s[S_M][s] = rho * sph_pow2(c.dr);
-    f.s[S_P][s] = P;
-    f.s[S_TH][s] = c.T_bg * pow((c.T_bg * c.R_gas * c.rho0) / P, c.R_gas / c.cp);
+    const double m = rho * sph_pow2(c.dr);
+    f.s[S_M][s] = m;
+    if (ADIABATIC) {
+        const double T = c.T_bg, cv = c.cp - c.R_mass;
+        const double P = c.R_mass * T * rho;
+        const double b = (c.T_bg * c.R_gas * c.rho0) / P;
+        f.s[S_T][s] = T;
+        f.s[S_P][s] = P;
+        f.s[S_TH][s] = T * pow(b * b, 1.0 / 7.0);
+        f.s[S_ENT][s] = m * cv * log((cv * T * (c.gamma - 1.0)) / (c.gamma * pow(rho, c.gamma - 1.0)));
+    } else {
+        const double P = rho * c.T_bg * c.R_mass;
+        f.s[S_P][s] = P;
+        f.s[S_TH][s] = c.T_bg * pow((c.T_bg * c.R_gas * c.rho0) / P, c.R_gas / c.cp);
+    }
     f.s[S_TYPE][s] = c.inflow;
     idx[s] = (uint32_t)s;
     pos_of_idx[s] = (uint32_t)s;
     tag[s] = TAG_OWNED;
 }
 
-int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added) {
+int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added, bool adiabatic) {
     if (n_added) *n_added = 0;
     if (c->slab_lo >= 0) { sphmw_set_error("add_new_particles: whole-domain contexts only"); return SPHMW_E_STATE; }
     const int64_t n = c->n;
     if (n == 0) return SPHMW_OK;
     TRY(need_slots(c, SL(S_X0, S_V0, S_TYPE, S_RHO, S_M, S_P, S_TH), SL(S_X0, S_V0, S_TYPE, S_RHO, S_M, S_P, S_TH)));
+    if (adiabatic) TRY(need_slots(c, SL(S_T, S_ENT), SL(S_T, S_ENT)));
     uint32_t *flags = c->rank;  // scratch of the cell-list build, free between builds
     {
         TIMED(c, "flow.flag_inflow");
@@ -729,10 +742,15 @@ int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added) {
         if (c->allocated[s]) CUDA_TRY(cudaMemsetAsync(c->cur.s[s] + n, 0, sizeof(double) * m, c->stream));
     {
         TIMED(c, "flow.spawn_inflow");
-        if (c->grid.dim == 2)
-            k_flow_spawn<2><<<grid_for(n, 256), 256, 0, c->stream>>>(c->cur, c->prm, c->idx, c->pos_of_idx, c->tag, n, flags);
-        else
-            k_flow_spawn<3><<<grid_for(n, 256), 256, 0, c->stream>>>(c->cur, c->prm, c->idx, c->pos_of_idx, c->tag, n, flags);
+#define SPAWN(D, A) k_flow_spawn<D, A><<<grid_for(n, 256), 256, 0, c->stream>>>(c->cur, c->prm, c->idx, c->pos_of_idx, c->tag, n, flags)
+        if (c->grid.dim == 2) {
+            if (adiabatic) SPAWN(2, true);
+            else SPAWN(2, false);
+        } else {
+            if (adiabatic) SPAWN(3, true);
+            else SPAWN(3, false);
+        }
+#undef SPAWN
     }
     CUDA_TRY(cudaGetLastError());
     c->n = n + m;
@@ -1167,9 +1185,15 @@ int sphmw_step_scheme(sphmw_ctx *c, const char *scheme, int nsteps) {
         } else if (!strcmp(scheme, "flow")) {
             // isothermal_flow_witch.jl:221-232
             TRY(apply_seq(c, {"flow.accelerate", "flow.move"}));
-            TRY(sphmw_flow_add_particles(c, nullptr));
+            TRY(sphmw_flow_add_particles(c, nullptr, false));
             TRY(apply_seq(c, {"create_cell_list", "flow.balance_of_mass", "flow.find_pressure",
                               "flow.find_pot_temp", "flow.internal_force", "flow.accelerate"}));
+        } else if (!strcmp(scheme, "aflow")) {
+            // adiabatic_flow_witch.jl:231-243
+            TRY(apply_seq(c, {"flow.accelerate", "aflow.move"}));
+            TRY(sphmw_flow_add_particles(c, nullptr, true));
+            TRY(apply_seq(c, {"create_cell_list", "+aflow.find_density", "aflow.find_s", "aflow.find_pressure",
+                              "aflow.entropy_production", "flow.internal_force", "flow.accelerate"}));
         } else if (!strcmp(scheme, "collision")) {
             // test_collision_2d.jl:106-116
             TRY(apply_seq(c, {"collision.accelerate", "collision.move", "create_cell_list",

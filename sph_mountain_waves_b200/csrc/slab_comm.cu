@@ -21,6 +21,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <utility>
+#include <vector>
 
 #include "sphmw_internal.h"
 
@@ -31,6 +33,8 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -60,6 +64,8 @@ static int nccl_load() {
     NCCL_SYM(CommDestroy, "ncclCommDestroy")
     NCCL_SYM(Send, "ncclSend")
     NCCL_SYM(Recv, "ncclRecv")
+    NCCL_SYM(AllGather, "ncclAllGather")
+    NCCL_SYM(AllReduce, "ncclAllReduce")
     NCCL_SYM(GroupStart, "ncclGroupStart")
     NCCL_SYM(GroupEnd, "ncclGroupEnd")
     NCCL_SYM(GetErrorString, "ncclGetErrorString")
@@ -90,6 +96,15 @@ struct SlabComm {
     cudaEvent_t recv_event = nullptr;
     int64_t exchanges = 0, renegotiations = 0;
     int64_t lost = 0;
+    // open box (sphmw_comm_open_box): particles may leave the global bounding box; every exchange
+    // gathers the dropped global indices of all ranks and replays the reference's swap-from-end
+    // renumbering (core.jl:72-81) on every rank
+    bool open_box = false;
+    int64_t n_global = -1;           // length of sys.particles; found with an all-reduce at the first exchange
+    uint32_t *gather_dev = nullptr;  // world x (1 + SLAB_LOST_CAP) words
+    uint32_t *gather_host = nullptr; // pinned
+    long long *count_dev = nullptr;  // all-reduce scratch
+    int64_t renumbered = 0;          // survivors that changed their index so far
 };
 
 extern "C" int sphmw_comm_unique_id(void *id128) {
@@ -112,6 +127,9 @@ void sphmw_comm_free(sphmw_ctx *c) {
         cudaFree(m->recv[s]);
     }
     if (m->h_head) cudaFreeHost(m->h_head);
+    if (m->gather_host) cudaFreeHost(m->gather_host);
+    cudaFree(m->gather_dev);
+    cudaFree(m->count_dev);
     if (m->recv_event) cudaEventDestroy(m->recv_event);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -259,10 +277,114 @@ static int comm_transfer_and_unpack(sphmw_ctx *c) {
     return SPHMW_OK;
 }
 
+// ---- open box -----------------------------------------------------------------------------------
+// ≙ the removal part of create_cell_list! (core.jl:60-81) on a slab decomposition.  Collective.
+// After it every exchange is followed by the renumbering below and sphmw_step runs the plain
+// schedule (the overlapped one packs the edge columns before the interior has drifted, so it
+// cannot see an interior particle leave through the top or the sides of the box).
+extern "C" int sphmw_comm_open_box(sphmw_ctx *c, int32_t on) {
+    if (!c || !c->comm) { sphmw_set_error("comm_open_box: context has no communicator (sphmw_comm_init)"); return SPHMW_E_STATE; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    SlabComm *m = c->comm;
+    m->open_box = on != 0;
+    if (m->open_box && !m->gather_dev) {
+        const size_t words = (size_t)m->world * (1 + SLAB_LOST_CAP);
+        CUDA_TRY(cudaMalloc(&m->gather_dev, sizeof(uint32_t) * words));
+        CUDA_TRY(cudaMallocHost(&m->gather_host, sizeof(uint32_t) * words));
+        CUDA_TRY(cudaMalloc(&m->count_dev, sizeof(long long) * 2));
+        CUDA_TRY(cudaMalloc(&c->lost_list, sizeof(uint32_t) * (1 + SLAB_LOST_CAP)));
+        CUDA_TRY(cudaMemsetAsync(c->lost_list, 0, sizeof(uint32_t) * (1 + SLAB_LOST_CAP), c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return SPHMW_OK;
+}
+
+// idx[p] is looked up in the sorted list of indices that move (a handful per step)
+__global__ void k_renumber_sorted(uint32_t *__restrict__ idx, int64_t n, const uint32_t *__restrict__ mv_old,
+                                  const uint32_t *__restrict__ mv_new, int m) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t id = idx[p];
+    int lo = 0, hi = m;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (mv_old[mid] < id) lo = mid + 1;
+        else hi = mid;
+    }
+    if (lo < m && mv_old[lo] == id) idx[p] = mv_new[lo];
+}
+
+// length of sys.particles = the owned particles of all ranks (called when nothing is in flight)
+static int comm_count_global(sphmw_ctx *c) {
+    SlabComm *m = c->comm;
+    const long long mine = c->n_owned;
+    CUDA_TRY(cudaMemcpyAsync(m->count_dev, &mine, sizeof(mine), cudaMemcpyHostToDevice, m->stream));
+    NCCL_TRY(g_nccl.AllReduce(m->count_dev, m->count_dev + 1, 1, ncclInt64, ncclSum, m->comm, m->stream));
+    long long total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, m->count_dev + 1, sizeof(total), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    m->n_global = total;
+    return SPHMW_OK;
+}
+
+// after an exchange: which particles did the ranks drop, and who moves into their slots
+static int comm_renumber_lost(sphmw_ctx *c) {
+    SlabComm *m = c->comm;
+    const size_t block = 1 + SLAB_LOST_CAP;
+    // (the comm stream has waited for the pack; the lists were complete before pack_event)
+    NCCL_TRY(g_nccl.AllGather(c->lost_list, m->gather_dev, block, ncclUint32, m->comm, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(m->gather_host, m->gather_dev, sizeof(uint32_t) * block * m->world, cudaMemcpyDeviceToHost,
+                             m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    std::vector<uint32_t> removed;
+    for (int r = 0; r < m->world; ++r) {
+        const uint32_t *b = m->gather_host + (size_t)r * block;
+        if (b[0] > SLAB_LOST_CAP) {
+            sphmw_set_error("open box: rank %d lost %u particles in one step (at most %u are tracked)", r, b[0], SLAB_LOST_CAP);
+            return SPHMW_E_CAPACITY;
+        }
+        removed.insert(removed.end(), b + 1, b + 1 + b[0]);
+    }
+    if (removed.empty()) return SPHMW_OK;
+    std::vector<uint32_t> mo, mn;
+    sphmw_replay_swap_removal(m->n_global, removed, mo, mn);
+    m->n_global -= (int64_t)removed.size();
+    const int64_t k = (int64_t)mo.size();
+    if (k == 0 || c->n == 0) return SPHMW_OK;
+    std::vector<std::pair<uint32_t, uint32_t>> mv(k);
+    for (int64_t i = 0; i < k; ++i) mv[i] = {mo[i], mn[i]};
+    std::sort(mv.begin(), mv.end());
+    for (int64_t i = 0; i < k; ++i) {
+        mo[i] = mv[i].first;
+        mn[i] = mv[i].second;
+    }
+    if (k > c->mv_cap) {
+        cudaFree(c->mv_old);
+        cudaFree(c->mv_new);
+        c->mv_old = c->mv_new = nullptr;
+        c->mv_cap = k * 2;
+        CUDA_TRY(cudaMalloc(&c->mv_old, sizeof(uint32_t) * c->mv_cap));
+        CUDA_TRY(cudaMalloc(&c->mv_new, sizeof(uint32_t) * c->mv_cap));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->mv_old, mo.data(), sizeof(uint32_t) * k, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->mv_new, mn.data(), sizeof(uint32_t) * k, cudaMemcpyHostToDevice, c->stream));
+    {
+        TIMED(c, "slab_renumber");
+        k_renumber_sorted<<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->idx, c->n, c->mv_old, c->mv_new, (int)k);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));  // mo/mn must outlive the copies
+    m->renumbered += k;
+    return SPHMW_OK;
+}
+
 static int comm_exchange_all(sphmw_ctx *c) {
     SlabComm *m = c->comm;
+    if (m->open_box && m->n_global < 0) TRY(comm_count_global(c));
     TRY(sphmw_halo_pack_enqueue(c, m->send[0], m->send[1], m->cap, false));
-    return comm_transfer_and_unpack(c);
+    TRY(comm_transfer_and_unpack(c));
+    if (m->open_box) TRY(comm_renumber_lost(c));
+    return SPHMW_OK;
 }
 
 // ≙ create_cell_list!(sys) on a slab context: halo exchange, then the sort
@@ -282,7 +404,7 @@ int sphmw_comm_step(sphmw_ctx *c, const char *scheme, int nsteps) {
         return SPHMW_E_UNSUPPORTED_OP;
     }
     if (nsteps <= 0) return SPHMW_OK;
-    const bool overlap = nsteps > 1 && !(c->flags & SPHMW_FLAG_CELL_PAIRS) && !getenv("SPHMW_NO_OVERLAP");
+    const bool overlap = nsteps > 1 && !(c->flags & SPHMW_FLAG_CELL_PAIRS) && !m->open_box && !getenv("SPHMW_NO_OVERLAP");
     if (!overlap) {
         for (int k = 0; k < nsteps; ++k) {
             TRY(sphmw_step_wcsph_phase(c, 0));

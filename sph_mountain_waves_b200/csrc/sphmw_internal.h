@@ -32,6 +32,7 @@ enum Slot : int {
     S_DRHO, S_RHO0,
     S_PR2,  // P'/max(rho,floor)^2            (wcsph_perturbed_witch.jl:272)
     S_CS,   // sqrt(gamma*P/max(rho,floor))   (wcsph_perturbed_witch.jl:276)
+    S_ENT, S_ENT_D,  // entropy S and entropy density s (legacy/adiabatic_flow_witch.jl:75-76)
     NSLOT
 };
 
@@ -163,6 +164,7 @@ __device__ __forceinline__ bool neighbour_pkey(const Grid &g, const CellCoord &c
 #define HALO_RECORD 13  // x0 x1 x2 v0 v1 v2 m h rho rho_p type idx kind
 #define HALO_KIND_MIGRANT 0.0
 #define HALO_KIND_GHOST 1.0
+#define SLAB_LOST_CAP 4096u  // particles one rank may lose to the global box in one step (open box, slab_comm.cu)
 
 // which cell columns a pass evaluates (slab mode): [a0,a1] U [b0,b1]; `copy` = particles outside
 // the set carry double-buffered outputs over (B_*::skip)
@@ -344,6 +346,7 @@ struct sphmw_ctx {
     int64_t slab_check_want[4][2] = {};           // the host's figures for the same builds
     uint64_t slab_checks = 0;
     struct SlabComm *comm = nullptr;              // NCCL halo transport (slab_comm.cu)
+    uint32_t *lost_list = nullptr;                // open box: [0] count, [1..] global indices the last pack dropped
     struct FrameAsync *frame_async = nullptr;     // asynchronous frame output / upload prefetch (frame_async.cu)
     uint32_t *halo_counters = nullptr;            // device: [0] left records [1] right records
                                                   // [2] left migrants [3] right migrants [4] lost
@@ -450,6 +453,10 @@ void sphmw_derive_params(Params &p);
 int sphmw_grid_setup(Grid &g, const double box_min[3], const double box_max[3], double h, int64_t slab_lo,
                      int64_t slab_hi, int64_t *global_cols);
 void sphmw_grid_set_order(Grid &g, bool zrun);  // physical cell order (Grid::zrun)
+// core.jl:72-81 on index space: the (old index -> new index) moves of the survivors when the
+// particles `removed` (any order) leave an array of N (cell_list.cu)
+void sphmw_replay_swap_removal(int64_t N, std::vector<uint32_t> &removed, std::vector<uint32_t> &mv_old,
+                               std::vector<uint32_t> &mv_new);
 // implemented in cell_list.cu
 int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive);
 int sphmw_ensure_slot(sphmw_ctx *c, int slot);
@@ -461,7 +468,7 @@ int sphmw_step_scheme_phase(sphmw_ctx *c, const char *scheme, int phase);
 int sphmw_materialize(sphmw_ctx *c, int slot);
 int64_t sphmw_list_ops(char *buf, int64_t cap);
 int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n);
-int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added);
+int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added, bool adiabatic);
 int sphmw_pair_list_stats(sphmw_ctx *c, int64_t out[4]);
 int sphmw_tile_stats(sphmw_ctx *c, int64_t out[6]);
 int sphmw_ensure_records(sphmw_ctx *c);  // api.cu: allocate the packed neighbour records

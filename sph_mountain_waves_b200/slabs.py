@@ -89,7 +89,10 @@ class SlabPlan:
         return xa, xb
 
     def owns(self, x0: np.ndarray) -> np.ndarray:
-        c = column_of(x0, self.h, self.phase0)
+        # a particle beyond the box along x still belongs to somebody — the outermost rank — until the
+        # first create_cell_list! removes it (core.jl:60-81: its slot is refilled from the end of
+        # sys.particles, which renumbers survivors)
+        c = np.clip(column_of(x0, self.h, self.phase0), 0, self.ncols - 1)
         return (c >= self.lo) & (c < self.hi)
 
 
@@ -399,7 +402,7 @@ class SlabRun:
             torch.cuda.current_stream(b.dev).synchronize()
 
     # ------------------------------------------------------------------ transport inside the library
-    def use_library_transport(self, halo_capacity: Optional[int] = None):
+    def use_library_transport(self, halo_capacity: Optional[int] = None, open_box: bool = False):
         """Hand the halo exchange to libsphmw (csrc/slab_comm.cu: ncclSend/ncclRecv on its own
         stream, driven by sphmw_step / sphmw_create_cell_list).  Collective over torch.distributed:
         rank 0 creates the NCCL id, everybody joins."""
@@ -419,6 +422,10 @@ class SlabRun:
         dist.all_reduce(cap, op=dist.ReduceOp.MAX)   # the same capacity on every rank
         raw = bytes(ident.cpu().tolist())
         check(lib.sphmw_comm_init(self.sys.ctx, self.plan.rank, self.plan.world, raw, int(cap.item())))
+        if open_box:
+            # particles may leave the global box: the library replays the reference's swap-from-end
+            # renumbering (core.jl:72-81) across ranks after every exchange
+            check(lib.sphmw_comm_open_box(self.sys.ctx, 1))
         self._lib_comm = True
         return self
 

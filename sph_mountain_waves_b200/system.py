@@ -29,7 +29,7 @@ from .geometry import Shape
 FIELD_NCOMP: Dict[str, int] = {
     "h": 1, "x": 3, "m": 1, "v": 3, "Dv": 3, "rho_bg": 1, "rho_p": 1, "rho": 1, "P_bg": 1,
     "P_p": 1, "P": 1, "theta_bg": 1, "theta_p": 1, "theta": 1, "T_bg": 1, "T_p": 1, "T": 1,
-    "type": 1, "A": 1, "A_bg": 1, "Drho": 1, "rho0": 1,
+    "type": 1, "A": 1, "A_bg": 1, "Drho": 1, "rho0": 1, "S": 1, "s": 1,
 }
 ALIASES = {"ρ_bg": "rho_bg", "ρ′": "rho_p", "ρ": "rho", "P′": "P_p", "θ_bg": "theta_bg",
            "θ′": "theta_p", "θ": "theta", "T′": "T_p", "a": "Dv", "u": "v"}
@@ -275,6 +275,13 @@ class ParticleSystem:
         self._flush()
         n = C.c_int64()
         check(_capi.lib().sphmw_flow_add_new_particles(self.ctx, C.byref(n)))
+        return n.value
+
+    def aflow_add_new_particles(self) -> int:
+        """≙ add_new_particles!(sys) — src/legacy/adiabatic_flow_witch.jl:197-208"""
+        self._flush()
+        n = C.c_int64()
+        check(_capi.lib().sphmw_aflow_add_new_particles(self.ctx, C.byref(n)))
         return n.value
 
     def set_flags(self, flags: int):

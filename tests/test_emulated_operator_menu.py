@@ -37,7 +37,7 @@ FIELD_SLOT = {"h": ("S_H", 1), "x": ("S_X0", 3), "m": ("S_M", 1), "v": ("S_V0", 
               "P_p": ("S_P_P", 1), "P": ("S_P", 1), "theta_bg": ("S_TH_BG", 1), "theta_p": ("S_TH_P", 1),
               "theta": ("S_TH", 1), "T_bg": ("S_T_BG", 1), "T_p": ("S_T_P", 1), "T": ("S_T", 1),
               "type": ("S_TYPE", 1), "A": ("S_A", 1), "A_bg": ("S_A_BG", 1), "Drho": ("S_DRHO", 1),
-              "rho0": ("S_RHO0", 1)}
+              "rho0": ("S_RHO0", 1), "S": ("S_ENT", 1), "s": ("S_ENT_D", 1)}
 
 # the operator sequences of one verlet_step! per scheme (csrc/pair_ops.cu sphmw_step_scheme)
 WCSPH = ["wcsph.accelerate", "wcsph.move", "create_cell_list", "wcsph.reset_density", "wcsph.compute_density",
@@ -66,6 +66,10 @@ SEQUENCES = {
                 "packing.move", "create_cell_list"],
     "flow": ["flow.accelerate", "flow.move", "create_cell_list", "flow.balance_of_mass", "flow.find_pressure",
              "flow.find_pot_temp", "flow.internal_force", "flow.accelerate"],
+    # src/legacy/adiabatic_flow_witch.jl:231-243 (add_new_particles! is host logic around a device kernel:
+    # tests/test_gpu_more_schemes.py)
+    "aflow": ["flow.accelerate", "aflow.move", "create_cell_list", "+aflow.find_density", "aflow.find_s",
+              "aflow.find_pressure", "aflow.entropy_production", "flow.internal_force", "flow.accelerate"],
 }
 
 
@@ -147,9 +151,13 @@ CASES = {
     "dambreak": lambda: cases.collapse_dry(dr=4e-2),
     "collision": cases.collision_2d,
     "flow": lambda: cases.flow_2d(n_y=20.0, dom_length=30e3, h_m=4e3, a=4e3, U_max=40.0),
+    "aflow": lambda: cases.aflow_2d(n_y=20.0, dom_length=30e3, h_m=4e3, a=4e3, U_max=40.0),
 }
 # what the drivers run once before the time loop
 PROLOGUE = {"dambreak": ["dambreak.internal_force"],
+            # what closes make_system() of the adiabatic driver (:121-126)
+            "aflow": ["aflow.find_density", "aflow.find_pressure", "aflow.find_pot_temp", "aflow.find_s",
+                      "flow.internal_force"],
             "collision": ["+collision.find_rho0", "+collision.find_rho", "collision.find_pressure",
                           "collision.internal_force"]}
 

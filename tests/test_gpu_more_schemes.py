@@ -236,6 +236,50 @@ def test_flow_with_inflow_and_outflow(gpu):
         assert field_err(case, f, s.field(f), o.field(f)) <= TOL, f
 
 
+def test_adiabatic_flow_with_inflow_and_outflow(gpu):
+    """src/legacy/adiabatic_flow_witch.jl: entropy carried per particle (find_s!, find_pressure!,
+    entropy_production!), density by summation over FLUID pairs with self = true, inflow re-seeding with
+    the adiabatic Particle constructor (:82-91).  The conversion line is moved 2.5 dr into the inflow
+    layer so that the first steps convert particles; their successors are born upstream of the
+    bounding box and leave through removal.  The device follows the oracle operator by operator, then
+    through sphmw_step("aflow")."""
+    case = cases.aflow_2d(n_y=20.0, dom_length=30e3, h_m=4e3, a=4e3, U_max=40.0)
+    case.params["x_inflow"] = -15e3 - 2.5 * case.info["dr"]
+    o, s = load_oracle(case), load_gpu(case, capacity=2 * case.n)
+    assert o.create_cell_list() == s.create_cell_list() == case.n
+    for sysm in (o, s):  # make_system :121-126
+        for op in ("aflow.find_density", "aflow.find_pressure", "aflow.find_pot_temp", "aflow.find_s",
+                   "flow.internal_force"):
+            sysm.apply(op)
+    for f in ("rho", "T", "P", "theta", "s", "Dv"):
+        assert field_err(case, f, s.field(f), o.field(f)) <= TOL, f
+    added = removed = 0
+    for k in range(6):
+        for sysm in (o, s):
+            sysm.apply("flow.accelerate")
+            sysm.apply("aflow.move")
+        a_o, a_s = o.aflow_add_new_particles(), s.aflow_add_new_particles()
+        assert a_o == a_s
+        added += a_s
+        before = len(s)
+        assert o.create_cell_list() == s.create_cell_list()
+        removed += before - len(s)
+        for sysm in (o, s):
+            sysm.apply("aflow.find_density", True)
+            for op in ("aflow.find_s", "aflow.find_pressure", "aflow.entropy_production", "flow.internal_force",
+                       "flow.accelerate"):
+                sysm.apply(op)
+        assert np.array_equal(s.field("type"), o.field("type"))
+        for f in ("x", "v", "rho", "P", "T", "S", "s", "m"):
+            assert field_err(case, f, s.field(f), o.field(f)) <= TOL, (k, f)
+    assert added > 0 and removed > 0, (added, removed)
+    o.step("aflow", 3)
+    s.step(3, "aflow")
+    assert len(s) == len(o)
+    for f in ("x", "v", "rho", "S", "T"):
+        assert field_err(case, f, s.field(f), o.field(f)) <= TOL, f
+
+
 def test_packing_driver_loop(gpu):
     """≙ packing!(sys) — src/utils/new_packing.jl:64-140, against the same loop on the oracle"""
     from sph_mountain_waves_b200.schemes.new_packing import packing, packing_params

@@ -31,3 +31,19 @@ def test_nccl_transports_match_the_whole_domain_run(world, flags):
            str(ROOT / "tests" / "mp" / "slab_nccl_worker.py"), "12", str(flags)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(ROOT))
     assert r.returncode == 0 and "SLAB_NCCL_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_open_box_removal_renumbers_like_the_reference(world):
+    """particles leave the global box on several ranks (downstream face, top): the library transport
+    replays create_cell_list!'s swap-from-end removal (src/core.jl:72-81) across ranks, so indices
+    and every field match the whole-domain run bit for bit (tests/mp/slab_open_box_worker.py)"""
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 31500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           str(ROOT / "tests" / "mp" / "slab_open_box_worker.py"), "14", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+    assert r.returncode == 0 and "SLAB_OPEN_BOX_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
