@@ -312,9 +312,10 @@ def run_ours(args):
         try:
             pk = json.loads((ROOT / "profiles" / "r02_final_fp64_peak.json").read_text())
             fp64 = {"peak_tflops_measured": pk["fp64_peak_tflops"], "dfma_per_clk_per_sm": pk["dfma_per_clk_per_sm"],
-                    "pipe_busy_frac_ncu": 0.454 if not (args.flags & 1) else 0.350,
-                    "source": "profiles/r02_final_fp64_peak.json, profiles/r02_ncu_shipped_64M_strict.txt "
-                              "(sm__inst_executed_pipe_fp64, 64 M particles strict; fast: 9 M particles)"}
+                    "pipe_busy_frac_ncu": 0.447 if not (args.flags & 1) else 0.350,
+                    "source": "profiles/r02_final_fp64_peak.json, profiles/r02b_ncu_final_64M_strict.txt "
+                              "(sm__inst_executed_pipe_fp64, 64 M particles strict; fast: 9 M particles, "
+                              "profiles/r02_ncu_records_8M_fast.txt)"}
         except Exception:
             pass
         roofline = {

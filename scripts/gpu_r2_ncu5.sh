@@ -1,0 +1,6 @@
+set -x
+cd $GRAFT_REPO_ROOT
+CMD="python bench.py --flags 0 --no-cpu-baseline --no-e2e --no-strict --steps 3 --warmup 1 --device-gen"
+$CMD > gpurun_out/r2z_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_binary_ -s 2 -c 2 -o gpurun_out/r2z_final64M $CMD > gpurun_out/r2z_ncu.log 2>&1
+echo "ncu rc=$?"; tail -3 gpurun_out/r2z_ncu.log
+$CMD > gpurun_out/r2z_plain2.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2z_launches_64M.csv $CMD > gpurun_out/r2z_ncu2.log 2>&1; echo "launch list rc=$?"

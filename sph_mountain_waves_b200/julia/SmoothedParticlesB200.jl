@@ -72,7 +72,9 @@ Same contract as structs.jl:43-92: particles of type `T`, removed once outside t
 `domain`, neighbours within `h`.  Keywords (all optional, none exists in the reference):
 `capacity` (device slots; default: grown on demand at the first upload), `device`, `flags`
 (SPHMW_FLAG_*), and for x-slabs over several GPUs `rank`, `world`, `nccl_id` (128 bytes from
-`comm_unique_id()`, the same on every rank), `halo_capacity`.
+`comm_unique_id()`, the same on every rank), `halo_capacity`, `open_box` (particles may leave the
+bounding box: the library then replays the swap-from-end renumbering of core.jl:72-81 across ranks
+after every halo exchange, `sphmw_comm_open_box`).
 """
 mutable struct ParticleSystem{T<:AbstractParticle}
     h::Float64
@@ -87,12 +89,12 @@ mutable struct ParticleSystem{T<:AbstractParticle}
     device::Int
     flags::Int
     slab::NTuple{2,Int64}
-    comm::Any                 # (rank, world, id, halo_capacity) or nothing
+    comm::Any                 # (rank, world, id, halo_capacity, open_box) or nothing
     host_touched::Bool        # host objects may differ from the device: upload before the next device call
     device_ahead::Bool        # device state is newer than the host objects
     function ParticleSystem(T::DataType, domain::Shape, h::Float64; capacity::Integer=0, device::Integer=0,
                             flags::Integer=0, rank::Integer=0, world::Integer=1, nccl_id=nothing,
-                            halo_capacity::Integer=0)
+                            halo_capacity::Integer=0, open_box::Bool=false)
         @assert(h > 0.0, "invalid ParticleSystem declaration! (h must be a positive float)")
         @assert(T <: AbstractParticle, "invalid ParticleSystem declaration! (" * string(T) * " is not an AbstractParticle subtype)")
         @assert(hasfield(T, :x) && (attribute_type(T, :x) == RealVector), "invalid ParticleSystem declaration! (particles must have a field `x::RealVector`)")
@@ -118,7 +120,7 @@ mutable struct ParticleSystem{T<:AbstractParticle}
             lo = div(key_lim[1] * rank, world)
             hi = div(key_lim[1] * (rank + 1), world)
             slab = (Int64(lo), Int64(hi))
-            comm = (Int(rank), Int(world), nccl_id, Int64(halo_capacity))
+            comm = (Int(rank), Int(world), nccl_id, Int64(halo_capacity), open_box)
         end
         sys = new{T}(h, box, key_phase, key_lim, prod(key_lim), key_diff, T[], C_NULL, Int64(capacity), Int(device),
                      Int(flags), slab, comm, true, false)
@@ -161,7 +163,7 @@ end
     use_device_operators!(scheme; constants...)
 
 The one line a driver adds: which family of device operators its closures name ("wcsph",
-"hopkins", "hopkins_full", "hopkins_total", "dambreak", "collision", "flow", "packing") and the
+"hopkins", "hopkins_full", "hopkins_total", "dambreak", "collision", "flow", "aflow", "packing") and the
 values of the module-level constants those closures capture, under libsphmw's names
 (`sphmw_set_param`: dt, g, c, gamma, alpha, beta, eps, eta, rho0, R_mass, R_gas, T_bg, rho_floor,
 P_floor, z_t, z_b, gamma_r, fluid, ...).
@@ -179,7 +181,11 @@ register_operator!(f::Function, name::String) = (OPERATORS[f] = name; f)
 function operator_name(f::Function)
     haskey(OPERATORS, f) && return OPERATORS[f]
     base = replace(String(nameof(f)), "!" => "")
-    for prefix in (SCHEME[], "wcsph")           # the Hopkins drivers reuse the WCSPH unary operators
+    # closures a driver shares character for character with another one live under that one's name:
+    # the Hopkins drivers reuse the WCSPH unary operators, the adiabatic flow driver the isothermal
+    # one's accelerate! and internal_force!
+    shared = startswith(SCHEME[], "hopkins") ? ("hopkins", "wcsph") : SCHEME[] == "aflow" ? ("flow",) : ()
+    for prefix in (SCHEME[], shared...)
         name = prefix * "." * base
         name in menu() && return (OPERATORS[f] = name)
     end
@@ -199,10 +205,11 @@ function ensure_context!(sys::ParticleSystem{T}) where T
     setfield!(sys, :ctx, out[])
     setfield!(sys, :capacity, Int64(cap))
     if sys.comm !== nothing
-        rank, world, id, hc = sys.comm
+        rank, world, id, hc, open_box = sys.comm
         id === nothing && throw(SphmwError(-1, "world > 1 needs nccl_id = comm_unique_id() of rank 0"))
         GC.@preserve id check(ccall((:sphmw_comm_init, libsphmw), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}, Int64),
                                     sys.ctx, rank, world, id, hc > 0 ? hc : max(4096, div(cap, 8))))
+        open_box && check(ccall((:sphmw_comm_open_box, libsphmw), Cint, (Ptr{Cvoid}, Int32), sys.ctx, 1))
     end
 end
 "128 bytes identifying an NCCL communicator: made by ONE rank, handed to the others (MPI.bcast, a file ...)"
@@ -300,6 +307,26 @@ function verlet_steps!(sys::ParticleSystem, n::Integer; scheme::String=SCHEME[])
     check(ccall((:sphmw_step, libsphmw), Cint, (Ptr{Cvoid}, Cstring, Int32), sys.ctx, scheme, n))
     setfield!(sys, :device_ahead, true)
     return nothing
+end
+
+"""
+    add_new_particles!(sys)
+
+≙ add_new_particles!(sys) of the constant-U flow drivers (isothermal_flow_witch.jl:175-186 under scheme
+"flow", adiabatic_flow_witch.jl:197-208 under "aflow"): INFLOW particles that entered the domain turn
+FLUID and a successor is created bc_width upstream with the driver's Particle constructor — on the
+device.  Returns the number of particles added.
+"""
+function add_new_particles!(sys::ParticleSystem)
+    before_device_call!(sys)
+    n = Ref{Int64}(0)
+    if SCHEME[] == "aflow"
+        check(ccall((:sphmw_aflow_add_new_particles, libsphmw), Cint, (Ptr{Cvoid}, Ref{Int64}), sys.ctx, n))
+    else
+        check(ccall((:sphmw_flow_add_new_particles, libsphmw), Cint, (Ptr{Cvoid}, Ref{Int64}), sys.ctx, n))
+    end
+    setfield!(sys, :device_ahead, true)
+    return n[]
 end
 
 assemble_matrix(args...) = throw(SphmwError(-3, "assemble_matrix (ISPH, core.jl:175-246) is outside the device path"))
