@@ -99,6 +99,12 @@ typedef struct sphmw_config {
  * longer hidden (profiles/r02_pair_kernels.md).  Ignored together with NO_PAIR_LIST / CELL_PAIRS /
  * NO_PRETEST. */
 #define SPHMW_FLAG_TILES 64
+/* Slab contexts, at sphmw_create only: keep THREE ghost columns per side instead of two.  Needed by
+ * the pressure-entropy (Hopkins) schemes, whose pressure sum reads the new smoothing length of a
+ * particle's neighbours (hopkins_perturbed_witch.jl:205-208), i.e. complete density sums two columns
+ * beyond the owned ones.  Such a context steps "hopkins"/"hopkins_full" (and "wcsph", on the plain
+ * schedule: the overlapped one is laid out for two ghost columns). */
+#define SPHMW_FLAG_GHOST3 256
 
 int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out);
 int sphmw_destroy(sphmw_ctx *ctx);

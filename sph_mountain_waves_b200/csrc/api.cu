@@ -257,7 +257,7 @@ extern "C" int sphmw_create(const sphmw_config *cfg, sphmw_ctx **out) {
     {
         // key tables, neighbour offsets, physical cell order, exact cut-off (grid_setup.cpp)
         const int rc = sphmw_grid_setup(g, cfg->box_min, cfg->box_max, cfg->h, cfg->slab_lo, cfg->slab_hi,
-                                        &c->global_cols);
+                                        &c->global_cols, (cfg->flags & SPHMW_FLAG_GHOST3) ? 3 : GHOST_COLS);
         if (rc != SPHMW_OK) {
             delete c;
             return rc;

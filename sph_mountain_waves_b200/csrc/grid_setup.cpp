@@ -54,8 +54,9 @@ void sphmw_grid_set_order(Grid &g, bool zrun) {
 }
 
 int sphmw_grid_setup(Grid &g, const double box_min[3], const double box_max[3], double h, int64_t slab_lo,
-                     int64_t slab_hi, int64_t *global_cols) {
+                     int64_t slab_hi, int64_t *global_cols, int ghost) {
     g.h = h;
+    g.ghost = slab_lo >= 0 ? ghost : 0;
     for (int a = 0; a < 3; ++a) {
         g.box[a] = box_min[a];
         g.box[3 + a] = box_max[a];
@@ -73,19 +74,19 @@ int sphmw_grid_setup(Grid &g, const double box_min[3], const double box_max[3], 
     }
     if (global_cols) *global_cols = 0;
     if (slab_lo >= 0) {
-        // local grid = owned columns + GHOST_COLS ghost columns each side; keys are local
+        // local grid = owned columns + `ghost` ghost columns each side; keys are local
         if (!(slab_hi > slab_lo) || slab_hi > g.lim[0]) {
             sphmw_set_error("invalid slab [%lld,%lld) for %lld columns", (long long)slab_lo, (long long)slab_hi,
                             g.lim[0]);
             return SPHMW_E_INVALID;
         }
-        if (slab_hi - slab_lo < 2 * GHOST_COLS) {
-            sphmw_set_error("a slab must own at least %d cell columns", 2 * GHOST_COLS);
+        if (slab_hi - slab_lo < 2 * ghost) {
+            sphmw_set_error("a slab must own at least %d cell columns", 2 * ghost);
             return SPHMW_E_INVALID;
         }
         if (global_cols) *global_cols = g.lim[0];
-        long long width = (slab_hi - slab_lo) + 2 * GHOST_COLS;
-        g.phase[0] += slab_lo - GHOST_COLS;
+        long long width = (slab_hi - slab_lo) + 2 * ghost;
+        g.phase[0] += slab_lo - ghost;
         g.key_max = g.key_max / g.lim[0] * width;
         g.lim[0] = width;
     }

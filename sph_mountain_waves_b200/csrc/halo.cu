@@ -1,7 +1,7 @@
 // x-slab halo exchange, device side (the reference has no distributed path).
 //
-// A rank owns the global cell columns [slab_lo, slab_hi) and keeps GHOST_COLS = 2 ghost
-// columns on each side.  Once per step, after the drift, k_halo_pack classifies every
+// A rank owns the global cell columns [slab_lo, slab_hi) and keeps Grid::ghost (2, or 3 with
+// SPHMW_FLAG_GHOST3) ghost columns on each side.  Once per step, after the drift, k_halo_pack classifies every
 // resident particle:
 //   ghost of the previous exchange      -> dropped
 //   owned, left the global box          -> dropped (counted as lost)
@@ -24,7 +24,7 @@ __global__ void k_halo_pack(Fields f, const uint32_t *__restrict__ idx, uint32_t
                             int64_t n, Grid g, int has_left, int has_right, double *buf_l,
                             double *buf_r, uint32_t cap, uint32_t *counters,
                             const uint32_t *__restrict__ cellx, ColFilter cf, uint32_t *__restrict__ lost_list,
-                            uint32_t lost_cap) {
+                            uint32_t lost_cap, int carry_a) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
     if (cf.on && !col_selected(cf, (int)cellx[p])) return;
@@ -49,17 +49,18 @@ __global__ void k_halo_pack(Fields f, const uint32_t *__restrict__ idx, uint32_t
     long long i = (long long)floor(x / g.h) - g.phase[0];  // local column
     int to_l = 0, to_r = 0;
     double kind = HALO_KIND_GHOST;
-    if (i < GHOST_COLS) {
+    const int G = g.ghost;
+    if (i < G) {
         to_l = 1;
         kind = HALO_KIND_MIGRANT;
         tag[p] = (i >= 0 && has_left) ? TAG_GHOST : TAG_DEAD;
-    } else if (i >= W - GHOST_COLS) {
+    } else if (i >= W - G) {
         to_r = 1;
         kind = HALO_KIND_MIGRANT;
         tag[p] = (i < W && has_right) ? TAG_GHOST : TAG_DEAD;
     } else {
-        to_l = i < 2 * GHOST_COLS;
-        to_r = i >= W - 2 * GHOST_COLS;
+        to_l = i < 2 * G;
+        to_r = i >= W - 2 * G;
     }
     to_l = to_l && has_left;
     to_r = to_r && has_right;
@@ -73,8 +74,10 @@ __global__ void k_halo_pack(Fields f, const uint32_t *__restrict__ idx, uint32_t
     rec[5] = DIM == 3 ? f.s[S_V2][p] : 0.0;
     rec[6] = f.s[S_M][p];
     rec[7] = f.s[S_H][p];
-    rec[8] = f.s[S_RHO][p];
-    rec[9] = f.s[S_RHO_P][p];
+    // rows 8/9: rho, rho' — or, for the pressure-entropy (Hopkins) drivers, the entropy functions A and
+    // A_bg, which are carried state there (densities are recomputed by the receiver either way)
+    rec[8] = carry_a ? f.s[S_A][p] : f.s[S_RHO][p];
+    rec[9] = carry_a ? (carry_a > 1 ? f.s[S_A_BG][p] : 0.0) : f.s[S_RHO_P][p];
     rec[10] = f.s[S_TYPE][p];
     rec[11] = (double)idx[p];
     rec[12] = kind;
@@ -94,7 +97,7 @@ __global__ void k_halo_pack(Fields f, const uint32_t *__restrict__ idx, uint32_t
 
 template <int DIM>
 __global__ void k_halo_unpack(Fields f, uint32_t *__restrict__ idx, uint32_t *__restrict__ tag,
-                              int64_t first, const double *__restrict__ buf, int64_t cnt) {
+                              int64_t first, const double *__restrict__ buf, int64_t cnt, int carry_a) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= cnt) return;
     const double *rec = buf + (size_t)t * HALO_RECORD;
@@ -107,8 +110,13 @@ __global__ void k_halo_unpack(Fields f, uint32_t *__restrict__ idx, uint32_t *__
     if (DIM == 3) f.s[S_V2][p] = rec[5];
     f.s[S_M][p] = rec[6];
     f.s[S_H][p] = rec[7];
-    f.s[S_RHO][p] = rec[8];
-    f.s[S_RHO_P][p] = rec[9];
+    if (carry_a) {
+        f.s[S_A][p] = rec[8];
+        if (carry_a > 1) f.s[S_A_BG][p] = rec[9];
+    } else {
+        f.s[S_RHO][p] = rec[8];
+        f.s[S_RHO_P][p] = rec[9];
+    }
     f.s[S_TYPE][p] = rec[10];
     idx[p] = (uint32_t)rec[11];
     tag[p] = rec[12] == HALO_KIND_MIGRANT ? TAG_OWNED : TAG_GHOST;
@@ -116,12 +124,20 @@ __global__ void k_halo_unpack(Fields f, uint32_t *__restrict__ idx, uint32_t *__
 
 static const int CARRIED[] = {S_X0, S_X1, S_X2, S_V0, S_V1, S_V2, S_M, S_H, S_RHO, S_RHO_P, S_TYPE};
 
+// 0: rows 8/9 of a record are rho, rho'; 1: A; 2: A and A_bg (contexts that hold those fields)
+static int carry_a(const sphmw_ctx *c) {
+    if (!c->allocated[S_A]) return 0;
+    return c->allocated[S_A_BG] ? 2 : 1;
+}
+
 static int ensure_carried(sphmw_ctx *c) {
     for (int s : CARRIED) {
         if (c->grid.dim == 2 && (s == S_X2 || s == S_V2)) continue;
         TRY(sphmw_ensure_slot(c, s));
         if (c->stale[s]) { sphmw_set_error("halo: carried field is stale"); return SPHMW_E_STATE; }
     }
+    for (int s : {S_A, S_A_BG})
+        if (c->allocated[s] && c->stale[s]) { sphmw_set_error("halo: carried field is stale"); return SPHMW_E_STATE; }
     return SPHMW_OK;
 }
 
@@ -164,11 +180,11 @@ static int pack_enqueue(sphmw_ctx *c, double *dev_buf_left, double *dev_buf_righ
         if (c->grid.dim == 2)
             k_halo_pack<2><<<grid_for(c->n, 256), 256, 0, c->stream>>>(
                 view, c->idx, c->tag, c->n, c->grid, has_left, has_right, dev_buf_left,
-                dev_buf_right, (uint32_t)cap_records, c->halo_counters, c->cellx, cf, c->lost_list, SLAB_LOST_CAP);
+                dev_buf_right, (uint32_t)cap_records, c->halo_counters, c->cellx, cf, c->lost_list, SLAB_LOST_CAP, carry_a(c));
         else
             k_halo_pack<3><<<grid_for(c->n, 256), 256, 0, c->stream>>>(
                 view, c->idx, c->tag, c->n, c->grid, has_left, has_right, dev_buf_left,
-                dev_buf_right, (uint32_t)cap_records, c->halo_counters, c->cellx, cf, c->lost_list, SLAB_LOST_CAP);
+                dev_buf_right, (uint32_t)cap_records, c->halo_counters, c->cellx, cf, c->lost_list, SLAB_LOST_CAP, carry_a(c));
         CUDA_TRY(cudaGetLastError());
     }
     if (c->lost_list)  // word 0 of the list: how many particles this pack dropped
@@ -269,10 +285,10 @@ extern "C" int sphmw_halo_unpack(sphmw_ctx *c, const double *dev_buf, int64_t co
         TIMED(c, "halo_unpack");
         if (c->grid.dim == 2)
             k_halo_unpack<2><<<grid_for(count, 256), 256, 0, c->stream>>>(
-                c->cur, c->idx, c->tag, c->n, dev_buf, count);
+                c->cur, c->idx, c->tag, c->n, dev_buf, count, carry_a(c));
         else
             k_halo_unpack<3><<<grid_for(count, 256), 256, 0, c->stream>>>(
-                c->cur, c->idx, c->tag, c->n, dev_buf, count);
+                c->cur, c->idx, c->tag, c->n, dev_buf, count, carry_a(c));
         CUDA_TRY(cudaGetLastError());
     }
     c->n += count;

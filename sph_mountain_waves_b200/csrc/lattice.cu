@@ -194,7 +194,7 @@ extern "C" int sphmw_generate_mountain_wave(sphmw_ctx *c, const sphmw_lattice_se
         // global column range owned by this rank; Grid::phase[0] was shifted by the slab
         J.col_lo = c->slab_lo;
         J.col_hi = c->slab_hi;
-        J.phase0 = c->grid.phase[0] - (c->slab_lo - GHOST_COLS);
+        J.phase0 = c->grid.phase[0] - (c->slab_lo - c->grid.ghost);
         J.cell_h = c->grid.h;
         // restrict the enumeration to the lattice planes that can fall into the slab
         double xa = (double)(J.phase0 + J.col_lo) * J.cell_h - 2 * J.sx;

@@ -252,9 +252,9 @@ static int run_unary(sphmw_ctx *c, const char *name) {
 // evaluate in slab mode; ignored for whole-domain contexts
 static ColFilter filter_for_depth(sphmw_ctx *c, int ghost_depth) {
     ColFilter cf{0, 0, (int)c->grid.lim[0] - 1, 1, 0, 1};
-    if (c->slab_lo >= 0 && ghost_depth < GHOST_COLS) {
+    if (c->slab_lo >= 0 && ghost_depth < c->grid.ghost) {
         cf.on = 1;
-        cf.a0 = GHOST_COLS - ghost_depth;
+        cf.a0 = c->grid.ghost - ghost_depth;
         cf.a1 = (int)c->grid.lim[0] - 1 - cf.a0;
     }
     return cf;
@@ -262,10 +262,11 @@ static ColFilter filter_for_depth(sphmw_ctx *c, int ghost_depth) {
 
 template <class Op, bool REC = false>
 static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Fields &out, ColFilter cf);
+#define GHOST_COLS_ALL 99  // ghost_depth: every ghost column the context keeps
 
 template <class Op, bool REC = false>
 static int run_binary(sphmw_ctx *c, const char *name, int self, const Fields &out,
-                      int ghost_depth = GHOST_COLS) {
+                      int ghost_depth = GHOST_COLS_ALL) {
     return run_binary_cols<Op, REC>(c, name, self, out, filter_for_depth(c, ghost_depth));
 }
 
@@ -553,8 +554,8 @@ static int run_cell_pairs(sphmw_ctx *c, const char *name, const Fields &out, int
     unsigned long long *pc = c->count_pairs ? c->d_counters : nullptr;
     if (pc) CUDA_TRY(cudaMemsetAsync(pc, 0, sizeof(unsigned long long), c->stream));
     int col_lo = 0, col_hi = (int)c->grid.lim[0] - 1;
-    if (c->slab_lo >= 0 && ghost_depth < GHOST_COLS) {
-        col_lo = GHOST_COLS - ghost_depth;
+    if (c->slab_lo >= 0 && ghost_depth < c->grid.ghost) {
+        col_lo = c->grid.ghost - ghost_depth;
         col_hi = (int)c->grid.lim[0] - 1 - col_lo;
     }
     // persistent grid: a multiple of the SM count, warps stride over the cells
@@ -887,12 +888,15 @@ static int step_wcsph_fused_post(sphmw_ctx *c, bool advance = false) {
 
 // hopkins_perturbed_witch.jl:324-349 / full_hopkins_perturbed_witch.jl:350-374 with the unary
 // sweeps folded into the three pair passes (ops_menu.cuh): the density pass records the pair
-// list, the pressure and force passes replay it.  Whole-domain contexts only: the pressure sum
-// needs the NEW smoothing length of a particle's neighbours, i.e. complete density sums two cell
-// columns beyond the owned ones — one ghost column more than a slab context keeps.
+// list, the pressure and force passes replay it.  On a slab context the pressure sum needs the NEW
+// smoothing length of a particle's neighbours, i.e. complete density sums two cell columns beyond
+// the owned ones: three ghost columns (SPHMW_FLAG_GHOST3), plain schedule.
 template <class Force>
-static int step_hopkins_fused(sphmw_ctx *c) {
-    TRY(step_wcsph_fused_pre(c));           // accelerate! + move! (:325-326)
+static int step_hopkins_fused_post(sphmw_ctx *c) {
+    if (c->slab_lo >= 0 && c->grid.ghost < 3) {
+        sphmw_set_error("the Hopkins schemes need three ghost columns on a slab context (SPHMW_FLAG_GHOST3)");
+        return SPHMW_E_STATE;
+    }
     TRY(sphmw_build_cell_list(c, nullptr));  // :329
     TRY(need_slots(c, SL(S_X0, S_V0, S_M, S_H, S_A, S_TYPE), SL()));
     TRY(need_slots(c, SL(S_DV0), SL()));     // all zero after accelerate!; the force operator starts from it
@@ -901,13 +905,21 @@ static int step_hopkins_fused(sphmw_ctx *c) {
         c->stale[s] = false;
     }
     c->want_list = true;
-    TRY((run_binary<B_hopkins_density_fused>(c, "hopkins.density_fused", 0, c->cur)));
-    TRY((run_binary<B_hopkins_pressure_fused>(c, "hopkins.pressure_fused", 0, c->cur)));
-    TRY((run_binary<B_force_kick_fused<Force>>(c, "hopkins.momentum_fused", 0, c->alt)));
+    // slab contexts (three ghost columns): the density sums — and with them the new smoothing lengths —
+    // are complete two columns beyond the owned ones, the pressure sums one column beyond, the force
+    // is needed on the owned columns only
+    TRY((run_binary<B_hopkins_density_fused>(c, "hopkins.density_fused", 0, c->cur, 2)));
+    TRY((run_binary<B_hopkins_pressure_fused>(c, "hopkins.pressure_fused", 0, c->cur, 1)));
+    TRY((run_binary<B_force_kick_fused<Force>>(c, "hopkins.momentum_fused", 0, c->alt, 0)));
     std::swap(c->cur.s[S_V0], c->alt.s[S_V0]);
     std::swap(c->cur.s[S_V1], c->alt.s[S_V1]);
     if (c->grid.dim == 3) std::swap(c->cur.s[S_V2], c->alt.s[S_V2]);
     return SPHMW_OK;
+}
+template <class Force>
+static int step_hopkins_fused(sphmw_ctx *c) {
+    TRY(step_wcsph_fused_pre(c));           // accelerate! + move! (:325-326)
+    return step_hopkins_fused_post<Force>(c);
 }
 
 // one step of a whole-domain multi-step call.  opened: the previous step's force pass already ran
@@ -1048,6 +1060,7 @@ static int step_wcsph_overlap_a(sphmw_ctx *c) {
         sphmw_set_error("step_phase 2/3: the overlapped step runs on slab contexts without CELL_PAIRS");
         return SPHMW_E_STATE;
     }
+    if (c->grid.ghost != GHOST_COLS) { sphmw_set_error("step_phase 2/3: the overlapped step is laid out for two ghost columns"); return SPHMW_E_STATE; }
     if (c->overlap_stage != 0) { sphmw_set_error("step_phase 2: an overlapped step is already in flight"); return SPHMW_E_STATE; }
     if (!c->dv_zero) { sphmw_set_error("step_phase 2: Dv must be zero (run step_phase 0 first)"); return SPHMW_E_STATE; }
     wcsph_before_sort(c);
@@ -1106,8 +1119,17 @@ static int step_wcsph_overlap_b(sphmw_ctx *c) {
 }
 
 int sphmw_step_scheme_phase(sphmw_ctx *c, const char *scheme, int phase) {
+    if (!strcmp(scheme, "hopkins") || !strcmp(scheme, "hopkins_full")) {
+        // plain schedule only: kick + drift | (the caller's halo exchange) | sort + three pair passes
+        if (phase == 0) return step_wcsph_fused_pre(c);
+        if (phase == 1)
+            return !strcmp(scheme, "hopkins") ? step_hopkins_fused_post<B_wcsph_momentum>(c)
+                                              : step_hopkins_fused_post<B_hf_momentum>(c);
+        sphmw_set_error("step_phase: the Hopkins schemes run the plain schedule (phases 0 and 1)");
+        return SPHMW_E_INVALID;
+    }
     if (strcmp(scheme, "wcsph")) {
-        sphmw_set_error("step_phase: only the fused 'wcsph' scheme runs on slabs");
+        sphmw_set_error("step_phase: only the fused 'wcsph' and 'hopkins'/'hopkins_full' schemes run on slabs");
         return SPHMW_E_UNSUPPORTED_OP;
     }
     switch (phase) {

@@ -399,12 +399,21 @@ int sphmw_comm_create_cell_list(sphmw_ctx *c, int64_t *n_alive) {
 // packed first and their records travel while the interior columns are in the force pass.
 int sphmw_comm_step(sphmw_ctx *c, const char *scheme, int nsteps) {
     SlabComm *m = c->comm;
-    if (strcmp(scheme, "wcsph")) {
-        sphmw_set_error("step: only the fused 'wcsph' scheme runs on slabs");
+    const bool hopkins = !strcmp(scheme, "hopkins") || !strcmp(scheme, "hopkins_full");
+    if (strcmp(scheme, "wcsph") && !hopkins) {
+        sphmw_set_error("step: the fused 'wcsph', 'hopkins' and 'hopkins_full' schemes run on slabs");
         return SPHMW_E_UNSUPPORTED_OP;
     }
     if (nsteps <= 0) return SPHMW_OK;
-    const bool overlap = nsteps > 1 && !(c->flags & SPHMW_FLAG_CELL_PAIRS) && !m->open_box && !getenv("SPHMW_NO_OVERLAP");
+    if (hopkins) {  // three pair passes per step, three ghost columns, plain schedule
+        for (int k = 0; k < nsteps; ++k) {
+            TRY(sphmw_step_scheme_phase(c, scheme, 0));
+            TRY(comm_exchange_all(c));
+            TRY(sphmw_step_scheme_phase(c, scheme, 1));
+        }
+        return SPHMW_OK;
+    }
+    const bool overlap = nsteps > 1 && c->grid.ghost == GHOST_COLS && !(c->flags & SPHMW_FLAG_CELL_PAIRS) && !m->open_box && !getenv("SPHMW_NO_OVERLAP");
     if (!overlap) {
         for (int k = 0; k < nsteps; ++k) {
             TRY(sphmw_step_wcsph_phase(c, 0));

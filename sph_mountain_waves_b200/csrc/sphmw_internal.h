@@ -94,6 +94,10 @@ struct Grid {
     // stays in L2.  zrun == 0: the x-chunked order above, kept for the shared-memory variants
     // (SPHMW_FLAG_TILES, SPHMW_FLAG_CELL_PAIRS) that stage x-rows.
     int zrun;
+    // slab contexts: ghost columns kept on each side of the owned ones (GHOST_COLS; three with
+    // SPHMW_FLAG_GHOST3, which the Hopkins schemes need: their pressure sum reads the NEW smoothing
+    // length of a particle's neighbours, i.e. complete density sums one column further out)
+    int ghost;
 };
 
 #if defined(__CUDACC__) || defined(SPHMW_EMU)
@@ -451,7 +455,7 @@ const FieldDesc *sphmw_find_field(const char *name);
 // implemented in grid_setup.cpp (host only, no CUDA calls)
 void sphmw_derive_params(Params &p);
 int sphmw_grid_setup(Grid &g, const double box_min[3], const double box_max[3], double h, int64_t slab_lo,
-                     int64_t slab_hi, int64_t *global_cols);
+                     int64_t slab_hi, int64_t *global_cols, int ghost = GHOST_COLS);
 void sphmw_grid_set_order(Grid &g, bool zrun);  // physical cell order (Grid::zrun)
 // core.jl:72-81 on index space: the (old index -> new index) moves of the survivors when the
 // particles `removed` (any order) leave an array of N (cell_list.cu)

@@ -31,12 +31,14 @@ from ._capi import check
 from .schemes import wcsph_perturbed_witch as wpw
 
 GHOST_COLS = 2
+GHOST3_FLAG = 256  # SPHMW_FLAG_GHOST3: three ghost columns per side (the Hopkins schemes)
 RECORD = 13  # x0 x1 x2 v0 v1 v2 m h rho rho_p type idx kind
 KIND_MIGRANT, KIND_GHOST = 0.0, 1.0
 
 
 # ----------------------------------------------------------------------------- planning
-def split_columns(ncols: int, world: int, weights: Optional[np.ndarray] = None) -> List[Tuple[int, int]]:
+def split_columns(ncols: int, world: int, weights: Optional[np.ndarray] = None,
+                  ghost: int = GHOST_COLS) -> List[Tuple[int, int]]:
     """Column ranges [lo, hi) per rank; equal widths for a uniform lattice, or
     balanced by per-column particle counts when `weights` is given."""
     if weights is None:
@@ -47,8 +49,8 @@ def split_columns(ncols: int, world: int, weights: Optional[np.ndarray] = None) 
         edges = [int(np.searchsorted(c, t, side="left")) for t in target]
         edges[0], edges[-1] = 0, ncols
     for r in range(world):
-        if edges[r + 1] - edges[r] < 2 * GHOST_COLS:
-            raise ValueError(f"a slab must own at least {2 * GHOST_COLS} cell columns")
+        if edges[r + 1] - edges[r] < 2 * ghost:
+            raise ValueError(f"a slab must own at least {2 * ghost} cell columns")
     return [(edges[r], edges[r + 1]) for r in range(world)]
 
 
@@ -96,9 +98,9 @@ class SlabPlan:
         return (c >= self.lo) & (c < self.hi)
 
 
-def plan_slab(box_min, box_max, h: float, rank: int, world: int) -> SlabPlan:
+def plan_slab(box_min, box_max, h: float, rank: int, world: int, ghost: int = GHOST_COLS) -> SlabPlan:
     phase, lim = key_tables(box_min, box_max, h)
-    lo, hi = split_columns(lim[0], world)[rank]
+    lo, hi = split_columns(lim[0], world, ghost=ghost)[rank]
     return SlabPlan(rank, world, lo, hi, phase[0], lim[0], h)
 
 
@@ -176,11 +178,17 @@ class LibSlabBackend:
         import torch
         return torch.empty((n, RECORD), dtype=torch.float64, device=self.dev)
 
+    @property
+    def scheme(self) -> bytes:
+        """the fused scheme this context steps: "wcsph", or "hopkins"/"hopkins_full" (three ghost columns)"""
+        s = getattr(self.sys.T, "scheme", "wcsph")
+        return s.encode() if s in ("hopkins", "hopkins_full") else b"wcsph"
+
     def pre(self):
-        check(_capi.lib().sphmw_step_phase(self.sys.ctx, b"wcsph", 0))
+        check(_capi.lib().sphmw_step_phase(self.sys.ctx, self.scheme, 0))
 
     def post(self):
-        check(_capi.lib().sphmw_step_phase(self.sys.ctx, b"wcsph", 1))
+        check(_capi.lib().sphmw_step_phase(self.sys.ctx, self.scheme, 1))
 
     def build(self):
         self.sys.create_cell_list(want_count=False)
@@ -203,7 +211,9 @@ class LibSlabBackend:
     # ---- overlapped step (include/sphmw.h: step_phase 2/3, halo_pack_begin/finish) ----------
     @property
     def can_overlap(self) -> bool:
-        return not (self.sys._flags & 2)   # CELL_PAIRS kernels take one column range only
+        # CELL_PAIRS kernels take one column range only; the overlapped schedule is the fused WCSPH
+        # step's, laid out for two ghost columns
+        return not (self.sys._flags & (2 | GHOST3_FLAG)) and self.scheme == b"wcsph"
 
     def overlap_enqueue(self):
         """finish the current step and start the next one: edge columns first (force, kick,
@@ -357,14 +367,18 @@ class SlabRun:
     @classmethod
     def from_global_case(cls, case, rank: int, world: int, device: int = 0, stream=None, flags: int = 0):
         """Slice a whole (small) case held on the host: reference indices are the positions in
-        `case.fields`.  Used by tests and by single-process multi-context runs."""
-        plan = plan_slab(case.box_min, case.box_max, case.h, rank, world)
+        `case.fields`.  Used by tests and by single-process multi-context runs.  A Hopkins case gets
+        three ghost columns per side (SPHMW_FLAG_GHOST3)."""
+        ghost = 3 if case.scheme in ("hopkins", "hopkins_full") else GHOST_COLS
+        if ghost == 3:
+            flags |= GHOST3_FLAG
+        plan = plan_slab(case.box_min, case.box_max, case.h, rank, world, ghost=ghost)
         own = plan.owns(case.fields["x"][:, 0])
         gidx = np.nonzero(own)[0].astype(np.int64)
         sub = cases.Case(case.name, case.scheme, case.dim, case.box_min, case.box_max, case.h,
                          case.params, {f: a[own] for f, a in case.fields.items()}, dict(case.info))
         n_own = sub.n
-        ghost_est = int(n_own * 2 * GHOST_COLS / max(1, plan.hi - plan.lo) * 2.0) + 4096
+        ghost_est = int(n_own * 2 * ghost / max(1, plan.hi - plan.lo) * 2.0) + 4096
         sys = cases.to_system(sub, device=device, stream=stream, slab=(plan.lo, plan.hi),
                               capacity=int(n_own * 1.2) + 2 * ghost_est, flags=flags)
         sys._flush()

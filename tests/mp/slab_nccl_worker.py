@@ -28,8 +28,14 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 12
     flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    case = cases.bell_hill_3d(64, 10, 8, h_m=3000.0, a=8e3, U=60.0)   # fast flow: particles migrate
-    names = ("x", "v", "rho", "h")
+    scheme = sys.argv[3] if len(sys.argv) > 3 else "wcsph"
+    if scheme == "wcsph":
+        case = cases.bell_hill_3d(64, 10, 8, h_m=3000.0, a=8e3, U=60.0)   # fast flow: particles migrate
+        names = ("x", "v", "rho", "h")
+    else:
+        # the pressure-entropy drivers: three ghost columns, records carry A (plain schedule)
+        case = cases.hopkins_2d(scheme, n_y=16.0, dom_length=160e3, h_m=3000.0, a=10e3, U=250.0)
+        names = ("x", "v", "rho", "h", "P", "A")
     failures = []
     for transport in ("library", "python"):
         run = SlabRun.from_global_case(case, rank, world, device=local, flags=flags)

@@ -101,3 +101,44 @@ def test_overlapped_step_refuses_fast_particles(gpu):
     cluster.create_cell_list()
     with pytest.raises(SphmwError, match="more than one cell column"):
         cluster.step(4)
+
+
+@pytest.mark.parametrize("variant,world,U", [("hopkins", 2, 20.0), ("hopkins", 3, 250.0), ("hopkins_full", 3, 20.0)])
+def test_hopkins_slabs_bitwise_equal_to_whole_domain(gpu, variant, world, U):
+    """the pressure-entropy drivers on slabs (hopkins_perturbed_witch.jl:324-349,
+    full_hopkins_perturbed_witch.jl:350-374): three pair passes per step; compute_pressure! reads the
+    neighbours' NEW smoothing length, so a slab keeps three ghost columns (SPHMW_FLAG_GHOST3) and the
+    halo records carry A (and A_bg).  Any number of ranks gives the whole-domain bits; U = 250 m/s makes
+    particles change owner on the way."""
+    case = cases.hopkins_2d(variant, n_y=16.0, dom_length=120e3, h_m=3000.0, a=10e3, U=U)
+    whole = load_gpu(case)
+    whole.create_cell_list()
+    cluster = LocalCluster([SlabRun.from_global_case(case, r, world) for r in range(world)])
+    cluster.create_cell_list()
+    assert sum(r.n_owned for r in cluster.runs) == case.n
+    own0 = [r.n_owned for r in cluster.runs]
+    nsteps = 30
+    whole.step(nsteps)
+    cluster.step(nsteps)
+    names = ("x", "v", "rho", "h", "P", "A", "m", "type") + (("A_bg",) if variant == "hopkins_full" else ())
+    gidx, got = cluster.gather(names)
+    assert np.array_equal(gidx, np.arange(case.n))
+    for f, a in got.items():
+        assert np.array_equal(a, whole.field(f)), f
+    assert sum(r.n_owned for r in cluster.runs) == case.n
+    if U > 100.0:
+        assert [r.n_owned for r in cluster.runs] != own0, "no particle changed owner"
+
+
+def test_hopkins_on_a_two_column_slab_is_refused(gpu):
+    """without the third ghost column the pressure sums next to the slab face would be incomplete:
+    the step fails loudly instead"""
+    from sph_mountain_waves_b200._capi import SphmwError
+    case = cases.hopkins_2d("hopkins", n_y=16.0, dom_length=120e3)
+    case.scheme = "wcsph"          # sliced like a WCSPH case: two ghost columns
+    run = SlabRun.from_global_case(case, 0, 2)
+    run.sys.T.scheme = "hopkins"
+    cluster = LocalCluster([run])
+    with pytest.raises(SphmwError):
+        run.backend.pre()
+        run.backend.post()

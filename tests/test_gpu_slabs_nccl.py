@@ -34,6 +34,22 @@ def test_nccl_transports_match_the_whole_domain_run(world, flags):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world,scheme", [(2, "hopkins"), (4, "hopkins_full")])
+def test_nccl_transports_step_the_hopkins_drivers(world, scheme):
+    """three pair passes per step on slabs with three ghost columns, through both transports
+    (sphmw_step(ctx, "hopkins", n) on a context with a communicator; step_phase 0/1 around
+    torch.distributed), bitwise equal to the whole-domain run"""
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 30500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           str(ROOT / "tests" / "mp" / "slab_nccl_worker.py"), "12", "0", scheme]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+    assert r.returncode == 0 and "SLAB_NCCL_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 4])
 def test_open_box_removal_renumbers_like_the_reference(world):
     """particles leave the global box on several ranks (downstream face, top): the library transport
