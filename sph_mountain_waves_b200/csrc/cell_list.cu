@@ -294,6 +294,17 @@ int sphmw_build_cell_list(sphmw_ctx *c, int64_t *n_alive) {
     c->cell_gen += 1;
     c->want_list = c->passes_this_gen >= 2;
     c->passes_this_gen = 0;
+    // The recording pass's queue (pair_list.cuh) is sized for the survivors particles really have, and a
+    // particle with more walks the cells in BOTH pair passes — a cliff (64 M particles: 38.6 -> 45.5 ms
+    // with 14 % such particles).  The overflow counter of the previous list (published to pinned memory
+    // one build ago, so no wait) tells when the rows are too few: then they grow, up to the list stride.
+    if (c->pl.list && c->h_counters) {
+        const unsigned long long seen = c->h_counters[2];
+        if (seen > c->pl_overflow_seen + (unsigned long long)(n >> 10) && c->pl.qrows < c->pl.stride + NL_QUEUE_SLACK)
+            c->pl.qrows = std::min(c->pl.qrows + 4, c->pl.stride + NL_QUEUE_SLACK);
+        c->pl_overflow_seen = seen;
+        TRY(sphmw_publish_words(c, (const uint32_t *)(c->d_counters + 2), (uint32_t *)(c->h_counters + 2), 2, c->stream));
+    }
     if (n == 0) {
         CUDA_TRY(cudaMemsetAsync(c->cell_start, 0, sizeof(uint32_t) * (ncells + 2), c->stream));
         c->cell_list_valid = true;

@@ -178,7 +178,6 @@ __device__ __forceinline__ void nl_count_pairs(unsigned long long *pair_counter,
 // zrun order) and an FP32 mirror of the absolute positions (slower still, profiles/r01b_pair_list.md).
 #define NL_FILTER_F64 0
 #define NL_FILTER_Q6 3
-#define NL_QUEUE_SLACK 4  // queue rows beyond the list stride: room is checked once per four slots
 // one candidate run [b, e) of the 6-bit pre-test; false: the queue is full.  Measured and set aside
 // (profiles/r02b_zrun.md): requesting the next four words ahead, aligned 16-byte loads of four
 // words, and two queue entries per iteration in phase 2 — the plain loop with the fewest registers
@@ -209,7 +208,11 @@ __global__ void __launch_bounds__(NL_BLOCK)
 k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
                const uint32_t *__restrict__ cellx, const uint32_t *__restrict__ cell_start, int64_t n,
                int self, unsigned long long *pair_counter, ColFilter cf, PairList pl) {
-    extern __shared__ uint32_t nl_queue[];  // [stride + NL_QUEUE_SLACK][NL_BLOCK]: a private column per thread
+    // [pl.qrows][NL_BLOCK]: a private column per thread.  The queue is what limits the L1 cache the nine
+    // resident blocks leave: 44 -> 36 rows took the 64 M density pass from 15.6 to 14.4 ms (16-bit
+    // entries, which halve it again, lost that to their decoding: profiles/r02b_zrun.md), so the rows are
+    // sized for the survivors a particle really has, independently of the list stride
+    extern __shared__ uint32_t nl_queue[];
     const int64_t p = blockIdx.x * (int64_t)NL_BLOCK + threadIdx.x;
     if (p >= n) return;
     const CellCoord home = cell_of(g, key[p], cellx[p]);
@@ -220,7 +223,7 @@ k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restr
     }
     const uint32_t stride = (uint32_t)pl.stride;
     const unsigned qbase = (unsigned)__cvta_generic_to_shared(nl_queue + threadIdx.x);
-    const unsigned qend = qbase + (stride + NL_QUEUE_SLACK) * (NL_BLOCK * 4u);
+    const unsigned qend = qbase + (unsigned)pl.qrows * (NL_BLOCK * 4u);
     unsigned qtop = qbase;
     const double px = f.s[S_X0][p], py = f.s[S_X1][p], pz = DIM == 3 ? f.s[S_X2][p] : 0.0;
     bool fits = true;

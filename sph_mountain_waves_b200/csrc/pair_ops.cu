@@ -289,6 +289,12 @@ static int ensure_pair_list(sphmw_ctx *c) {
     c->pl.list = list;
     c->pl.cnt = cnt;
     c->pl.stride = stride;
+    // queue rows: a particle of a resolved flow has 26-29 neighbours in 3D (h = 1.8 dr) and the 6-bit
+    // pre-test lets ~8 % more through; one with more survivors than rows - 4 walks the cells instead
+    int qrows = c->grid.dim == 3 ? 36 : 28;
+    if (const char *e = getenv("SPHMW_PAIR_QUEUE_ROWS")) qrows = atoi(e);
+    qrows = std::min(qrows, stride + NL_QUEUE_SLACK);
+    c->pl.qrows = std::max(qrows, 2 * NL_QUEUE_SLACK);
     c->pl.overflow = c->d_counters + 2;
     return SPHMW_OK;
 }
@@ -366,7 +372,7 @@ static int run_binary_cols(sphmw_ctx *c, const char *name, int self, const Field
         // pre-test of the recording pass: integers on the 6-bit mirror of the zrun cell order, or
         // (SPHMW_FLAG_NO_PRETEST, x-chunked cell order) the exact FP64 test only
         const bool q6 = c->grid.zrun && !(c->flags & SPHMW_FLAG_NO_PRETEST);
-        const size_t smem = sizeof(uint32_t) * (size_t)(c->pl.stride + NL_QUEUE_SLACK) * NL_BLOCK;
+        const size_t smem = sizeof(uint32_t) * (size_t)c->pl.qrows * NL_BLOCK;
         TIMED(c, name);
         c->pl_gen = c->cell_gen;
         c->pl_format = 0;

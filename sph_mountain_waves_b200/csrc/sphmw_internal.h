@@ -193,6 +193,7 @@ __host__ __device__ __forceinline__ bool col_selected(const ColFilter &cf, int i
 // ---------------------------------------------------------------------------
 #define NL_NONE 0xFFFFFFFFu  // cnt value: no list for this particle (walk the cells)
 #define NL_BLOCK 128
+#define NL_QUEUE_SLACK 4  // room in the recording pass's queue is checked once per four slots: the last four rows are slack
 // Pre-test of the recording pass on the quantised mirror.  A position is cell + (q + e)/1024 with
 // e in [0,1) per axis, so for a pair with r <= h the integer differences d_a (in h/1024, cell
 // offsets included) satisfy |d_a| < |t_a| + 1 with sum t_a^2 <= 1024^2, hence
@@ -304,6 +305,7 @@ struct PairList {
     // (rebuilt by every cell-list build, cell_list.cu)
     const uint32_t *xq;
     int stride;
+    int qrows;  // rows of the recording pass's shared-memory queue (survivors of the pre-test + NL_QUEUE_SLACK)
     unsigned long long *overflow;  // counter: particles whose candidates did not fit `stride`
 };
 
@@ -382,6 +384,7 @@ struct sphmw_ctx {
     bool want_list = false;        // build the list in the next binary pass
     int passes_this_gen = 0;       // binary passes since the last cell-list build
     int64_t pl_builds = 0;
+    unsigned long long pl_overflow_seen = 0;  // overflow counter at the last look (queue rows adapt, cell_list.cu)
     int pl_format = 0;             // what the valid list holds: 0 global positions, 1 tile slots
     // neighbourhood tiles (tile_map.cuh): one record per block of TM_BLOCK particles
     uint32_t *tile_tab = nullptr;

@@ -152,6 +152,7 @@ struct System {
         pl.cnt = cnt.data();
         pl.xq = xq.data();
         pl.stride = stride;
+        pl.qrows = stride + NL_QUEUE_SLACK;
         pl.overflow = &counters[2];
         const uint32_t *k = key.data(), *cx = cellx.data(), *cs = cell_start.data();
         if (list_built) {  // replay

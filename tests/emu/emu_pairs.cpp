@@ -158,6 +158,7 @@ static Result run_variant(State st, const Grid &g, const Params &prm, Variant v,
     pl.cnt = st.cnt.data();
     pl.xq = st.xq.data();
     pl.stride = stride;
+    pl.qrows = stride + NL_QUEUE_SLACK;
     pl.overflow = &counters[2];
     pl.recA = st.rec[0].data();
     pl.recB = st.rec[1].data();

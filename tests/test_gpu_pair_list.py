@@ -66,6 +66,28 @@ def test_overflowing_particles_walk_the_cells(gpu, make, monkeypatch):
             assert bits_equal(s.field(f), ref.field(f)), (stride, f)
 
 
+def test_queue_rows_grow_when_particles_overflow(gpu, monkeypatch):
+    """the recording pass's shared-memory queue starts far too short here: particles overflow and walk
+    the cells (same bits), the library sees the overflow counter grow and adds rows, four per cell
+    list, until the lists fit again"""
+    monkeypatch.setenv("SPHMW_PAIR_QUEUE_ROWS", "16")
+    case = small_3d()
+    ref = load_gpu(case, flags=NO_LIST)
+    ref.create_cell_list()
+    s = load_gpu(case)
+    s.create_cell_list()
+    s.step(2)
+    first = s.pair_list_info()["overflow"]
+    assert first > 0
+    s.step(10)
+    settled = s.pair_list_info()["overflow"]
+    s.step(4)
+    assert s.pair_list_info()["overflow"] == settled   # no particle overflows any more
+    ref.step(16)
+    for f in FIELDS:
+        assert bits_equal(s.field(f), ref.field(f)), f
+
+
 @pytest.mark.parametrize("flags", [EAGER, EAGER | NO_PRETEST])
 def test_operator_by_operator_with_eager_list(gpu, flags):
     """op-by-op through apply!: the density pass records, the force pass replays; sums stay
