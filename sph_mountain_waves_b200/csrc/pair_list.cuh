@@ -203,8 +203,13 @@ __device__ __forceinline__ bool nl_q6_run(const uint32_t *__restrict__ xq, uint3
 }
 // REC (fused density pass only): phase 2 reads q from record A, and the particle's own records B
 // and C are written once its density, smoothing length and pressure are final
+#ifdef NL_BUILD_MIN_BLOCKS  // A/B builds (scripts/build_variant.sh)
+#define NL_BUILD_BOUNDS __launch_bounds__(NL_BLOCK, NL_BUILD_MIN_BLOCKS)
+#else
+#define NL_BUILD_BOUNDS __launch_bounds__(NL_BLOCK)
+#endif
 template <int DIM, class Op, int FILTER, bool REC = false>
-__global__ void __launch_bounds__(NL_BLOCK)
+__global__ void NL_BUILD_BOUNDS
 k_binary_build(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
                const uint32_t *__restrict__ cellx, const uint32_t *__restrict__ cell_start, int64_t n,
                int self, unsigned long long *pair_counter, ColFilter cf, PairList pl) {
@@ -356,8 +361,13 @@ __device__ __forceinline__ void nl_list_particle(int64_t p, const Fields &f, con
     nl_count_pairs(pair_counter, accepted);
 }
 
+#ifdef NL_LIST_MIN_BLOCKS  // A/B builds (scripts/build_variant.sh)
+#define NL_LIST_BOUNDS __launch_bounds__(NL_BLOCK, NL_LIST_MIN_BLOCKS)
+#else
+#define NL_LIST_BOUNDS __launch_bounds__(NL_BLOCK)
+#endif
 template <int DIM, class Op, bool REC = false>
-__global__ void __launch_bounds__(NL_BLOCK)
+__global__ void NL_LIST_BOUNDS
 k_binary_list(Fields f, Fields out, Params prm, Grid g, const uint32_t *__restrict__ key,
               const uint32_t *__restrict__ cellx, const uint32_t *__restrict__ cell_start, int64_t n,
               int self, unsigned long long *pair_counter, ColFilter cf, PairList pl) {
