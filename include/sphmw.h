@@ -355,7 +355,10 @@ int sphmw_comm_info(sphmw_ctx *ctx, int64_t out[6]);
  * open box every halo exchange gathers the indices all ranks dropped (one small all-gather) and
  * replays that loop on each rank, and sphmw_step uses the plain (non-overlapped) schedule.  Without
  * it (the default: walled configurations) a particle leaving the global box of a slab context is
- * dropped and counted (sphmw_comm_info out[4]), and an interior one fails the step loudly. */
+ * dropped and counted (sphmw_comm_info out[4]), and an interior one fails the step loudly.
+ * The open box also enables sphmw_step(ctx, "flow", n) on slabs: the inflow re-seeding of
+ * isothermal_flow_witch.jl:175-186 numbers the new particles in the reference's order across ranks
+ * (one all-gather of the converting indices per step). */
 int sphmw_comm_open_box(sphmw_ctx *ctx, int32_t on);
 /* global particle index of every resident particle (physical order) */
 int sphmw_set_index(sphmw_ctx *ctx, const int64_t *global_idx, int64_t n);

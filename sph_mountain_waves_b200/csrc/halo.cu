@@ -120,6 +120,12 @@ __global__ void k_halo_unpack(Fields f, uint32_t *__restrict__ idx, uint32_t *__
     f.s[S_TYPE][p] = rec[10];
     idx[p] = (uint32_t)rec[11];
     tag[p] = rec[12] == HALO_KIND_MIGRANT ? TAG_OWNED : TAG_GHOST;
+    // accumulators of the op-by-op schemes: the sender's move! / find_pressure! left them zero
+    // (isothermal_flow_witch.jl:157,205), the slot here may hold anything
+    if (f.s[S_DRHO]) f.s[S_DRHO][p] = 0.0;
+    if (f.s[S_DV0]) f.s[S_DV0][p] = 0.0;
+    if (f.s[S_DV1]) f.s[S_DV1][p] = 0.0;
+    if (DIM == 3 && f.s[S_DV2]) f.s[S_DV2][p] = 0.0;
 }
 
 static const int CARRIED[] = {S_X0, S_X1, S_X2, S_V0, S_V1, S_V2, S_M, S_H, S_RHO, S_RHO_P, S_TYPE};

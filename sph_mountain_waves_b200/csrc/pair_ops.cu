@@ -675,19 +675,11 @@ __global__ void k_flow_flag(Fields f, Params c, const uint32_t *__restrict__ idx
     flag_by_idx[idx[p]] = (f.s[S_TYPE][p] == c.inflow && f.s[S_X0][p] >= c.x_inflow) ? 1u : 0u;
 }
 
-// One thread per old particle; a converting particle creates its successor at index
-// n + (number of converting particles with a smaller index): the order of the reference's loop.
-// ADIABATIC: the constructor of src/legacy/adiabatic_flow_witch.jl:82-91 (T = T0, entropy from T and rho)
+// Particle(x - bc_width*VECX, U_max*VECX, INFLOW) of the flow drivers, built in slot s from the
+// converting particle p: isothermal_flow_witch.jl:72-82; ADIABATIC: adiabatic_flow_witch.jl:82-91
+// (T = T0, entropy from T and rho)
 template <int DIM, bool ADIABATIC>
-__global__ void k_flow_spawn(Fields f, Params c, uint32_t *__restrict__ idx,
-                             uint32_t *__restrict__ pos_of_idx, uint32_t *__restrict__ tag, int64_t n,
-                             const uint32_t *__restrict__ rank_by_idx) {
-    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    if (!(f.s[S_TYPE][p] == c.inflow && f.s[S_X0][p] >= c.x_inflow)) return;
-    f.s[S_TYPE][p] = c.fluid;
-    const int64_t s = n + rank_by_idx[idx[p]];
-    // Particle(x - bc_width*VECX, U_max*VECX, INFLOW), constructor :72-82
+__device__ __forceinline__ void flow_construct(const Fields &f, const Params &c, int64_t p, int64_t s) {
     const double y = f.s[S_X1][p] - c.bc_width * 0.0;
     f.s[S_X0][s] = f.s[S_X0][p] - c.bc_width * 1.0;
     f.s[S_X1][s] = y;
@@ -713,9 +705,79 @@ __global__ void k_flow_spawn(Fields f, Params c, uint32_t *__restrict__ idx,
         f.s[S_TH][s] = c.T_bg * pow((c.T_bg * c.R_gas * c.rho0) / P, c.R_gas / c.cp);
     }
     f.s[S_TYPE][s] = c.inflow;
+}
+
+// One thread per old particle; a converting particle creates its successor at index
+// n + (number of converting particles with a smaller index): the order of the reference's loop.
+template <int DIM, bool ADIABATIC>
+__global__ void k_flow_spawn(Fields f, Params c, uint32_t *__restrict__ idx,
+                             uint32_t *__restrict__ pos_of_idx, uint32_t *__restrict__ tag, int64_t n,
+                             const uint32_t *__restrict__ rank_by_idx) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    if (!(f.s[S_TYPE][p] == c.inflow && f.s[S_X0][p] >= c.x_inflow)) return;
+    f.s[S_TYPE][p] = c.fluid;
+    const int64_t s = n + rank_by_idx[idx[p]];
+    flow_construct<DIM, ADIABATIC>(f, c, p, s);
     idx[s] = (uint32_t)s;
     pos_of_idx[s] = (uint32_t)s;
     tag[s] = TAG_OWNED;
+}
+
+// ---- slab contexts (slab_comm.cu): the converting particles of ALL ranks are ranked by global
+// index on the host, so the device only collects them and later builds the successors it is told to
+template <int DIM>
+__global__ void k_flow_collect(Fields f, Params c, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ tag,
+                               int64_t n, uint32_t *__restrict__ list, uint32_t *__restrict__ pos, uint32_t cap) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n || tag[p] != TAG_OWNED) return;
+    if (!(f.s[S_TYPE][p] == c.inflow && f.s[S_X0][p] >= c.x_inflow)) return;
+    const uint32_t slot = atomicAdd(&list[0], 1u);
+    if (slot < cap) {
+        list[1 + slot] = idx[p];
+        pos[slot] = (uint32_t)p;
+    }
+}
+template <int DIM, bool ADIABATIC>
+__global__ void k_flow_spawn_list(Fields f, Params c, uint32_t *__restrict__ idx, uint32_t *__restrict__ tag, int64_t n,
+                                  const uint32_t *__restrict__ pos, const uint32_t *__restrict__ new_idx, int m) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const int64_t p = pos[k], s = n + k;
+    f.s[S_TYPE][p] = c.fluid;
+    flow_construct<DIM, ADIABATIC>(f, c, p, s);
+    idx[s] = new_idx[k];
+    tag[s] = TAG_OWNED;
+}
+// collect: list[0] = count, list[1..] = global indices, pos[k] = physical position (device arrays)
+int sphmw_flow_collect_slab(sphmw_ctx *c, uint32_t *list, uint32_t *pos, uint32_t cap) {
+    TRY(need_slots(c, SL(S_X0, S_V0, S_TYPE, S_RHO, S_M, S_P, S_TH), SL(S_X0, S_V0, S_TYPE, S_RHO, S_M, S_P, S_TH)));
+    CUDA_TRY(cudaMemsetAsync(list, 0, sizeof(uint32_t), c->stream));
+    if (c->n == 0) return SPHMW_OK;
+    TIMED(c, "flow.flag_inflow");
+    if (c->grid.dim == 2) k_flow_collect<2><<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->cur, c->prm, c->idx, c->tag, c->n, list, pos, cap);
+    else k_flow_collect<3><<<grid_for(c->n, 256), 256, 0, c->stream>>>(c->cur, c->prm, c->idx, c->tag, c->n, list, pos, cap);
+    CUDA_TRY(cudaGetLastError());
+    return SPHMW_OK;
+}
+// build m successors at the end of the resident set: pos[k] converts, its successor gets new_idx[k]
+int sphmw_flow_spawn_slab(sphmw_ctx *c, const uint32_t *pos, const uint32_t *new_idx, int m) {
+    if (m <= 0) return SPHMW_OK;
+    const int64_t n = c->n;
+    if (n + m > c->cap) {
+        sphmw_set_error("add_new_particles: %lld + %d particles exceed capacity %lld", (long long)n, m, (long long)c->cap);
+        return SPHMW_E_CAPACITY;
+    }
+    for (int s = 0; s < NSLOT; ++s)  // every other field of a new particle is the constructor's zero
+        if (c->allocated[s]) CUDA_TRY(cudaMemsetAsync(c->cur.s[s] + n, 0, sizeof(double) * m, c->stream));
+    TIMED(c, "flow.spawn_inflow");
+    if (c->grid.dim == 2) k_flow_spawn_list<2, false><<<grid_for(m, 128), 128, 0, c->stream>>>(c->cur, c->prm, c->idx, c->tag, n, pos, new_idx, m);
+    else k_flow_spawn_list<3, false><<<grid_for(m, 128), 128, 0, c->stream>>>(c->cur, c->prm, c->idx, c->tag, n, pos, new_idx, m);
+    CUDA_TRY(cudaGetLastError());
+    c->n = n + m;
+    c->n_owned += m;
+    c->cell_list_valid = false;
+    return SPHMW_OK;
 }
 
 int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added, bool adiabatic) {

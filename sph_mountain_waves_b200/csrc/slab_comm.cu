@@ -104,6 +104,9 @@ struct SlabComm {
     uint32_t *gather_dev = nullptr;  // world x (1 + SLAB_LOST_CAP) words
     uint32_t *gather_host = nullptr; // pinned
     long long *count_dev = nullptr;  // all-reduce scratch
+    uint32_t *conv_list = nullptr;   // inflow: [0] count, [1..] global indices of this rank's converting particles
+    uint32_t *conv_pos = nullptr;    // ... and their physical positions; then (pos, new index) pairs for the spawn
+    uint32_t *h_conv = nullptr;      // pinned scratch, 2 * SLAB_LOST_CAP words
     int64_t renumbered = 0;          // survivors that changed their index so far
 };
 
@@ -130,6 +133,9 @@ void sphmw_comm_free(sphmw_ctx *c) {
     if (m->gather_host) cudaFreeHost(m->gather_host);
     cudaFree(m->gather_dev);
     cudaFree(m->count_dev);
+    cudaFree(m->conv_list);
+    cudaFree(m->conv_pos);
+    if (m->h_conv) cudaFreeHost(m->h_conv);
     if (m->recv_event) cudaEventDestroy(m->recv_event);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -292,6 +298,9 @@ extern "C" int sphmw_comm_open_box(sphmw_ctx *c, int32_t on) {
         CUDA_TRY(cudaMalloc(&m->gather_dev, sizeof(uint32_t) * words));
         CUDA_TRY(cudaMallocHost(&m->gather_host, sizeof(uint32_t) * words));
         CUDA_TRY(cudaMalloc(&m->count_dev, sizeof(long long) * 2));
+        CUDA_TRY(cudaMalloc(&m->conv_list, sizeof(uint32_t) * (1 + SLAB_LOST_CAP)));
+        CUDA_TRY(cudaMalloc(&m->conv_pos, sizeof(uint32_t) * 2 * SLAB_LOST_CAP));
+        CUDA_TRY(cudaMallocHost(&m->h_conv, sizeof(uint32_t) * 2 * SLAB_LOST_CAP));
         CUDA_TRY(cudaMalloc(&c->lost_list, sizeof(uint32_t) * (1 + SLAB_LOST_CAP)));
         CUDA_TRY(cudaMemsetAsync(c->lost_list, 0, sizeof(uint32_t) * (1 + SLAB_LOST_CAP), c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -378,6 +387,51 @@ static int comm_renumber_lost(sphmw_ctx *c) {
     return SPHMW_OK;
 }
 
+// ≙ add_new_particles!(sys) (isothermal_flow_witch.jl:175-186) on a slab decomposition.  The
+// reference's loop runs over sys.particles in index order and appends one successor per converting
+// INFLOW particle, so successor k gets index N + k where k counts the converting particles of ALL
+// ranks with a smaller index: every rank contributes its list (one all-gather per step), the merged
+// list is sorted on every host, and each rank builds the successors of its own particles with the
+// indices that order gives them.
+static int comm_flow_spawn(sphmw_ctx *c) {
+    SlabComm *m = c->comm;
+    if (m->n_global < 0) TRY(comm_count_global(c));
+    const size_t block = 1 + SLAB_LOST_CAP;
+    TRY(sphmw_flow_collect_slab(c, m->conv_list, m->conv_pos, SLAB_LOST_CAP));
+    CUDA_TRY(cudaEventRecord(c->pack_event, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(m->stream, c->pack_event, 0));
+    NCCL_TRY(g_nccl.AllGather(m->conv_list, m->gather_dev, block, ncclUint32, m->comm, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(m->gather_host, m->gather_dev, sizeof(uint32_t) * block * m->world, cudaMemcpyDeviceToHost,
+                             m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    std::vector<uint32_t> all;
+    for (int r = 0; r < m->world; ++r) {
+        const uint32_t *b = m->gather_host + (size_t)r * block;
+        if (b[0] > SLAB_LOST_CAP) {
+            sphmw_set_error("inflow: rank %d converts %u particles in one step (at most %u are tracked)", r, b[0], SLAB_LOST_CAP);
+            return SPHMW_E_CAPACITY;
+        }
+        all.insert(all.end(), b + 1, b + 1 + b[0]);
+    }
+    if (all.empty()) return SPHMW_OK;
+    std::sort(all.begin(), all.end());
+    const uint32_t *mine = m->gather_host + (size_t)m->rank * block;
+    const int k = (int)mine[0];
+    if (k > 0) {
+        // my converting particles' positions stay on the device (conv_pos[0..k), in the order of my
+        // list); what the host adds are their successors' indices
+        for (int i = 0; i < k; ++i) {
+            const size_t rank_in_all = (size_t)(std::lower_bound(all.begin(), all.end(), mine[1 + i]) - all.begin());
+            m->h_conv[SLAB_LOST_CAP + i] = (uint32_t)(m->n_global + (int64_t)rank_in_all);
+        }
+        CUDA_TRY(cudaMemcpyAsync(m->conv_pos + SLAB_LOST_CAP, m->h_conv + SLAB_LOST_CAP, sizeof(uint32_t) * k,
+                                 cudaMemcpyHostToDevice, c->stream));
+        TRY(sphmw_flow_spawn_slab(c, m->conv_pos, m->conv_pos + SLAB_LOST_CAP, k));
+    }
+    m->n_global += (int64_t)all.size();
+    return SPHMW_OK;
+}
+
 static int comm_exchange_all(sphmw_ctx *c) {
     SlabComm *m = c->comm;
     if (m->open_box && m->n_global < 0) TRY(comm_count_global(c));
@@ -400,8 +454,27 @@ int sphmw_comm_create_cell_list(sphmw_ctx *c, int64_t *n_alive) {
 int sphmw_comm_step(sphmw_ctx *c, const char *scheme, int nsteps) {
     SlabComm *m = c->comm;
     const bool hopkins = !strcmp(scheme, "hopkins") || !strcmp(scheme, "hopkins_full");
+    if (!strcmp(scheme, "flow")) {
+        // isothermal_flow_witch.jl:221-232, operator by operator; inflow re-seeding and outflow by
+        // removal renumber particles across ranks: open box only
+        if (!m->open_box) {
+            sphmw_set_error("step: the flow scheme loses and gains particles; call sphmw_comm_open_box first");
+            return SPHMW_E_STATE;
+        }
+        for (int k = 0; k < nsteps; ++k) {
+            TRY(sphmw_apply_named(c, "flow.accelerate", 0));
+            TRY(sphmw_apply_named(c, "flow.move", 0));
+            TRY(comm_flow_spawn(c));
+            TRY(comm_exchange_all(c));
+            TRY(sphmw_build_cell_list(c, nullptr));
+            for (const char *op : {"flow.balance_of_mass", "flow.find_pressure", "flow.find_pot_temp", "flow.internal_force",
+                                   "flow.accelerate"})
+                TRY(sphmw_apply_named(c, op, 0));
+        }
+        return SPHMW_OK;
+    }
     if (strcmp(scheme, "wcsph") && !hopkins) {
-        sphmw_set_error("step: the fused 'wcsph', 'hopkins' and 'hopkins_full' schemes run on slabs");
+        sphmw_set_error("step: the fused 'wcsph', 'hopkins', 'hopkins_full' and the 'flow' schemes run on slabs");
         return SPHMW_E_UNSUPPORTED_OP;
     }
     if (nsteps <= 0) return SPHMW_OK;

@@ -476,6 +476,8 @@ int sphmw_materialize(sphmw_ctx *c, int slot);
 int64_t sphmw_list_ops(char *buf, int64_t cap);
 int sphmw_dump_pairs(sphmw_ctx *c, int64_t *pi, int64_t *pj, int64_t cap, int64_t *n);
 int sphmw_flow_add_particles(sphmw_ctx *c, int64_t *n_added, bool adiabatic);
+int sphmw_flow_collect_slab(sphmw_ctx *c, uint32_t *list, uint32_t *pos, uint32_t cap);  // slab contexts (slab_comm.cu)
+int sphmw_flow_spawn_slab(sphmw_ctx *c, const uint32_t *pos, const uint32_t *new_idx, int m);
 int sphmw_pair_list_stats(sphmw_ctx *c, int64_t out[4]);
 int sphmw_tile_stats(sphmw_ctx *c, int64_t out[6]);
 int sphmw_ensure_records(sphmw_ctx *c);  // api.cu: allocate the packed neighbour records

@@ -63,3 +63,19 @@ def test_open_box_removal_renumbers_like_the_reference(world):
            str(ROOT / "tests" / "mp" / "slab_open_box_worker.py"), "14", "0"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(ROOT))
     assert r.returncode == 0 and "SLAB_OPEN_BOX_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_flow_scheme_on_slabs_with_inflow_and_outflow(world):
+    """the constant-U flow driver on x-slabs: inflow re-seeding (new global indices in the reference's
+    order) and outflow by removal (swap-from-end renumbering), both across ranks, bitwise equal to the
+    whole-domain run (tests/mp/slab_flow_worker.py)"""
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 32500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           str(ROOT / "tests" / "mp" / "slab_flow_worker.py"), "40"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+    assert r.returncode == 0 and "SLAB_FLOW_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
