@@ -214,3 +214,72 @@ def test_fifty_steps_with_removal_against_numpy_restatement(make, nsteps):
     assert removed > 0 and len(o) == case.n - removed == len(ref["m"])
     for name in ("x", "v", "rho", "h", "m", "type"):
         assert rel_err(o.field(name), ref[name]) < 1e-9, name
+
+
+def numpy_aflow_step(f, p, h):
+    """one verlet_step! of src/legacy/adiabatic_flow_witch.jl:231-243 (without add_new_particles!, which
+    the device tests cover), written from the Julia source with k-d tree neighbours"""
+    FLUID = p["fluid"]
+    cv = p["cp"] - p["R_mass"]
+    gam = p["gamma"]
+    ey = np.array([0.0, 1.0, 0.0])
+    sn = np.sin(np.pi / 2 * (1 - (p["z_t"] - p["z_b"]) / p["z_b"]))
+
+    def accelerate():                                    # :225-229, damping_structure :210-216
+        fl = f["type"] == FLUID
+        damp = np.where(f["x"][:, 1] >= p["z_t"] - p["z_b"], p["gamma_r"] * sn ** 2, 0.0)
+        dv = 0.5 * p["dt"] * (f["Dv"] - p["g"] * ey[None, :] - damp[:, None] * ey[None, :])
+        f["v"] = np.where(fl[:, None], f["v"] + dv, f["v"])
+
+    accelerate()
+    fl = f["type"] == FLUID
+    f["Dv"] = np.zeros_like(f["Dv"])                     # move! :217-223
+    f["x"] = np.where(fl[:, None], f["x"] + p["dt"] * f["v"], f["x"])
+    f["rho"] = np.where(fl, 0.0, f["rho"])
+    n = len(f["m"])
+    i, j, d, r = neighbour_pairs(f["x"], h)
+    both = fl[i] & fl[j]
+    # find_density! with self = true (:159-163, :238): the particle itself contributes wendland2(h, 0)
+    rho_sum = np.bincount(i[both], weights=(f["m"][j] * wendland2(h, r))[both], minlength=n)
+    f["rho"] = f["rho"] + rho_sum + np.where(fl, f["m"] * wendland2(h, 0.0), 0.0)
+    f["s"] = np.where(fl, f["S"] * f["rho"] / f["m"], f["s"])                        # find_s! :165-169
+    with np.errstate(all="ignore"):
+        T = f["rho"] ** (gam - 1.0) * np.exp(f["s"] / (f["rho"] * cv)) / (cv * (gam - 1.0))   # find_pressure! :171-176
+    f["T"] = np.where(fl, T, f["T"])
+    f["P"] = np.where(fl, p["R_mass"] * f["rho"] * f["T"], f["P"])
+    ker = rDwendland2(h, r)
+    u = f["v"][i] - f["v"][j]
+    dot = (u * d).sum(-1)
+    # entropy_production! :184-191
+    dS = -4.0 * f["m"][i] * f["m"][j] * ker * p["mu"] / (f["T"][i] * f["rho"][i] * f["rho"][j]) * dot ** 2 \
+        / (r * r + 0.01 * h * h) * p["dt"]
+    f["S"] = f["S"] + np.bincount(i[both], weights=dS[both], minlength=n)
+    # internal_force! :146-153
+    kq = f["m"][j] * ker
+    a1 = -kq * (f["P"][i] / f["rho"][i] ** 2 + f["P"][j] / f["rho"][j] ** 2)
+    a2 = 8.0 * kq * p["mu"] / (f["rho"][i] * f["rho"][j]) * dot / (r * r + 0.01 * h * h)
+    Dv = np.zeros_like(f["Dv"])
+    for a in range(3):
+        Dv[:, a] = np.bincount(i, weights=(a1 + a2) * d[:, a], minlength=n)
+    f["Dv"] = Dv
+    accelerate()
+
+
+def test_adiabatic_flow_steps_against_numpy_restatement():
+    """the oracle's adiabatic flow closures (find_density! with self, find_s!, find_pressure!,
+    entropy_production!, internal_force!, move!, accelerate!) against an independent numpy restatement
+    over three steps"""
+    case = cases.aflow_2d(n_y=16.0, dom_length=24e3, h_m=4e3, a=4e3, U_max=40.0)
+    o = load_oracle(case)
+    assert o.create_cell_list() == case.n
+    f = {k: np.array(v, dtype=np.float64, copy=True) for k, v in case.fields.items()}
+    for op in ("aflow.find_density", "aflow.find_pressure", "aflow.find_pot_temp", "aflow.find_s", "flow.internal_force"):
+        o.apply(op)                                      # what closes make_system(), :121-126
+    for name in ("rho", "T", "P", "s", "Dv"):
+        f[name] = o.field(name).copy()                   # start both from that state
+    for step in range(3):
+        # no INFLOW particle converts in this case (they do not move, :219): the step is the closures
+        o.step("aflow", 1)
+        numpy_aflow_step(f, case.params, case.h)
+        for name in ("x", "v", "rho", "s", "T", "P", "S", "Dv"):
+            assert rel_err(f[name], o.field(name)) <= 1e-11, (step, name)
