@@ -70,13 +70,13 @@ typedef struct sphmw_config {
 #define SPHMW_FLAG_FAST_MATH 1
 #define SPHMW_FLAG_CELL_PAIRS 2
 /* Pair list (no reference equivalent; results are unchanged bit for bit).  By default the first
- * binary pass after a create_cell_list! records each particle's candidates in traversal order
+ * binary pass after a create_cell_list! records each particle's accepted neighbours in traversal order
  * when the previous cell list saw two or more binary passes (always inside the fused "wcsph"
  * step), and later passes on the same cell list read that list instead of walking the 9/27
  * neighbour cells again.  NO_PAIR_LIST: always walk the cells.  PAIR_LIST_EAGER: record on the
  * first pass of every cell list.  NO_PRETEST: the recording pass tests candidates in FP64 only
- * (default: conservative integer pre-test on a 10-bit-per-axis mirror of each particle's position
- * inside its cell, exact FP64 test for the survivors). */
+ * (default: conservative integer pre-test on a 6-bit mirror of each particle's position inside its
+ * cell — one packed add and one DP4A per candidate —, exact FP64 test for the survivors). */
 #define SPHMW_FLAG_NO_PAIR_LIST 4
 #define SPHMW_FLAG_PAIR_LIST_EAGER 8
 #define SPHMW_FLAG_NO_PRETEST 16

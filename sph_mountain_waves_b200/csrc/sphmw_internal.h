@@ -183,18 +183,18 @@ __host__ __device__ __forceinline__ bool col_selected(const ColFilter &cf, int i
 // ---------------------------------------------------------------------------
 // Neighbour ("pair") list of one cell-list generation.  The first binary pass after a
 // create_cell_list! walks the 9/27 neighbour cells once and records, per particle and in the
-// reference's traversal order (core.jl:94-112), the candidates that passed a CONSERVATIVE
-// cut-off test; every later pass on the same cell list (the force pass of verlet_step!,
-// wcsph_perturbed_witch.jl:330) reads that list instead of walking ~157 candidates again and
-// repeats only the exact FP64 test `r > sys.h` (core.jl:104-105).  Order and accepted set are
-// unchanged, so every sum keeps its bits.
+// reference's traversal order (core.jl:94-112), the ACCEPTED neighbours (r <= h, the particle itself
+// left out: core.jl:105); every later pass on the same cell list (the force pass of verlet_step!,
+// wcsph_perturbed_witch.jl:330) reads that list instead of walking ~157 candidates again.  Order and
+// accepted set are unchanged, so every sum keeps its bits.
 // Layout: entry k of particle p is list[((p >> 5) * stride + k) * 32 + (p & 31)] — the 32
 // particles of a warp interleaved, so a warp reads/writes one 128-byte line per k.
 // ---------------------------------------------------------------------------
 #define NL_NONE 0xFFFFFFFFu  // cnt value: no list for this particle (walk the cells)
 #define NL_BLOCK 128
 #define NL_QUEUE_SLACK 4  // room in the recording pass's queue is checked once per four slots: the last four rows are slack
-// Pre-test of the recording pass on the quantised mirror.  A position is cell + (q + e)/1024 with
+// ---- 10-bit mirror of the x-chunked cell order (shared-memory tile variant, pair_tile.cuh) ----------
+// Pre-test of its recording pass on the quantised mirror.  A position is cell + (q + e)/1024 with
 // e in [0,1) per axis, so for a pair with r <= h the integer differences d_a (in h/1024, cell
 // offsets included) satisfy |d_a| < |t_a| + 1 with sum t_a^2 <= 1024^2, hence
 // sum d_a^2 < (1024 + sqrt(3))^2.  1.74 > sqrt(3) leaves room for the rounding of x/h (1e-13).
@@ -301,8 +301,9 @@ struct PairList {
     uint32_t *list16;  // tiled kernels (pair_tile.cuh): 16-bit tile slots, two per word
     uint32_t *cnt;
     NbRec *recA, *recB, *recC;  // null unless SPHMW_FLAG_PACKED_RECORDS
-    // 10-bit-per-axis mirror: the position inside its own cell in units of h/1024, x | y<<10 | z<<20
-    // (rebuilt by every cell-list build, cell_list.cu)
+    // quantised mirror of the positions, rebuilt by every cell-list build (cell_gather.cuh): the 6-bit
+    // word of the zrun cell order (nl_q6_word above), or — x-chunked order, tile variant — 10 bits per
+    // axis inside the particle's own cell, x | y<<10 | z<<20
     const uint32_t *xq;
     int stride;
     int qrows;  // rows of the recording pass's shared-memory queue (survivors of the pre-test + NL_QUEUE_SLACK)
