@@ -235,6 +235,12 @@ int sphmw_pretest_pairs(const double *xp, const double *xq, int64_t n, double h,
 int sphmw_pretest_pairs_q6(const double *xp, const double *xq, int64_t n, double h, int32_t dim,
                            uint8_t *pass);
 int sphmw_slab_column_sets(int32_t width, int32_t has_left, int32_t has_right, int32_t out[16]);
+/* sphmw_swap_removal_moves: the removal loop of create_cell_list! (src/core.jl:72-81) on index space —
+ * `removed` (k distinct 0-based indices, any order) leave an array of n; out: the survivors whose index
+ * changes, old -> new (at most k of them; arrays of k entries suffice).  What the cell-list build and
+ * the open box of the slab transport replay. */
+int sphmw_swap_removal_moves(int64_t n, const int64_t *removed, int64_t k, int64_t *old_index,
+                             int64_t *new_index, int64_t *n_moves);
 
 /* ≙ avg_velocity / max_velocity / length(sys.particles)
  * (wcsph_perturbed_witch.jl:338-350,377).  what: "avg_speed" | "max_speed" |

@@ -84,6 +84,7 @@ _SIGS = {
     "sphmw_count_pairs": (C.c_int, [_P, C.c_int32]),
     "sphmw_pair_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "sphmw_pretest_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int32, C.c_void_p]),
+    "sphmw_swap_removal_moves": (C.c_int, [C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "sphmw_pretest_pairs_q6": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int32, C.c_void_p]),
     "sphmw_slab_column_sets": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "sphmw_pair_list_info": (C.c_int, [_P, C.POINTER(C.c_int64)]),

@@ -784,6 +784,24 @@ extern "C" int sphmw_pretest_pairs_q6(const double *xp, const double *xq, int64_
     }
     return SPHMW_OK;
 }
+// core.jl:72-81 replayed on index space (cell_list.cu sphmw_replay_swap_removal: what the whole-domain
+// cell-list build and the open box of the slab transport both use): which survivors change their index
+extern "C" int sphmw_swap_removal_moves(int64_t n, const int64_t *removed, int64_t k, int64_t *old_index,
+                                        int64_t *new_index, int64_t *n_moves) {
+    if (n < 0 || k < 0 || k > n || (k > 0 && !removed) || !n_moves) return SPHMW_E_INVALID;
+    std::vector<uint32_t> rem(k), mo, mn;
+    for (int64_t i = 0; i < k; ++i) {
+        if (removed[i] < 0 || removed[i] >= n) return SPHMW_E_INVALID;
+        rem[i] = (uint32_t)removed[i];
+    }
+    sphmw_replay_swap_removal(n, rem, mo, mn);
+    *n_moves = (int64_t)mo.size();
+    for (size_t i = 0; i < mo.size() && old_index && new_index; ++i) {
+        old_index[i] = mo[i];
+        new_index[i] = mn[i];
+    }
+    return SPHMW_OK;
+}
 extern "C" int sphmw_slab_column_sets(int32_t width, int32_t has_left, int32_t has_right, int32_t out[16]) {
     if (!out || width < 2 * GHOST_COLS + 2 * GHOST_COLS) return SPHMW_E_INVALID;
     const SlabCols sc = sphmw_slab_cols_of(width, has_left != 0, has_right != 0);

@@ -130,3 +130,45 @@ def test_slab_column_sets(width, has_left, has_right):
 def test_slab_column_sets_reject_too_narrow():
     out = (C.c_int32 * 16)()
     assert _capi.lib().sphmw_slab_column_sets(7, 1, 1, out) < 0
+
+
+def reference_removal(n, removed):
+    """create_cell_list! on a vector of labels (src/core.jl:60-81): the removal cell holds the indices in
+    DESCENDING order (add_index!, core.jl:26-41), entry i is overwritten by particles[end+1-i], then the
+    vector is cut"""
+    particles = list(range(n))
+    rem = sorted(removed, reverse=True)
+    for i, r in enumerate(rem, start=1):
+        particles[r] = particles[n - i]
+    return particles[: n - len(rem)]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_swap_from_end_removal_moves(seed):
+    """the index moves the library derives (host replay over a sparse map, csrc/cell_list.cu) against the
+    reference's loop executed literally: also when removed particles sit in the tail that is swapped in"""
+    rng = np.random.default_rng(seed)
+    for n, k in ((1, 1), (2, 1), (10, 10), (50, 7), (1000, 1), (1000, 333), (5000, 4999)):
+        removed = rng.choice(n, size=k, replace=False).astype(np.int64)
+        if seed % 2:  # crowd the tail: the swapped-in particles are themselves removed ones
+            removed = np.unique(np.concatenate([removed[: k // 2], np.arange(n - (k - k // 2), n)])).astype(np.int64)
+            k = len(removed)
+        old = np.empty(k, dtype=np.int64)
+        new = np.empty(k, dtype=np.int64)
+        m = C.c_int64()
+        rc = _capi.lib().sphmw_swap_removal_moves(n, _capi.ptr(removed), k, _capi.ptr(old), _capi.ptr(new), C.byref(m))
+        assert rc == 0 and 0 <= m.value <= k
+        want = reference_removal(n, removed.tolist())
+        got = np.arange(n)                       # label at each slot
+        alive = np.ones(n, dtype=bool)
+        alive[removed] = False
+        label_at = {}                            # new slot -> label
+        moved_from = set(old[: m.value].tolist())
+        for o, w in zip(old[: m.value].tolist(), new[: m.value].tolist()):
+            assert alive[o] and w < n - k
+            label_at[w] = o
+        for slot in range(n - k):
+            if slot in label_at:
+                assert want[slot] == label_at[slot]
+            else:
+                assert alive[slot] and slot not in moved_from and want[slot] == slot
